@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""
+Generate the golden vectors under tests/golden/ by running the reference's OWN code
+(/root/reference, through oracle/refrun.py: lexical py2->py3 + a weave.inline shim that compiles
+the reference's C++ loop bodies with g++).  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Inputs are seeded and stored next to the outputs, so the parity tests never depend on a RNG
+stream.  The SciPy PCG (scipy.sparse.linalg.cg, SciPy %(scipy)s on this box) drives the
+reference operators exactly as src/test_BD_precond_onto_real_data.py:47 and
+tests/test_2level_preconditioner.py:52 do.
+"""
+import os
+import sys
+
+import numpy as np
+import scipy
+import scipy.sparse.linalg as spla
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import refrun  # noqa: E402
+
+R = refrun.load_reference()
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print("wrote %s (%.1f kB)" % (path, os.path.getsize(path) / 1e3))
+
+
+def make_scan(rng, nt=2400, npix_main=60, npix_old=70, flag_frac=0.03):
+    """Random pointing with flags plus a few pathological pixels (few hits / degenerate angles)."""
+    pix = rng.integers(0, npix_main, size=nt).astype(np.int64)
+    phi = R.angles_gen(float(rng.uniform(0, np.pi)), nt)
+    k = nt - 20
+    pix[k] = 60                               # 1 hit
+    pix[k + 1:k + 3] = 61                     # 2 hits
+    pix[k + 3:k + 6] = 62                     # 3 hits, identical angle -> singular 2x2 block
+    phi[k + 3:k + 6] = phi[k + 3]
+    pix[k + 6:k + 9] = 63                     # 3 hits, distinct angles
+    pix[k + 9:k + 15] = 64                    # 6 hits, nearly identical angles -> cond > 1e3
+    phi[k + 9:k + 15] = phi[k + 9] + 1e-4 * np.arange(6)
+    flags = rng.random(nt) < flag_frac
+    flags[k:] = False
+    pix[flags] = -1
+    return pix, phi, npix_old
+
+
+def case_process_and_pointing():
+    for pol in (1, 2, 3):
+        for weighted in (False, True):
+            rng = np.random.default_rng(100 + 10 * pol + int(weighted))
+            pix0, phi, npix_old = make_scan(rng)
+            nt = len(pix0)
+            nb = 6
+            tdiag = rng.random(nb) + 0.5
+            w = None
+            if weighted:
+                N = R.BlockLO(nt // nb, tdiag, offdiag=False)
+                w = N.diag.copy()
+            pix = pix0.copy()
+            pts = R.ProcessTimeSamples(pix, npix_old, pol=pol, phi=phi, w=w)
+            npix, obspix = pts.get_new_pixel
+            P = R.SparseLO(npix, nt, pix, pol=pol, angle_processed=pts)
+            x = rng.standard_normal(pol * npix)
+            d = rng.standard_normal(nt)
+            Mbd = R.BlockDiagonalPreconditionerLO(pts, npix, pol=pol)
+            Bd = R.BlockDiagonalLO(pts, npix, pol=pol)
+            out = dict(pix_in=pix0, phi=phi, npix_old=npix_old, pol=pol, tdiag=tdiag,
+                       weighted=weighted, w=(w if w is not None else np.zeros(0)),
+                       pix_out=pix, npix_new=npix, obspix=np.asarray(obspix),
+                       old2new=np.asarray(pts.old2new), mask=np.asarray(pts.mask),
+                       x=x, d=d, Px=P * x, Ptd=P.T * d, PtPx=P.T * (P * x),
+                       Mbd_x=Mbd * x, Bd_x=Bd * x)
+            for nm in ("counts", "cosine", "sine", "cos2", "sin2", "sincos", "cos", "sin"):
+                if hasattr(pts, nm):
+                    out["pts_" + nm] = np.asarray(getattr(pts, nm))
+            if weighted:
+                out["PtNPx"] = P.T * (N * (P * x))
+            save("pointing_pol%d_%s" % (pol, "w" if weighted else "u"), **out)
+
+
+def case_obspix2():
+    """The SetObspix / compute_arrays path (process_ces.py:80-83, 94-189)."""
+    for pol in (1, 3):
+        rng = np.random.default_rng(300 + pol)
+        nt, npix_old = 1500, 40
+        pix0 = rng.integers(0, npix_old, size=nt).astype(np.int64)
+        pix0[rng.random(nt) < 0.05] = -1
+        phi = R.angles_gen(0.3, nt)
+        obspix = np.arange(1000, 1000 + npix_old, dtype=np.int64)
+        obspix2 = obspix[3:31].copy()
+        pix = pix0.copy()
+        pts = R.ProcessTimeSamples(pix, npix_old, obspix=obspix.copy(), pol=pol, phi=phi,
+                                   obspix2=obspix2)
+        npix, op = pts.get_new_pixel
+        out = dict(pix_in=pix0, phi=phi, npix_old=npix_old, pol=pol, obspix=obspix,
+                   obspix2=obspix2, pix_out=pix, npix_new=npix, obspix_out=np.asarray(op),
+                   old2new=np.asarray(pts.old2new))
+        for nm in ("counts", "cosine", "sine", "cos2", "sin2", "sincos"):
+            if hasattr(pts, nm):
+                out["pts_" + nm] = np.asarray(getattr(pts, nm))
+        save("obspix2_pol%d" % pol, **out)
+
+
+def case_toeplitz():
+    rng = np.random.default_rng(7)
+    out = {}
+    n = 257
+    v = rng.standard_normal(n)
+    out["v"] = v
+    for L in (1, 2, 5, 17, 64):
+        a = rng.random(L)
+        a[0] += 2.0
+        T = R.ToeplitzLO(a, n)
+        out["a%d" % L] = a
+        out["y%d" % L] = T * v
+    nb, bs = 4, 300
+    t = [rng.random(3) + np.array([2., 0, 0]) for _ in range(nb)]
+    N = R.BlockLO(bs, t, offdiag=True)
+    vv = rng.standard_normal(nb * bs)
+    out["blk_t"] = np.array(t)
+    out["blk_v"] = vv
+    out["blk_y"] = N * vv
+    out["blk_diag"] = np.asarray(N.diag)
+    tw = rng.random(nb) + 0.5
+    Nw = R.BlockLO(bs, tw, offdiag=False)
+    out["white_t"] = tw
+    out["white_y"] = Nw * vv
+    out["white_diag"] = np.asarray(Nw.diag)
+    W = R.WeightingLO([2, 3], [100, 200], rng.random(5))
+    dd = rng.standard_normal(W.size)
+    out["wt_weights"] = np.asarray(W.weights)
+    out["wt_d"] = dd
+    out["wt_y"] = W * dd.copy()
+    save("noise_ops", **out)
+
+
+def make_subscans(rng, ns, nsub, gap=7):
+    """Subscan (lengths, starts) inside [0, ns) with gaps; trailing samples left outside."""
+    edges = np.sort(rng.choice(np.arange(gap, ns - gap), size=nsub - 1, replace=False))
+    starts = np.concatenate([[3], edges + gap])
+    ends = np.concatenate([edges, [ns - 5]])
+    keep = ends > starts
+    return (ends - starts)[keep].astype(np.int64), starts[keep].astype(np.int64)
+
+
+def case_filter():
+    rng = np.random.default_rng(11)
+    nsamples = [400, 300]
+    nbolos = [3, 2]
+    subs, tst = [], []
+    for ns in nsamples:
+        L, S = make_subscans(rng, ns, 6)
+        subs.append(L)
+        tst.append(S)
+    nt = sum(a * b for a, b in zip(nsamples, nbolos))
+    npix = 30
+    pix = rng.integers(0, npix, size=nt).astype(np.int64)
+    pix[rng.random(nt) < 0.1] = -1
+    # one fully flagged subscan: detector 1 of CES 0, subscan 2
+    s0 = nsamples[0] * 1 + tst[0][2]
+    pix[s0:s0 + subs[0][2]] = -1
+    d = rng.standard_normal(nt) + 3.0
+    F = R.FilterLO(nt, [subs, tst], nsamples, nbolos, pix)
+    out = dict(nsamples=np.array(nsamples), nbolos=np.array(nbolos), pix=pix, d=d, Fd=F * d, npix=npix)
+    for i in range(2):
+        out["sub_len%d" % i] = subs[i]
+        out["sub_start%d" % i] = tst[i]
+    # single-CES scalar form of the ctor (linearoperators.py:269-273)
+    F1 = R.FilterLO(nsamples[0] * nbolos[0], [subs[0], tst[0]], nsamples[0], nbolos[0],
+                    pix[:nsamples[0] * nbolos[0]])
+    out["Fd_single"] = F1 * d[:nsamples[0] * nbolos[0]]
+    # A = P^T F P through the reference operators, pol 1 and 3
+    for pol in (1, 3):
+        phi = R.angles_gen(0.7, nt)
+        pp = pix.copy()
+        pts = R.ProcessTimeSamples(pp, npix, pol=pol, phi=phi)
+        npn = pts.get_new_pixel[0]
+        P = R.SparseLO(npn, nt, pp, pol=pol, angle_processed=pts)
+        Fp = R.FilterLO(nt, [subs, tst], nsamples, nbolos, P.pairs)
+        x = rng.standard_normal(pol * npn)
+        out["phi"] = phi
+        out["A_x_pol%d" % pol] = x
+        out["A_y_pol%d" % pol] = P.T * (Fp * (P * x))
+        out["A_pix_pol%d" % pol] = pp
+        out["A_npix_pol%d" % pol] = npn
+    save("filter_ops", **out)
+
+
+def case_pcg_and_deflation():
+    """PCG with Toeplitz noise + M_BD; ARPACK deflation space; CoarseLO / DeflationLO / M2;
+    in-tree arnoldi (tests/test_2level_preconditioner.py, tests/test_coarse_operator.py)."""
+    for pol in (1, 2, 3):
+        rng = np.random.default_rng(500 + pol)
+        nt, npix_old, nb = 6000, 48, 4
+        pix0 = rng.integers(0, npix_old, size=nt).astype(np.int64)
+        pix0[rng.random(nt) < 0.02] = -1
+        phi = R.angles_gen(float(rng.uniform(0, np.pi)), nt)
+        d = rng.random(nt)
+        t = [np.array([1.0 + rng.random(), -0.3 * rng.random(), 0.1 * rng.random()]) for _ in range(nb)]
+        N = R.BlockLO(nt // nb, t, offdiag=True)
+        pix = pix0.copy()
+        pts = R.ProcessTimeSamples(pix, npix_old, pol=pol, phi=phi)
+        npix = pts.get_new_pixel[0]
+        P = R.SparseLO(npix, nt, pix, pol=pol, angle_processed=pts)
+        Mbd = R.BlockDiagonalPreconditionerLO(pts, npix, pol=pol)
+        B = R.BlockDiagonalLO(pts, npix, pol=pol)
+        A = P.T * N * P
+        b = P.T * N * d
+        n = pol * npix
+        # --- PCG, M_BD
+        hist = []
+        xs = []
+
+        def cb(xk):
+            xs.append(xk.copy())
+            hist.append(np.linalg.norm(b - A * xk))
+        x, info = spla.cg(A, b, x0=np.zeros(n), M=Mbd, rtol=1e-8, maxiter=200, callback=cb)
+        out = dict(pix_in=pix0, phi=phi, d=d, t=np.array(t), nb=nb, npix_old=npix_old, pol=pol,
+                   npix=npix, b=b, cg_x=x, cg_info=info, cg_iters=len(hist), cg_hist=np.array(hist))
+        # --- deflation space through ARPACK exactly as tests/test_2level_preconditioner.py:33
+        x0 = np.ones(n)
+        eigv, Z = spla.eigsh(A, M=B, Minv=Mbd, k=5, v0=x0, which="SM", ncv=15, tol=1e-10)
+        r = Z.shape[1]
+        Az = Z * 0.
+        for i in range(r):
+            Az[:, i] = A * Z[:, i]
+        E_lu = R.CoarseLO(Z, Az, r)
+        E_eig = R.CoarseLO(Z, Az, r, apply="eig")
+        Zd = R.DeflationLO(Z)
+        AZd = R.DeflationLO(Az)
+        v_r = rng.standard_normal(r)
+        v_n = rng.standard_normal(n)
+        I = R.lp.IdentityOperator(n)
+        Rop = I - AZd * E_eig * Zd.T
+        M2 = Mbd * Rop + Zd * E_eig * Zd.T
+        out.update(eigv=eigv, Z=Z, Az=Az, v_r=v_r, v_n=v_n, E=R.dgemm(Z, Az.T),
+                   Elu_v=E_lu * v_r, Eeig_v=E_eig * v_r, Zd_v=Zd * v_r, ZdT_v=Zd.T * v_n,
+                   M2_v=M2 * v_n, R_v=Rop * v_n)
+        hist2 = []
+        x2, info2 = spla.cg(A, b, x0=np.zeros(n), M=M2, rtol=1e-8, maxiter=200,
+                            callback=lambda xk: hist2.append(np.linalg.norm(b - A * xk)))
+        out.update(cg2_x=x2, cg2_info=info2, cg2_iters=len(hist2), cg2_hist=np.array(hist2))
+        # --- in-tree Arnoldi on Mbd*A (src/test_M2_precond_onto_real_data.py:42-44)
+        # tol=1e-3 terminates through the reference's element-wise stop test (deflationlib.py:101);
+        # tol=1e-5 runs into inner_m and raises (deflationlib.py:111-112) -- both are recorded.
+        vs, hs, m = R.arnoldi(Mbd * A, Mbd * b, x0=np.ones(n), tol=1e-3, inner_m=n - 1)
+        H = R.build_hess(hs, m)
+        try:
+            R.arnoldi(Mbd * A, Mbd * b, x0=np.ones(n), tol=1e-5, inner_m=n - 1)
+            raised = 0
+        except RuntimeError:
+            raised = 1
+        out.update(arn_m=m, arn_V=np.array(vs), arn_H=H, arn_raises_tol1em5=raised)
+        save("solve_pol%d" % pol, **out)
+
+
+if __name__ == "__main__":
+    print("scipy", scipy.__version__, "numpy", np.__version__)
+    case_process_and_pointing()
+    case_obspix2()
+    case_toeplitz()
+    case_filter()
+    case_pcg_and_deflation()

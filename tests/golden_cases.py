@@ -1,0 +1,211 @@
+"""
+Shared golden-vector recipes.  Every function takes ``impl`` -- a namespace exposing the
+reference's operator surface (the oracle, or the CUDA product) -- replays the recipe that
+tests/golden/make_golden.py ran on the reference's own code, and compares with the stored
+outputs.  Bars (BASELINE.json north_star): pixel indices / hit counts / masks bit-exact,
+floating point within ``RTOL`` = 1e-10 relative (scaled by the vector's max magnitude).
+"""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-10
+
+
+def load(name):
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def close(a, b, rtol=RTOL, what=""):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, "%s: shape %s vs %s" % (what, a.shape, b.shape)
+    scale = max(np.max(np.abs(b)) if b.size else 0.0, 1e-300)
+    err = np.max(np.abs(a - b)) / scale if b.size else 0.0
+    assert err <= rtol, "%s: rel err %.3e > %.1e" % (what, err, rtol)
+
+
+def exact(a, b, what=""):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape and np.array_equal(a, b), "%s: integer mismatch" % what
+
+
+def check_pointing(impl, name):
+    g = load(name)
+    pol = int(g["pol"])
+    pix = g["pix_in"].copy()
+    w = g["w"] if bool(g["weighted"]) else None
+    pts = impl.ProcessTimeSamples(pix, int(g["npix_old"]), pol=pol, phi=g["phi"], w=w)
+    npix, obspix = pts.get_new_pixel
+    assert npix == int(g["npix_new"])
+    exact(pix, g["pix_out"], "relabelled pixs (in place)")
+    exact(np.asarray(pts.old2new), g["old2new"], "old2new")
+    exact(np.asarray(pts.mask), g["mask"], "mask")
+    exact(np.asarray(obspix), g["obspix"], "obspix")
+    for nm in ("counts", "cosine", "sine", "cos2", "sin2", "sincos", "cos", "sin"):
+        if "pts_" + nm in g:
+            close(getattr(pts, nm), g["pts_" + nm], what="pts." + nm)
+    if not bool(g["weighted"]) and pol in (1, 3):
+        exact(np.asarray(pts.counts).astype(np.int64), g["pts_counts"].astype(np.int64), "hit counts")
+    nt = len(pix)
+    P = impl.SparseLO(npix, nt, pix, pol=pol, angle_processed=pts)
+    assert P.shape == (nt, pol * npix)
+    close(P * g["x"], g["Px"], what="P x")
+    close(P.T * g["d"], g["Ptd"], what="P^T d")
+    close(P.T * (P * g["x"]), g["PtPx"], what="P^T P x")
+    Mbd = impl.BlockDiagonalPreconditionerLO(pts, npix, pol=pol)
+    Bd = impl.BlockDiagonalLO(pts, npix, pol=pol)
+    close(Mbd * g["x"], g["Mbd_x"], what="M_BD x")
+    close(Bd * g["x"], g["Bd_x"], what="BlockDiagonalLO x")
+    if bool(g["weighted"]):
+        N = impl.BlockLO(nt // len(g["tdiag"]), g["tdiag"], offdiag=False)
+        close(N.diag, g["w"], what="N.diag")
+        close(P.T * (N * (P * g["x"])), g["PtNPx"], what="P^T N P x (unfused)")
+        close((P.T * N * P) * g["x"], g["PtNPx"], what="P^T N P x (composed)")
+
+
+def check_obspix2(impl, name):
+    g = load(name)
+    pol = int(g["pol"])
+    pix = g["pix_in"].copy()
+    pts = impl.ProcessTimeSamples(pix, int(g["npix_old"]), obspix=g["obspix"].copy(), pol=pol,
+                                  phi=g["phi"], obspix2=g["obspix2"].copy())
+    npix, op = pts.get_new_pixel
+    assert npix == int(g["npix_new"])
+    exact(pix, g["pix_out"], "relabelled pixs")
+    exact(np.asarray(pts.old2new), g["old2new"], "old2new")
+    exact(np.asarray(op), g["obspix_out"], "obspix")
+    for nm in ("counts", "cosine", "sine", "cos2", "sin2", "sincos"):
+        if "pts_" + nm in g:
+            close(getattr(pts, nm), g["pts_" + nm], what="pts." + nm)
+
+
+def check_noise_ops(impl):
+    g = load("noise_ops")
+    n = len(g["v"])
+    for L in (1, 2, 5, 17, 64):
+        T = impl.ToeplitzLO(g["a%d" % L], n)
+        close(T * g["v"], g["y%d" % L], what="Toeplitz L=%d" % L)
+    nb = g["blk_t"].shape[0]
+    bs = len(g["blk_v"]) // nb
+    N = impl.BlockLO(bs, [g["blk_t"][i] for i in range(nb)], offdiag=True)
+    close(N * g["blk_v"], g["blk_y"], what="BlockLO offdiag")
+    close(N.diag, g["blk_diag"], what="BlockLO offdiag .diag")
+    Nw = impl.BlockLO(bs, g["white_t"], offdiag=False)
+    close(Nw * g["blk_v"], g["white_y"], what="BlockLO white")
+    close(Nw.diag, g["white_diag"], what="BlockLO white .diag")
+    W = impl.WeightingLO([2, 3], [100, 200], g["wt_weights"])
+    d = g["wt_d"].copy()
+    y = W * d
+    close(y, g["wt_y"], what="WeightingLO")
+
+
+def check_filter_ops(impl):
+    g = load("filter_ops")
+    nsamples = [int(i) for i in g["nsamples"]]
+    nbolos = [int(i) for i in g["nbolos"]]
+    subs = [g["sub_len0"], g["sub_len1"]]
+    tst = [g["sub_start0"], g["sub_start1"]]
+    nt = len(g["d"])
+    F = impl.FilterLO(nt, [subs, tst], nsamples, nbolos, g["pix"].copy())
+    close(F * g["d"], g["Fd"], what="FilterLO d")
+    n0 = nsamples[0] * nbolos[0]
+    F1 = impl.FilterLO(n0, [subs[0], tst[0]], nsamples[0], nbolos[0], g["pix"][:n0].copy())
+    close(F1 * g["d"][:n0], g["Fd_single"], what="FilterLO single CES")
+    for pol in (1, 3):
+        pix = g["pix"].copy()
+        pts = impl.ProcessTimeSamples(pix, int(g["npix"]), pol=pol, phi=g["phi"])
+        npn = pts.get_new_pixel[0]
+        assert npn == int(g["A_npix_pol%d" % pol])
+        exact(pix, g["A_pix_pol%d" % pol], "pix")
+        P = impl.SparseLO(npn, nt, pix, pol=pol, angle_processed=pts)
+        Fp = impl.FilterLO(nt, [subs, tst], nsamples, nbolos, P.pairs)
+        x = g["A_x_pol%d" % pol]
+        close(P.T * (Fp * (P * x)), g["A_y_pol%d" % pol], what="P^T F P x unfused pol%d" % pol)
+        close((P.T * Fp * P) * x, g["A_y_pol%d" % pol], what="P^T F P x composed pol%d" % pol)
+
+
+def build_solve_system(impl, g):
+    pol = int(g["pol"])
+    pix = g["pix_in"].copy()
+    nt = len(pix)
+    nb = int(g["nb"])
+    N = impl.BlockLO(nt // nb, [g["t"][i] for i in range(nb)], offdiag=True)
+    pts = impl.ProcessTimeSamples(pix, int(g["npix_old"]), pol=pol, phi=g["phi"])
+    npix = pts.get_new_pixel[0]
+    assert npix == int(g["npix"])
+    P = impl.SparseLO(npix, nt, pix, pol=pol, angle_processed=pts)
+    Mbd = impl.BlockDiagonalPreconditionerLO(pts, npix, pol=pol)
+    B = impl.BlockDiagonalLO(pts, npix, pol=pol)
+    A = P.T * N * P
+    b = P.T * N * g["d"]
+    return pol, npix, P, N, Mbd, B, A, b
+
+
+def check_solve(impl, name, cg, hist_rtol=1e-6, strict_arnoldi_m=True):
+    """PCG (M_BD and M_2lvl), coarse/deflation operators, in-tree Arnoldi."""
+    g = load(name)
+    pol, npix, P, N, Mbd, B, A, b = build_solve_system(impl, g)
+    n = pol * npix
+    close(b, g["b"], what="b = P^T N d")
+    # -- M_BD PCG: solution, exit code, iteration count +-1, residual history
+    hist = []
+    x, info = cg(A, b, x0=np.zeros(n), M=Mbd, rtol=1e-8, maxiter=200,
+                 callback=lambda xk: hist.append(np.linalg.norm(b - A * np.asarray(xk))))
+    assert info == int(g["cg_info"])
+    assert abs(len(hist) - int(g["cg_iters"])) <= 1
+    close(x, g["cg_x"], rtol=1e-7, what="PCG(M_BD) solution")
+    k = min(len(hist), len(g["cg_hist"]))
+    ref = g["cg_hist"][:k]
+    got = np.array(hist[:k])
+    assert np.all(np.abs(got - ref) <= hist_rtol * np.maximum(ref, ref[0] * 1e-9) + 1e-12 * ref[0]), \
+        "residual history differs"
+    # -- deflation / coarse operators on the stored Z (built by ARPACK on the reference ops)
+    Z, Az = g["Z"], g["Az"]
+    r = Z.shape[1]
+    Az_impl = np.column_stack([A * Z[:, i] for i in range(r)])
+    close(Az_impl, Az, what="A Z")
+    E_lu = impl.CoarseLO(Z, Az, r)
+    E_eig = impl.CoarseLO(Z, Az, r, apply="eig")
+    close(impl.dgemm(Z, Az.T), g["E"], what="E = Z^T A Z")
+    close(E_lu * g["v_r"], g["Elu_v"], rtol=1e-8, what="E^-1 v (LU)")
+    close(E_eig * g["v_r"], g["Eeig_v"], rtol=1e-8, what="E^-1 v (eig)")
+    Zd = impl.DeflationLO(Z)
+    AZd = impl.DeflationLO(Az)
+    close(Zd * g["v_r"], g["Zd_v"], what="Z y")
+    close(Zd.T * g["v_n"], g["ZdT_v"], what="Z^T x")
+    I = impl.lp.IdentityOperator(n)
+    R = I - AZd * E_eig * Zd.T
+    M2 = Mbd * R + Zd * E_eig * Zd.T
+    close(R * g["v_n"], g["R_v"], rtol=1e-8, what="R v")
+    close(M2 * g["v_n"], g["M2_v"], rtol=1e-8, what="M2 v")
+    for i in range(r):     # tests/test_2level_preconditioner.py:50-51
+        assert np.allclose(M2 * (A * Z[:, i]), Z[:, i])
+        assert np.linalg.norm(R * (A * Z[:, i])) <= 1e-10 * max(1.0, np.linalg.norm(Az[:, i]))
+    hist2 = []
+    x2, info2 = cg(A, b, x0=np.zeros(n), M=M2, rtol=1e-8, maxiter=200,
+                   callback=lambda xk: hist2.append(0))
+    assert info2 == int(g["cg2_info"])
+    assert abs(len(hist2) - int(g["cg2_iters"])) <= 1
+    close(x2, g["cg2_x"], rtol=1e-7, what="PCG(M_2lvl) solution")
+    # -- in-tree Arnoldi (interfaces/deflationlib.py:17-137).  M_BD A is close to the identity,
+    # so h_{j+1,j} is small and every normalisation amplifies rounding differences by ~1/h
+    # (measured: x50 per step in the reference itself, which loses orthogonality at the same
+    # rate).  Only the leading columns are therefore comparable to 1e-8; the rest is checked
+    # through the Arnoldi relation A V_m = V_{m+1} H, which holds to rounding for any m.
+    vs, hs, m = impl.arnoldi(Mbd * A, Mbd * b, x0=np.ones(n), tol=1e-3, inner_m=n - 1)
+    if strict_arnoldi_m:
+        assert m == int(g["arn_m"])
+    H = impl.build_hess(hs, m)
+    V = np.array([np.asarray(v) for v in vs])
+    k = min(4, m, int(g["arn_m"]))
+    close(H[:k, :k - 1], g["arn_H"][:k, :k - 1], rtol=1e-8, what="Hessenberg (leading block)")
+    close(V[:k], g["arn_V"][:k], rtol=1e-8, what="Arnoldi basis (leading vectors)")
+    MA = Mbd * A
+    for j in range(min(m, len(vs)) - 1):
+        lhs = MA * V[j]
+        rhs = sum(hs[j][i] * V[i] for i in range(j + 2))
+        close(lhs, rhs, rtol=1e-9, what="Arnoldi relation column %d" % j)
