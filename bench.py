@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""
+bench.py -- BASELINE.json's metric on BASELINE.json's configuration.
+
+    metric   : TOD samples/s per PCG iteration (one A apply + one M apply + the CG vector work)
+    workload : configs[1] -- synthetic raster scan, 1e8 samples per GPU, IQU nside=512, white noise
+               (64 detector blocks), block-diagonal-preconditioned PCG on A = P^T N^-1 P
+    N GPUs   : weak scaling -- every rank owns its own 64 detectors x 1e8/64 samples of the same sky
+               patch; one NCCL all-reduce of the map-domain A p per iteration
+
+    python bench.py --gpus N --steps K --warmup W        (torchrun launches it for N > 1)
+    python bench.py --impl reference ...                  (CPU arm: the oracle port on host cores)
+
+A step = one full PCG iteration from a fresh residual (r <- b, x <- 0, then z = M r, rho, p, q = A p,
+alpha, x, r, ||r||).  White noise with the weights fed to M_BD makes M_BD A = I, so the solve
+converges in ONE iteration (the reference expects exactly that,
+src/test_BD_precond_onto_real_data.py:52); iterating on the converged residual would only process
+rounding noise until it underflows, hence the restart -- the work per step is the full iteration.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "tod_samples_per_s_per_pcg_iter"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nt", type=int, default=100000000, help="TOD samples per GPU (configs[1]: 1e8)")
+    ap.add_argument("--cpu-nt", type=int, default=30000000, help="samples of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-iters", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (plain-C twin of the reference's weave loops + SciPy's cg), host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_pcg_throughput(nt, iters, warmup=1, seed=0):
+    """samples/s per PCG iteration of the oracle on a bounded sample of the same workload."""
+    import scipy.sparse.linalg as spla
+    import oracle
+    from oracle import cloops
+    from cosmomap2_b200 import synthetic
+    cloops.build()
+    sc = synthetic.config_c2(nt=nt, seed=seed)
+    pix = sc.pix.astype(np.int64)
+    N = oracle.BlockLO(sc.ns, sc.weights)
+    pts = oracle.ProcessTimeSamples(pix, sc.npix_full, pol=3, phi=sc.phi, w=N.diag)
+    npix = pts.get_new_pixel[0]
+    P = oracle.SparseLO(npix, sc.nt, pix, pol=3, angle_processed=pts)
+    Mbd = oracle.BlockDiagonalPreconditionerLO(pts, npix, pol=3)
+    A = P.T * N * P
+    b = P.T * (N * sc.d)
+    for _ in range(warmup):
+        spla.cg(A, b, M=Mbd, rtol=1e-30, maxiter=1)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        spla.cg(A, b, M=Mbd, rtol=1e-30, maxiter=1)        # one full iteration from a fresh residual
+    dt = time.perf_counter() - t0
+    return sc.nt * iters / dt, dt / iters, sc.nt, npix
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    v, t_iter, nt, npix = cpu_pcg_throughput(args.cpu_nt, max(args.steps, 1), warmup=max(args.warmup, 0))
+    sample = ("oracle port (C twin of the weave loops, gcc -O3, + scipy.sparse.linalg.cg) on %d of the "
+              "1e8 samples/GPU of configs[1] (same generator, same patch), %d timed iterations"
+              % (nt, max(args.steps, 1)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_iter, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: raster scan, IQU nside=512, white noise, M_BD PCG (bounded sample)",
+                   "nt_sample": nt, "npix_observed": int(npix), "pol": 3},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": os.cpu_count(),
+                         "note": "the reference's loops are serial (weave.inline, no omp pragma): 1 thread"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except Exception:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import cosmomap2_b200 as cm
+    from cosmomap2_b200 import synthetic, _cabi, distributed
+    from cosmomap2_b200.pcg import PCG
+    from cosmomap2_b200 import _device as dv
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- inputs: this rank's detectors of configs[1] -----------------------------------------------
+    pol = 3
+    sc = synthetic.config_c2(nt=args.nt, seed=rank)
+    nt = sc.nt
+    N = cm.BlockLO(sc.ns, sc.weights)
+    pix = sc.pix                                     # int32 HEALPix ids, relabelled in place
+    pts = cm.ProcessTimeSamples(pix, sc.npix_full, pol=pol, phi=sc.phi, w=N.diag, comm=(True if world > 1 else None))
+    npix = pts.get_new_pixel[0]
+    n = pol * npix
+    P = cm.SparseLO(npix, nt, pix, pol=pol, angle_processed=pts)
+    Mbd = cm.BlockDiagonalPreconditionerLO(pts, npix, pol=pol)
+    A_local = P.T * N * P                              # planned as ONE fused kernel (cm2_amatvec_white)
+    a_events = []
+
+    class Timed(cm.lp.LinearOperator):                 # CUDA events around the local fused kernel only
+        def __init__(self, op):
+            self.op = op
+            super(Timed, self).__init__(op.nargin, op.nargout, matvec=self._run, symmetric=True, device=True)
+            self.record = False
+
+        def _run(self, x):
+            if not self.record:
+                return self.op._apply(x)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            y = self.op._apply(x)
+            e1.record()
+            a_events.append((e0, e1))
+            return y
+
+    A_timed = Timed(A_local)
+    A = distributed.AllReduceLO(A_timed) if world > 1 else A_timed
+    d_dev = dv.to_dev_f64(sc.d)
+    b = P.T._apply(N._apply(d_dev))
+    if world > 1:
+        distributed.all_reduce_sum_(b)
+    del d_dev
+    sc.d = None
+    torch.cuda.synchronize()
+
+    # ---- correctness gate (not timed): the solve converges, A x = b ---------------------------------
+    res = []
+    x_sol, info = cm.cg(A, b, M=Mbd, rtol=1e-10, maxiter=20, residuals=res)
+    relres = float(torch.linalg.norm(b - A._apply(x_sol)) / torch.linalg.norm(b))
+    check = {"cg_info": int(info), "cg_iterations": len(res) - 1 if info == 0 else len(res), "relres": relres}
+    del x_sol
+
+    # ---- device-resident timing -----------------------------------------------------------------------
+    solver = PCG(A, Mbd, n)
+
+    def one_step():
+        solver.start(b, need_norm=False)
+        solver.step()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _cabi.launch_count()
+    A_timed.record = True
+    t_wall0 = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        one_step()
+    ev1.record()
+    barrier()
+    A_timed.record = False
+    launches = _cabi.launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * nt * args.steps / (ms * 1e-3)
+    t_a_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in a_events]))
+    assert bool(torch.isfinite(solver.x).all().item()), "PCG state is not finite"
+
+    # keep the GPU under the same load for ~1.5 s so that nvidia-smi sees the clocks of this loop
+    t_end = time.time() + 1.5
+    while time.time() < t_end:
+        for _ in range(20):
+            one_step()
+        torch.cuda.synchronize()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    if clocks is not None:
+        clocks["window"] = "timed loop + 1.5 s repeat of the same loop"
+
+    # ---- end to end: the reference's own driver (SciPy cg) over the drop-in operators, HOST vectors ----
+    import scipy.sparse.linalg as spla
+    b_host = dv.to_host(b)
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    spla.cg(A, b_host, M=Mbd, rtol=1e-30, maxiter=1)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        x_h, _info = spla.cg(A, b_host, M=Mbd, rtol=1e-30, maxiter=1)
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_value = world * nt * e2e_steps / float(tt.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        alg_bytes = 20.0 * nt + 48.0 * npix
+        achieved = alg_bytes / (t_a_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "amatvec_white_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: synthetic raster scan, 1e8 samples/GPU, IQU nside=512, white noise "
+                                   "(64 detector blocks), M_BD PCG on A=P^T N^-1 P",
+                       "nt_per_gpu": nt, "npix_observed": int(npix), "pol": pol, "nside": 512,
+                       "samples_per_pixel_crossing": sc.samples_per_pixel,
+                       "step": "one PCG iteration from a fresh residual (A apply + M_BD apply + CG vector work + ||r|| readback)",
+                       "l2": "inputs (2.0 GB TOD per pass) larger than L2 (126 MB); no flush needed",
+                       "parallelism": "tod sharded by detector x%d, map all-reduce (NCCL)" % world if world > 1 else "single GPU",
+                       "check": check},
+            "roofline": {"bound": "hbm", "kernel": "k_amatvec_white<3> (cm2_amatvec_white)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_ms": t_a_ms, "frac_of_8TBs_spec": achieved / 8000.0},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * n, "d2h_bytes_per_step": 2 * 8 * n,
+                    "steps": e2e_steps,
+                    "path": "scipy.sparse.linalg.cg(A, b, M=Mbd, maxiter=1) on host ndarrays over the drop-in operators"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, t_iter, nt_cpu, _np = cpu_pcg_throughput(args.cpu_nt, args.cpu_iters)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": "oracle port (C twin of the reference's weave loops, gcc -O3, + scipy cg) on %d samples of the "
+                          "same workload generator, %d iterations, %.2f s/iteration" % (nt_cpu, args.cpu_iters, t_iter),
+                "host_cores_available": os.cpu_count()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,127 @@
+"""
+Device-buffer plumbing.  PyTorch is used only to own HBM buffers and streams (and, in
+distributed.py, for the NCCL process group); every computation goes through the C ABI.
+"""
+import weakref
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("cosmomap2_b200 runs on a CUDA device (B200, sm_100a); "
+                           "no GPU is visible and there is no CPU fallback")
+
+
+def device():
+    require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream():
+    """cudaStream_t of torch's current stream, as the void* the C ABI takes."""
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def is_dev(x):
+    return isinstance(x, torch.Tensor)
+
+
+def empty_f64(n):
+    return torch.empty(int(n), dtype=torch.float64, device=device())
+
+
+def zeros_f64(n):
+    return torch.zeros(int(n), dtype=torch.float64, device=device())
+
+
+def to_dev(a, dtype=None):
+    """numpy / torch / sequence -> contiguous CUDA tensor (a new buffer unless already one)."""
+    if isinstance(a, torch.Tensor):
+        t = a
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        if not t.is_cuda:
+            t = t.to(device())
+        t = t.contiguous()
+        if t.data_ptr() % 32:          # kernels use 256-bit loads: views at odd offsets are copied
+            t = t.clone()
+        return t
+    arr = np.ascontiguousarray(a)
+    if arr.dtype == np.bool_:
+        arr = arr.astype(np.uint8)
+    if not arr.flags.writeable:
+        arr = arr.copy()
+    t = torch.from_numpy(arr).to(device())
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t
+
+
+def to_dev_f64(a):
+    return to_dev(a, torch.float64)
+
+
+def to_host(t):
+    return t.detach().cpu().numpy()
+
+
+def call(name, *args):
+    return _cabi.call(name, *args)
+
+
+# ---- registry: caller-owned host arrays whose device image already exists --------------------
+# ProcessTimeSamples relabels ``pixs`` on the device and writes it back into the caller's array;
+# SparseLO / FilterLO are then handed that same array (every reference test does this) and pick up
+# the device copy here instead of uploading it again.
+_registry = {}
+
+
+def register_host_image(arr, tensor):
+    if not isinstance(arr, np.ndarray):
+        return
+    key = id(arr)
+
+    def _drop(_ref, key=key):
+        _registry.pop(key, None)
+    try:
+        _registry[key] = (weakref.ref(arr, _drop), tensor)
+    except TypeError:
+        pass
+
+
+def lookup_host_image(arr):
+    if not isinstance(arr, np.ndarray):
+        return None
+    hit = _registry.get(id(arr))
+    if hit is None:
+        return None
+    ref, tensor = hit
+    return tensor if ref() is arr else None
+
+
+def pix_to_dev(pix):
+    """Pixel indices (host int32/int64 array or CUDA tensor) -> int32 CUDA tensor, 32-B aligned."""
+    if isinstance(pix, torch.Tensor):
+        t = pix if pix.is_cuda else pix.to(device())
+        if t.dtype == torch.int32:
+            return t.contiguous()
+        t = t.to(torch.int64).contiguous()
+    else:
+        hit = lookup_host_image(pix)
+        if hit is not None:
+            return hit
+        arr = np.ascontiguousarray(pix)
+        if arr.dtype == np.int32:
+            return to_dev(arr)
+        t = to_dev(arr.astype(np.int64, copy=False))
+    out = torch.empty(t.numel(), dtype=torch.int32, device=t.device)
+    call("cm2_pix_narrow", ptr(t), t.numel(), ptr(out), stream())
+    return out

@@ -1,0 +1,187 @@
+// cosmomap2_b200 -- deflation space, coarse operator and two-level preconditioner (sm_100a).
+//
+//   cm2_defl_zt_apply   out = Z^T X      (DeflationLO.rmult linearoperators.py:1056; E build :1019)
+//   cm2_defl_z_apply    y = beta y0 + alpha Z c          (DeflationLO.mult :1047-1050)
+//   cm2_coarse_apply    c = Einv v                        (CoarseLO.mult_eig :984)
+//   cm2_m2_apply        y = M_BD (v - AZ c) + Z c, c = Einv Z^T v
+//                       (src/test_M2_precond_onto_real_data.py:109-112; reads Z twice, AZ once)
+//
+// Z is tall-skinny (n x r, column-major, r <= 64): these are HBM-bound streaming kernels
+// (8 r bytes per row), so they run on the fp64 pipes with coalesced 128-bit column reads; the
+// r x r work is negligible.
+#include "cm2_common.cuh"
+
+namespace cm2 {
+
+constexpr int DB = 256;
+constexpr int RC = 8;          // Z columns accumulated per pass
+constexpr int DG_MAX = 1024;   // max CTAs of the Z^T x reduction
+
+// partial[blockIdx.x * r + c] = sum over this CTA's rows of Z[row, c] * x[row]
+__global__ void __launch_bounds__(DB) k_zt_partial(const double *__restrict__ Z, int64_t n, int r, int64_t ldz,
+                                                   const double *__restrict__ x, double *__restrict__ partial) {
+    __shared__ double red[32];
+    for (int c0 = 0; c0 < r; c0 += RC) {
+        double acc[RC];
+#pragma unroll
+        for (int c = 0; c < RC; ++c) acc[c] = 0.0;
+        for (int64_t i = (int64_t)blockIdx.x * DB + threadIdx.x; i < n; i += (int64_t)gridDim.x * DB) {
+            const double xi = x[i];
+#pragma unroll
+            for (int c = 0; c < RC; ++c)
+                if (c0 + c < r) acc[c] = fma(Z[i + (int64_t)(c0 + c) * ldz], xi, acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < RC; ++c) {
+            const double t = block_sum(acc[c], red);
+            if (threadIdx.x == 0 && c0 + c < r) partial[(int64_t)blockIdx.x * r + c0 + c] = t;
+        }
+    }
+}
+
+// out[c] = sum_b partial[b*r + c] in CTA order (deterministic); optional out = Einv * (that)
+__global__ void __launch_bounds__(DB) k_zt_final(const double *__restrict__ partial, int nb, int r,
+                                                 const double *__restrict__ Einv, double *__restrict__ t_out,
+                                                 double *__restrict__ c_out) {
+    extern __shared__ double st[];   // r doubles
+    for (int c = threadIdx.x; c < r; c += DB) {
+        double s = 0.0;
+        for (int b = 0; b < nb; ++b) s += partial[(int64_t)b * r + c];
+        st[c] = s;
+        if (t_out) t_out[c] = s;
+    }
+    __syncthreads();
+    if (Einv != nullptr) {
+        for (int i = threadIdx.x; i < r; i += DB) {
+            double s = 0.0;
+            for (int j = 0; j < r; ++j) s = fma(Einv[i + (int64_t)j * r], st[j], s);
+            c_out[i] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(DB) k_z_apply(const double *__restrict__ Z, int64_t n, int r, int64_t ldz,
+                                                const double *__restrict__ coef, double alpha, double beta,
+                                                const double *__restrict__ y0, double *__restrict__ y) {
+    extern __shared__ double sc[];
+    for (int c = threadIdx.x; c < r; c += DB) sc[c] = coef[c];
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * DB + threadIdx.x; i < n; i += (int64_t)gridDim.x * DB) {
+        double s = 0.0;
+        for (int c = 0; c < r; ++c) s = fma(Z[i + (int64_t)c * ldz], sc[c], s);
+        const double b = (y0 != nullptr && beta != 0.0) ? beta * y0[i] : 0.0;
+        y[i] = fma(alpha, s, b);
+    }
+}
+
+__global__ void __launch_bounds__(DB) k_coarse_apply(const double *__restrict__ Einv, int r, const double *__restrict__ v,
+                                                     double *__restrict__ c) {
+    extern __shared__ double sv[];
+    for (int j = threadIdx.x; j < r; j += DB) sv[j] = v[j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < r; i += DB) {
+        double s = 0.0;
+        for (int j = 0; j < r; ++j) s = fma(Einv[i + (int64_t)j * r], sv[j], s);
+        c[i] = s;
+    }
+}
+
+// per pixel: u = v - AZ c ; y = Minv u + Z c
+template <int POL>
+__global__ void __launch_bounds__(DB) k_m2_finish(const double *__restrict__ Z, const double *__restrict__ AZ, int r, int64_t ld,
+                                                  const double *__restrict__ coef, const double *__restrict__ inv, int64_t npix,
+                                                  const double *__restrict__ v, double *__restrict__ y) {
+    extern __shared__ double sc[];
+    for (int c = threadIdx.x; c < r; c += DB) sc[c] = coef[c];
+    __syncthreads();
+    for (int64_t j = (int64_t)blockIdx.x * DB + threadIdx.x; j < npix; j += (int64_t)gridDim.x * DB) {
+        double u[POL], zc[POL];
+#pragma unroll
+        for (int k = 0; k < POL; ++k) { u[k] = v[POL * j + k]; zc[k] = 0.0; }
+        for (int c = 0; c < r; ++c) {
+            const double cc = sc[c];
+#pragma unroll
+            for (int k = 0; k < POL; ++k) {
+                u[k] = fma(-AZ[POL * j + k + (int64_t)c * ld], cc, u[k]);
+                zc[k] = fma(Z[POL * j + k + (int64_t)c * ld], cc, zc[k]);
+            }
+        }
+        const double *b = inv + 6 * j;
+        if constexpr (POL == 1) {
+            y[j] = fma(b[0], u[0], zc[0]);
+        } else if constexpr (POL == 2) {
+            y[2 * j] = b[3] * u[0] + b[4] * u[1] + zc[0];
+            y[2 * j + 1] = b[4] * u[0] + b[5] * u[1] + zc[1];
+        } else {
+            y[3 * j] = b[0] * u[0] + b[1] * u[1] + b[2] * u[2] + zc[0];
+            y[3 * j + 1] = b[1] * u[0] + b[3] * u[1] + b[4] * u[2] + zc[1];
+            y[3 * j + 2] = b[2] * u[0] + b[4] * u[1] + b[5] * u[2] + zc[2];
+        }
+    }
+}
+
+static int dgrid(int64_t n, int per_sm = 4) {
+    int64_t b = (n + DB - 1) / DB;
+    int64_t cap = (int64_t)sm_count() * per_sm;
+    if (cap > DG_MAX) cap = DG_MAX;
+    if (b > cap) b = cap;
+    return (int)(b < 1 ? 1 : b);
+}
+
+}  // namespace cm2
+
+using namespace cm2;
+
+extern "C" int64_t cm2_defl_work_doubles(int r) { return (int64_t)DG_MAX * r + 2 * (int64_t)r; }
+
+extern "C" int cm2_defl_zt_apply(const double *Z, int64_t n, int r, int64_t ldz, const double *X, int ncols_x,
+                                 int64_t ldx, double *out, double *work, cm2_stream_t stream) {
+    CM2_REQUIRE(n >= 0 && r >= 1 && ncols_x >= 1 && ldz >= n, "bad sizes");
+    CM2_REQUIRE(work != nullptr, "work (cm2_defl_work_doubles) required");
+    cudaStream_t st = as_stream(stream);
+    const int g = dgrid(n);
+    for (int k = 0; k < ncols_x; ++k) {
+        k_zt_partial<<<g, DB, 0, st>>>(Z, n, r, ldz, X + (int64_t)k * ldx, work);
+        CM2_LAUNCHED();
+        k_zt_final<<<1, DB, sizeof(double) * r, st>>>(work, g, r, nullptr, out + (int64_t)k * r, nullptr);
+        CM2_LAUNCHED();
+    }
+    return CM2_OK;
+}
+
+extern "C" int cm2_defl_z_apply(const double *Z, int64_t n, int r, int64_t ldz, const double *c, double alpha,
+                                double beta, const double *y0, double *y, cm2_stream_t stream) {
+    CM2_REQUIRE(n >= 0 && r >= 1 && ldz >= n, "bad sizes");
+    if (n == 0) return CM2_OK;
+    k_z_apply<<<dgrid(n, 8), DB, sizeof(double) * r, as_stream(stream)>>>(Z, n, r, ldz, c, alpha, beta, y0, y);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+extern "C" int cm2_coarse_apply(const double *Einv, int r, const double *v, double *c, cm2_stream_t stream) {
+    CM2_REQUIRE(r >= 1, "r < 1");
+    k_coarse_apply<<<1, DB, sizeof(double) * r, as_stream(stream)>>>(Einv, r, v, c);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+extern "C" int cm2_m2_apply(const double *Z, const double *AZ, int64_t n, int r, int64_t ld, const double *Einv,
+                            const double *bd_inv, int64_t npix, int pol, const double *v, double *y, double *work,
+                            cm2_stream_t stream) {
+    CM2_REQUIRE(pol >= 1 && pol <= 3 && n == npix * pol && r >= 1 && ld >= n, "bad sizes");
+    CM2_REQUIRE(work != nullptr, "work (cm2_defl_work_doubles) required");
+    cudaStream_t st = as_stream(stream);
+    const int g = dgrid(n);
+    double *coef = work + (int64_t)DG_MAX * r;   // r doubles: c = Einv Z^T v
+    k_zt_partial<<<g, DB, 0, st>>>(Z, n, r, ld, v, work);
+    CM2_LAUNCHED();
+    k_zt_final<<<1, DB, sizeof(double) * r, st>>>(work, g, r, Einv, nullptr, coef);
+    CM2_LAUNCHED();
+    const int g2 = dgrid(npix, 8);
+    const size_t sm = sizeof(double) * r;
+    if (pol == 1) k_m2_finish<1><<<g2, DB, sm, st>>>(Z, AZ, r, ld, coef, bd_inv, npix, v, y);
+    else if (pol == 2) k_m2_finish<2><<<g2, DB, sm, st>>>(Z, AZ, r, ld, coef, bd_inv, npix, v, y);
+    else k_m2_finish<3><<<g2, DB, sm, st>>>(Z, AZ, r, ld, coef, bd_inv, npix, v, y);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}

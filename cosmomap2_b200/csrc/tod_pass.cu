@@ -1,0 +1,569 @@
+// cosmomap2_b200 -- time-domain passes over the TOD (sm_100a).
+//
+//   cm2_pointing_apply      d = P x            gather     (linearoperators.py:356-384,411-438,463-497)
+//   cm2_pointing_apply_t    y = P^T d          scatter    (linearoperators.py:385-410,439-462,498-526)
+//   cm2_amatvec_white       y = P^T diag(w) P x, fused, no TOD temporary
+//   cm2_weights_moments     per-pixel moments of P^T diag(w) P (process_ces.py:480-542,125-189)
+//   cm2_hits_i64            integer hit counts
+//
+// Data layout in HBM: pix int32[nt], cos2phi fp64[nt], sin2phi fp64[nt] (20 B/sample), maps
+// interleaved fp64.  Every warp walks tiles of 32*K consecutive samples; lane l owns the K=8
+// consecutive samples [tile*256 + 8l, +8) and reads them with 256-bit streaming loads
+// (L2 evict-first, so the multi-GB TOD stream does not evict the L2-resident map).
+//
+// Scatter-add: a scan crosses a pixel in a run of consecutive samples, so (1) each lane compresses
+// its 8 samples into runs in registers, (2) the open runs at lane boundaries are merged across the
+// warp with a segmented shuffle scan, (3) one fp64 RED per (run, Stokes component) goes to L2.
+// Random pointing degenerates gracefully to one RED per sample and component.
+#include "cm2_common.cuh"
+
+namespace cm2 {
+
+constexpr int K = 8;          // consecutive samples per lane
+constexpr int TILE = 32 * K;  // samples per warp tile
+constexpr int BLOCK = 256;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct BlockW {
+    const double *w;       // per-block weights, nullptr = unit weights
+    int64_t nblocks;
+    int64_t blocksize;     // equal-size blocks when start == nullptr
+    const int64_t *start;  // nblocks+1 block boundaries, or nullptr
+};
+
+__device__ __forceinline__ int64_t block_of(const BlockW &bw, int64_t t) {
+    if (bw.start == nullptr) {
+        if (((uint64_t)t | (uint64_t)bw.blocksize) >> 32 == 0) return (uint32_t)t / (uint32_t)bw.blocksize;
+        return t / bw.blocksize;
+    }
+    int64_t lo = 0, hi = bw.nblocks;
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (bw.start[mid] <= t) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// weights of the K samples starting at t0 (one lookup when the chunk sits inside one block)
+__device__ __forceinline__ void chunk_weights(const BlockW &bw, int64_t t0, int64_t nt, double (&w)[K]) {
+    if (bw.w == nullptr) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) w[j] = 1.0;
+        return;
+    }
+    int64_t b0 = block_of(bw, t0);
+    if (b0 >= bw.nblocks) b0 = bw.nblocks - 1;
+    int64_t bend = bw.start ? bw.start[b0 + 1] : (b0 + 1) * bw.blocksize;
+    if (t0 + K <= bend) {
+        double w0 = __ldg(bw.w + b0);
+#pragma unroll
+        for (int j = 0; j < K; ++j) w[j] = w0;
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            int64_t t = t0 + j;
+            int64_t b = t < nt ? block_of(bw, t) : b0;
+            if (b >= bw.nblocks) b = bw.nblocks - 1;
+            w[j] = __ldg(bw.w + b);
+        }
+    }
+}
+
+__device__ __forceinline__ void load_pix(const int32_t *__restrict__ pix, int64_t t0, int64_t nt, int (&p)[K]) {
+    if (t0 + K <= nt) {
+        I8 v = ld_stream_i8(pix + t0);
+#pragma unroll
+        for (int j = 0; j < K; ++j) p[j] = v.v[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) p[j] = (t0 + j < nt) ? ld_stream_i1(pix + t0 + j) : -1;
+    }
+}
+
+__device__ __forceinline__ void load_f64(const double *__restrict__ a, int64_t t0, int64_t nt, double (&c)[K]) {
+    if (t0 + K <= nt) {
+        D4 v0 = ld_stream_d4(a + t0);
+        D4 v1 = ld_stream_d4(a + t0 + 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c[j] = v0.v[j]; c[4 + j] = v1.v[j]; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) c[j] = (t0 + j < nt) ? ld_stream_d1(a + t0 + j) : 0.0;
+    }
+}
+
+// x values of the K samples; one gather per run start, copied along the run
+template <int POL>
+__device__ __forceinline__ void gather_x(const double *__restrict__ x, const int (&p)[K], double (&xv)[K][POL]) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const bool nw = (j == 0) || (p[j] != p[j - 1]);
+#pragma unroll
+        for (int k = 0; k < POL; ++k) xv[j][k] = 0.0;
+        if (nw && p[j] >= 0) {
+            const double *xp = x + (int64_t)POL * p[j];
+#pragma unroll
+            for (int k = 0; k < POL; ++k) xv[j][k] = __ldg(xp + k);
+        }
+    }
+#pragma unroll
+    for (int j = 1; j < K; ++j) {
+        if (p[j] == p[j - 1]) {
+#pragma unroll
+            for (int k = 0; k < POL; ++k) xv[j][k] = xv[j - 1][k];
+        }
+    }
+}
+
+template <int POL>
+__device__ __forceinline__ double project(const double (&xv)[POL], double c, double s) {
+    if constexpr (POL == 1) return xv[0];
+    else if constexpr (POL == 2) return fma(xv[1], s, xv[0] * c);
+    else return fma(xv[2], s, fma(xv[1], c, xv[0]));
+}
+
+template <int NV, int STRIDE>
+__device__ __forceinline__ void emit(double *__restrict__ y, int pix, const double (&v)[NV]) {
+    if (pix >= 0) {
+        double *dst = y + (int64_t)STRIDE * pix;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) atomicAdd(dst + k, v[k]);  // result unused -> RED.E.ADD.F64
+    }
+}
+
+// Run-compressed, warp-merged scatter-add of K samples per lane.  contrib(j, out[NV]) yields the
+// NV values sample j adds to pixel p[j].  All 32 lanes must call (shuffles use the full mask).
+template <int NV, int STRIDE, class F>
+__device__ __forceinline__ void run_scatter(double *__restrict__ y, const int (&p)[K], F contrib) {
+    const int lane = threadIdx.x & 31;
+    double acc[NV], head[NV];
+    int cur = p[0];
+    bool single = true;
+    contrib(0, acc);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) head[k] = 0.0;
+#pragma unroll
+    for (int j = 1; j < K; ++j) {
+        double v[NV];
+        contrib(j, v);
+        if (p[j] != cur) {
+            if (single) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) head[k] = acc[k];
+                single = false;
+            } else {
+                emit<NV, STRIDE>(y, cur, acc);
+            }
+            cur = p[j];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc[k] = v[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc[k] += v[k];
+        }
+    }
+    const int ph = p[0], pt = cur;
+    const int pt_prev = __shfl_up_sync(FULL, pt, 1);
+    const int ph_next = __shfl_down_sync(FULL, ph, 1);
+    const bool cont_prev = (lane > 0) && (pt_prev == ph);   // my first run continues the previous lane's last
+    const bool cont_next = (lane < 31) && (ph_next == pt);  // my last run continues into the next lane
+    // segmented inclusive scan of the open partial (acc) over lanes; a lane starts a segment
+    // unless it is one single run that continues the previous lane
+    bool f = !(single && cont_prev);
+    if (__any_sync(FULL, !f)) {
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            double up[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) up[k] = __shfl_up_sync(FULL, acc[k], d);
+            const int fu = __shfl_up_sync(FULL, (int)f, d);
+            if (lane >= d) {
+                if (!f) {
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) acc[k] += up[k];
+                }
+                f = f || (fu != 0);
+            }
+        }
+    }
+    // acc = partial of the run that is open at the end of this lane (carry-out)
+    double cin[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) cin[k] = __shfl_up_sync(FULL, acc[k], 1);
+    if (!single) {
+        if (cont_prev) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) head[k] += cin[k];
+        }
+        emit<NV, STRIDE>(y, ph, head);
+    }
+    if (!cont_next) emit<NV, STRIDE>(y, pt, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+template <int POL>
+__global__ void __launch_bounds__(BLOCK) k_pointing_apply(const int32_t *__restrict__ pix, const double *__restrict__ cs,
+                                                          const double *__restrict__ sn, int64_t nt,
+                                                          const double *__restrict__ x, double *__restrict__ d) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
+    const int64_t ntiles = (nt + TILE - 1) / TILE;
+    for (int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
+        const int64_t t0 = tile * TILE + (int64_t)lane * K;
+        if (t0 >= nt) continue;
+        int p[K];
+        double c[K], s[K], xv[K][POL], out[K];
+        load_pix(pix, t0, nt, p);
+        if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
+        gather_x<POL>(x, p, xv);
+#pragma unroll
+        for (int j = 0; j < K; ++j) out[j] = p[j] >= 0 ? project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0) : 0.0;
+        if (t0 + K <= nt) {
+            D4 a, b;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { a.v[j] = out[j]; b.v[j] = out[4 + j]; }
+            st_stream_d4(d + t0, a);
+            st_stream_d4(d + t0 + 4, b);
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j) if (t0 + j < nt) d[t0 + j] = out[j];
+        }
+    }
+}
+
+template <int POL>
+__global__ void __launch_bounds__(BLOCK) k_pointing_apply_t(const int32_t *__restrict__ pix, const double *__restrict__ cs,
+                                                            const double *__restrict__ sn, int64_t nt,
+                                                            const double *__restrict__ d, double *__restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
+    const int64_t ntiles = (nt + TILE - 1) / TILE;
+    for (int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
+        const int64_t t0 = tile * TILE + (int64_t)lane * K;
+        int p[K];
+        double c[K], s[K], v[K];
+        load_pix(pix, t0, nt, p);
+        load_f64(d, t0, nt, v);
+        if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
+        run_scatter<POL, POL>(y, p, [&](int j, double (&o)[POL]) {
+            if constexpr (POL == 1) { o[0] = v[j]; }
+            else if constexpr (POL == 2) { o[0] = v[j] * c[j]; o[1] = v[j] * s[j]; }
+            else { o[0] = v[j]; o[1] = v[j] * c[j]; o[2] = v[j] * s[j]; }
+        });
+    }
+}
+
+template <int POL>
+__global__ void __launch_bounds__(BLOCK) k_amatvec_white(const int32_t *__restrict__ pix, const double *__restrict__ cs,
+                                                         const double *__restrict__ sn, int64_t nt, BlockW bw,
+                                                         const double *__restrict__ x, double *__restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
+    const int64_t ntiles = (nt + TILE - 1) / TILE;
+    for (int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
+        const int64_t t0 = tile * TILE + (int64_t)lane * K;
+        int p[K];
+        double c[K], s[K], w[K], xv[K][POL], v[K];
+        load_pix(pix, t0, nt, p);
+        if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
+        gather_x<POL>(x, p, xv);
+        chunk_weights(bw, t0 < nt ? t0 : nt - 1, nt, w);
+#pragma unroll
+        for (int j = 0; j < K; ++j) v[j] = w[j] * project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0);
+        run_scatter<POL, POL>(y, p, [&](int j, double (&o)[POL]) {
+            if constexpr (POL == 1) { o[0] = v[j]; }
+            else if constexpr (POL == 2) { o[0] = v[j] * c[j]; o[1] = v[j] * s[j]; }
+            else { o[0] = v[j]; o[1] = v[j] * c[j]; o[2] = v[j] * s[j]; }
+        });
+    }
+}
+
+// moments layout: mom[npix][6] = {h, c, s, c2, cs, s2}; pol=1 fills {h}, pol=2 {c2,cs,s2}, pol=3 all
+template <int POL>
+__global__ void __launch_bounds__(BLOCK) k_moments(const int32_t *__restrict__ pix, const double *__restrict__ cs,
+                                                   const double *__restrict__ sn, const double *__restrict__ wsamp,
+                                                   BlockW bw, int64_t nt, double *__restrict__ mom) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
+    const int64_t ntiles = (nt + TILE - 1) / TILE;
+    constexpr int NV = POL == 1 ? 1 : (POL == 2 ? 3 : 6);
+    for (int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
+        const int64_t t0 = tile * TILE + (int64_t)lane * K;
+        int p[K];
+        double c[K], s[K], w[K];
+        load_pix(pix, t0, nt, p);
+        if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
+        if (wsamp) load_f64(wsamp, t0, nt, w);
+        else chunk_weights(bw, t0 < nt ? t0 : nt - 1, nt, w);
+        double *base = mom + (POL == 2 ? 3 : 0);
+        run_scatter<NV, 6>(base, p, [&](int j, double (&o)[NV]) {
+            // same association as the reference loops: (w*c)*c, (w*s)*s, (w*s)*c
+            if constexpr (POL == 1) { o[0] = w[j]; }
+            else if constexpr (POL == 2) {
+                o[0] = (w[j] * c[j]) * c[j]; o[1] = (w[j] * s[j]) * c[j]; o[2] = (w[j] * s[j]) * s[j];
+            } else {
+                o[0] = w[j]; o[1] = w[j] * c[j]; o[2] = w[j] * s[j];
+                o[3] = (w[j] * c[j]) * c[j]; o[4] = (w[j] * s[j]) * c[j]; o[5] = (w[j] * s[j]) * s[j];
+            }
+        });
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK) k_hits(const int32_t *__restrict__ pix, int64_t nt, unsigned long long *__restrict__ hits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
+    const int64_t ntiles = (nt + TILE - 1) / TILE;
+    for (int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
+        const int64_t t0 = tile * TILE + (int64_t)lane * K;
+        if (t0 >= nt) continue;
+        int p[K];
+        load_pix(pix, t0, nt, p);
+        int cur = p[0];
+        unsigned long long n = 1;
+#pragma unroll
+        for (int j = 1; j < K; ++j) {
+            if (p[j] != cur) {
+                if (cur >= 0) atomicAdd(hits + cur, n);
+                cur = p[j];
+                n = 1;
+            } else {
+                ++n;
+            }
+        }
+        if (cur >= 0) atomicAdd(hits + cur, n);
+    }
+}
+
+
+// ---- fused y = P^T F P x (offset filter) --------------------------------------------------------
+// One CTA per subscan segment [a, b).  Pass 1 gathers d_t = (P x)_t, keeps it in shared memory and
+// reduces the masked sum (fixed order -> deterministic mean); pass 2 scatters (d_t - mean) for the
+// unflagged samples.  pix/cos/sin are read from HBM once (pass 1 leaves them in L2 for pass 2).
+// Tiles are aligned to multiples of TILE in the global sample index so the 256-bit loads stay
+// aligned; samples of a tile outside [a, b) are treated as flagged.
+constexpr int SEG_SMEM = 8192;   // d_t values kept on chip per segment (64 kB dynamic smem); longer -> recompute
+
+__device__ __forceinline__ void load_pix_keep(const int32_t *__restrict__ pix, int64_t t0, int64_t nt, int (&p)[K]) {
+    if (t0 + K <= nt) {
+        I8 v = ld_keep_i8(pix + t0);
+#pragma unroll
+        for (int j = 0; j < K; ++j) p[j] = v.v[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) p[j] = (t0 + j < nt) ? pix[t0 + j] : -1;
+    }
+}
+__device__ __forceinline__ void load_f64_keep(const double *__restrict__ a, int64_t t0, int64_t nt, double (&c)[K]) {
+    if (t0 + K <= nt) {
+        D4 v0 = ld_keep_d4(a + t0);
+        D4 v1 = ld_keep_d4(a + t0 + 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c[j] = v0.v[j]; c[4 + j] = v1.v[j]; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) c[j] = (t0 + j < nt) ? a[t0 + j] : 0.0;
+    }
+}
+
+template <int POL>
+__global__ void __launch_bounds__(BLOCK) k_amatvec_filter(const int32_t *__restrict__ pix, const double *__restrict__ cs,
+                                                          const double *__restrict__ sn, int64_t nt,
+                                                          const int64_t *__restrict__ seg_start,
+                                                          const int64_t *__restrict__ seg_end, int64_t nseg,
+                                                          const double *__restrict__ x, double *__restrict__ y) {
+    extern __shared__ double sd[];   // SEG_SMEM doubles
+    __shared__ double red[32];
+    __shared__ double s_mean;
+    __shared__ int s_skip;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t k = blockIdx.x; k < nseg; k += gridDim.x) {
+        const int64_t a = seg_start[k], b = seg_end[k];
+        const int64_t tile0 = a / TILE, tile1 = (b + TILE - 1) / TILE;   // [tile0, tile1)
+        const int64_t base = tile0 * TILE;
+        const bool fits = (tile1 - tile0) * TILE <= SEG_SMEM;
+        double sum = 0.0, cnt = 0.0;
+        for (int64_t tile = tile0 + warp; tile < tile1; tile += BLOCK / 32) {
+            const int64_t t0 = tile * TILE + (int64_t)lane * K;
+            int p[K];
+            double c[K], s[K], xv[K][POL];
+            load_pix_keep(pix, t0, nt, p);
+#pragma unroll
+            for (int j = 0; j < K; ++j) if (t0 + j < a || t0 + j >= b) p[j] = -1;
+            if (POL > 1) { load_f64_keep(cs, t0, nt, c); load_f64_keep(sn, t0, nt, s); }
+            gather_x<POL>(x, p, xv);
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const double dv = p[j] >= 0 ? project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0) : 0.0;
+                if (p[j] >= 0) { sum += dv; cnt += 1.0; }
+                if (fits) sd[t0 + j - base] = dv;
+            }
+        }
+        const double tsum = block_sum(sum, red);
+        const double tcnt = block_sum(cnt, red);
+        if (threadIdx.x == 0) {
+            s_skip = !(tcnt > 0.0);
+            s_mean = tcnt > 0.0 ? tsum / tcnt : 0.0;
+        }
+        __syncthreads();
+        if (!s_skip) {
+            const double mu = s_mean;
+            for (int64_t tile = tile0 + warp; tile < tile1; tile += BLOCK / 32) {
+                const int64_t t0 = tile * TILE + (int64_t)lane * K;
+                int p[K];
+                double c[K], s[K], v[K];
+                load_pix(pix, t0, nt, p);
+#pragma unroll
+                for (int j = 0; j < K; ++j) if (t0 + j < a || t0 + j >= b) p[j] = -1;
+                if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
+                if (fits) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) v[j] = sd[t0 + j - base] - mu;
+                } else {
+                    double xv[K][POL];
+                    gather_x<POL>(x, p, xv);
+#pragma unroll
+                    for (int j = 0; j < K; ++j)
+                        v[j] = project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0) - mu;
+                }
+                run_scatter<POL, POL>(y, p, [&](int j, double (&o)[POL]) {
+                    if constexpr (POL == 1) { o[0] = v[j]; }
+                    else if constexpr (POL == 2) { o[0] = v[j] * c[j]; o[1] = v[j] * s[j]; }
+                    else { o[0] = v[j]; o[1] = v[j] * c[j]; o[2] = v[j] * s[j]; }
+                });
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <class Kern>
+static int tod_grid(Kern k, int64_t nt) {
+    int64_t ntiles = (nt + TILE - 1) / TILE;
+    int64_t blocks = (ntiles + (BLOCK / 32) - 1) / (BLOCK / 32);
+    return persistent_grid(k, BLOCK, 0, blocks);
+}
+
+static int check_tod(const void *pix, const void *c, const void *s, int64_t nt, int pol) {
+    if (nt < 0) return set_error(CM2_ERR_ARG, "nt < 0");
+    if (pol < 1 || pol > 3) return set_error(CM2_ERR_ARG, "No valid polarization key set! pol=%d (1=I, 2=QU, 3=IQU)", pol);
+    if (nt > 0 && pix == nullptr) return set_error(CM2_ERR_ARG, "pix is NULL");
+    if (pol > 1 && nt > 0 && (c == nullptr || s == nullptr)) return set_error(CM2_ERR_ARG, "cos/sin required for pol>1");
+    if (!aligned(pix, 32) || !aligned(c, 32) || !aligned(s, 32))
+        return set_error(CM2_ERR_ARG, "TOD arrays must be 32-byte aligned");
+    return CM2_OK;
+}
+
+}  // namespace cm2
+
+using namespace cm2;
+
+extern "C" int cm2_pointing_apply(const int32_t *pix, const double *c, const double *s, int64_t nt, int pol,
+                                  const double *x, double *d, cm2_stream_t stream) {
+    int rc = check_tod(pix, c, s, nt, pol);
+    if (rc) return rc;
+    CM2_REQUIRE(aligned(d, 32), "d must be 32-byte aligned");
+    if (nt == 0) return CM2_OK;
+    cudaStream_t st = as_stream(stream);
+    if (pol == 1) k_pointing_apply<1><<<tod_grid(k_pointing_apply<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, x, d);
+    else if (pol == 2) k_pointing_apply<2><<<tod_grid(k_pointing_apply<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, x, d);
+    else k_pointing_apply<3><<<tod_grid(k_pointing_apply<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, x, d);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+extern "C" int cm2_pointing_apply_t(const int32_t *pix, const double *c, const double *s, int64_t nt, int pol,
+                                    const double *d, double *y, int64_t npix, cm2_stream_t stream) {
+    int rc = check_tod(pix, c, s, nt, pol);
+    if (rc) return rc;
+    CM2_REQUIRE(aligned(d, 32), "d must be 32-byte aligned");
+    CM2_REQUIRE(npix >= 0, "npix < 0");
+    cudaStream_t st = as_stream(stream);
+    if (npix > 0) CM2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)npix * pol, st));
+    if (nt == 0 || npix == 0) return CM2_OK;
+    if (pol == 1) k_pointing_apply_t<1><<<tod_grid(k_pointing_apply_t<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, d, y);
+    else if (pol == 2) k_pointing_apply_t<2><<<tod_grid(k_pointing_apply_t<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, d, y);
+    else k_pointing_apply_t<3><<<tod_grid(k_pointing_apply_t<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, d, y);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+static int check_blocks(const double *wblk, int64_t nblocks, int64_t blocksize, const int64_t *blk_start) {
+    if (wblk == nullptr) return CM2_OK;
+    if (nblocks <= 0) return set_error(CM2_ERR_ARG, "nblocks must be > 0 when weights are given");
+    if (blk_start == nullptr && blocksize <= 0) return set_error(CM2_ERR_ARG, "blocksize must be > 0");
+    return CM2_OK;
+}
+
+extern "C" int cm2_amatvec_white(const int32_t *pix, const double *c, const double *s, int64_t nt, int pol,
+                                 const double *wblk, int64_t nblocks, int64_t blocksize, const int64_t *blk_start,
+                                 const double *x, double *y, int64_t npix, cm2_stream_t stream) {
+    int rc = check_tod(pix, c, s, nt, pol);
+    if (rc) return rc;
+    rc = check_blocks(wblk, nblocks, blocksize, blk_start);
+    if (rc) return rc;
+    CM2_REQUIRE(npix >= 0, "npix < 0");
+    cudaStream_t st = as_stream(stream);
+    if (npix > 0) CM2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)npix * pol, st));
+    if (nt == 0 || npix == 0) return CM2_OK;
+    BlockW bw{wblk, nblocks, blocksize, blk_start};
+    if (pol == 1) k_amatvec_white<1><<<tod_grid(k_amatvec_white<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, x, y);
+    else if (pol == 2) k_amatvec_white<2><<<tod_grid(k_amatvec_white<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, x, y);
+    else k_amatvec_white<3><<<tod_grid(k_amatvec_white<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, x, y);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+extern "C" int cm2_weights_moments(const int32_t *pix, const double *c, const double *s, const double *w,
+                                   const double *wblk, int64_t nblocks, int64_t blocksize, const int64_t *blk_start,
+                                   int64_t nt, int pol, double *mom, int64_t npix, cm2_stream_t stream) {
+    int rc = check_tod(pix, c, s, nt, pol);
+    if (rc) return rc;
+    rc = check_blocks(wblk, nblocks, blocksize, blk_start);
+    if (rc) return rc;
+    CM2_REQUIRE(aligned(w, 32), "w must be 32-byte aligned");
+    CM2_REQUIRE(npix >= 0, "npix < 0");
+    cudaStream_t st = as_stream(stream);
+    if (npix > 0) CM2_CUDA(cudaMemsetAsync(mom, 0, sizeof(double) * 6 * (size_t)npix, st));
+    if (nt == 0 || npix == 0) return CM2_OK;
+    BlockW bw{wblk, nblocks, blocksize, blk_start};
+    if (pol == 1) k_moments<1><<<tod_grid(k_moments<1>, nt), BLOCK, 0, st>>>(pix, c, s, w, bw, nt, mom);
+    else if (pol == 2) k_moments<2><<<tod_grid(k_moments<2>, nt), BLOCK, 0, st>>>(pix, c, s, w, bw, nt, mom);
+    else k_moments<3><<<tod_grid(k_moments<3>, nt), BLOCK, 0, st>>>(pix, c, s, w, bw, nt, mom);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+extern "C" int cm2_hits_i64(const int32_t *pix, int64_t nt, int64_t npix, int64_t *hits, cm2_stream_t stream) {
+    CM2_REQUIRE(nt >= 0 && npix >= 0, "negative size");
+    CM2_REQUIRE(aligned(pix, 32), "pix must be 32-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    if (npix > 0) CM2_CUDA(cudaMemsetAsync(hits, 0, sizeof(int64_t) * (size_t)npix, st));
+    if (nt == 0 || npix == 0) return CM2_OK;
+    k_hits<<<tod_grid(k_hits, nt), BLOCK, 0, st>>>(pix, nt, reinterpret_cast<unsigned long long *>(hits));
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+extern "C" int cm2_amatvec_filter(const int32_t *pix, const double *c, const double *s, int64_t nt, int pol,
+                                  const int64_t *seg_start, const int64_t *seg_end, int64_t nseg, const double *x,
+                                  double *y, int64_t npix, cm2_stream_t stream) {
+    int rc = check_tod(pix, c, s, nt, pol);
+    if (rc) return rc;
+    CM2_REQUIRE(npix >= 0 && nseg >= 0, "negative size");
+    cudaStream_t st = as_stream(stream);
+    if (npix > 0) CM2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)npix * pol, st));
+    if (nt == 0 || npix == 0 || nseg == 0) return CM2_OK;
+    const size_t smem = sizeof(double) * SEG_SMEM;
+    if (pol == 1) {
+        CM2_CUDA(cudaFuncSetAttribute(k_amatvec_filter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_amatvec_filter<1><<<persistent_grid(k_amatvec_filter<1>, BLOCK, smem, nseg), BLOCK, smem, st>>>(pix, c, s, nt, seg_start, seg_end, nseg, x, y);
+    } else if (pol == 2) {
+        CM2_CUDA(cudaFuncSetAttribute(k_amatvec_filter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_amatvec_filter<2><<<persistent_grid(k_amatvec_filter<2>, BLOCK, smem, nseg), BLOCK, smem, st>>>(pix, c, s, nt, seg_start, seg_end, nseg, x, y);
+    } else {
+        CM2_CUDA(cudaFuncSetAttribute(k_amatvec_filter<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_amatvec_filter<3><<<persistent_grid(k_amatvec_filter<3>, BLOCK, smem, nseg), BLOCK, smem, st>>>(pix, c, s, nt, seg_start, seg_end, nseg, x, y);
+    }
+    CM2_LAUNCHED();
+    return CM2_OK;
+}

@@ -1,0 +1,671 @@
+"""
+Drop-in operator classes for the map-making hot path, with the names, constructor signatures and
+attributes of the reference's ``interfaces/linearoperators.py`` / ``interfaces/blkop.py``.
+
+Every ``mult``/``rmult`` below is a CUDA kernel behind the C ABI (include/cosmomap2_b200.h); the
+classes only own device buffers and describe the launch.  There is no CPU path.
+"""
+import numpy as np
+import torch
+from scipy.linalg import eigh, lu_factor, lu_solve
+
+from . import _device as dv
+from . import linop as lp
+from .process_ces import BlockWeights, ProcessTimeSamples  # noqa: F401
+
+
+def _stream():
+    return dv.stream()
+
+
+# =============================================================================================
+# pointing
+# =============================================================================================
+class SparseLO(lp.LinearOperator):
+    """Pointing operator P (nt x pol*npix) and P^T -- interfaces/linearoperators.py:326-557.
+
+    ``SparseLO(n, m, pix_samples, pol=1, angle_processed=None)``; attributes ``ncols, nrows, pol,
+    pairs, cos, sin, maptype``.  The device image of ``pix_samples`` is taken at construction
+    (the reference aliases the caller's array, :531).
+    """
+
+    def __init__(self, n, m, pix_samples, pol=1, angle_processed=None):
+        dv.require_cuda()
+        self.ncols = int(n)
+        self.nrows = int(m)
+        self.pol = pol
+        self.pairs = pix_samples
+        if pol not in (1, 2, 3):
+            raise RuntimeError("No valid polarization key set!\t=>\tpol=%d \n \
+                                    Possible values are pol=%d(I),%d(QU), %d(IQU)." % (pol, 1, 2, 3))
+        if len(pix_samples) != self.nrows:
+            raise lp.ShapeError("pix_samples must have one pixel per time sample")
+        self._angles = angle_processed
+        self._pix_dev = dv.pix_to_dev(pix_samples)
+        self._cos_dev = self._sin_dev = None
+        if pol > 1:
+            c = getattr(angle_processed, "_cos_dev", None)
+            if c is not None:
+                self._cos_dev, self._sin_dev = angle_processed._cos_dev, angle_processed._sin_dev
+            else:
+                self._cos_dev = dv.to_dev_f64(angle_processed.cos)
+                self._sin_dev = dv.to_dev_f64(angle_processed.sin)
+        self._sorted = None
+        self.__runcase = {1: "I", 2: "QU", 3: "IQU"}[pol]
+        super(SparseLO, self).__init__(nargin=self.pol * self.ncols, nargout=self.nrows, matvec=self.mult,
+                                       rmatvec=self.rmult, symmetric=False, device=True)
+
+    # reference attribute names; host copies are made on demand
+    @property
+    def cos(self):
+        return self._angles.cos
+
+    @property
+    def sin(self):
+        return self._angles.sin
+
+    @property
+    def maptype(self):
+        return self.__runcase
+
+    def mult(self, v):                                    # :356-384, 411-438, 463-497
+        d = dv.empty_f64(self.nrows)
+        dv.call("cm2_pointing_apply", dv.ptr(self._pix_dev), dv.ptr(self._cos_dev), dv.ptr(self._sin_dev),
+                self.nrows, self.pol, dv.ptr(v), dv.ptr(d), _stream())
+        return d
+
+    mult_qu = mult_iqu = mult
+
+    def rmult(self, v):                                   # :385-410, 439-462, 498-526
+        y = dv.empty_f64(self.ncols * self.pol)
+        dv.call("cm2_pointing_apply_t", dv.ptr(self._pix_dev), dv.ptr(self._cos_dev), dv.ptr(self._sin_dev),
+                self.nrows, self.pol, dv.ptr(v), dv.ptr(y), self.ncols, _stream())
+        return y
+
+    rmult_qu = rmult_iqu = rmult
+
+    # -- deterministic transpose (pixel-sorted, no atomics) ---------------------------------------
+    def build_sorted(self):
+        """Stable argsort of the samples by pixel (flagged dropped) for ``rmult_sorted``."""
+        if self._sorted is None:
+            pix = self._pix_dev
+            order = torch.sort(pix, stable=True).indices            # one-off set-up
+            nflag = int((pix < 0).sum().item())
+            perm = order[nflag:].to(torch.int32).contiguous()
+            counts = torch.bincount(pix[pix >= 0].to(torch.int64), minlength=self.ncols)
+            rowptr = torch.zeros(self.ncols + 1, dtype=torch.int64, device=pix.device)
+            rowptr[1:] = torch.cumsum(counts, 0)
+            self._sorted = (rowptr, perm)
+        return self._sorted
+
+    def rmult_sorted(self, v):
+        rowptr, perm = self.build_sorted()
+        v = dv.to_dev_f64(v)
+        y = dv.empty_f64(self.ncols * self.pol)
+        dv.call("cm2_pointing_apply_t_sorted", dv.ptr(rowptr), dv.ptr(perm), dv.ptr(self._cos_dev),
+                dv.ptr(self._sin_dev), self.pol, dv.ptr(v), dv.ptr(y), self.ncols, _stream())
+        return y
+
+    def hits(self):
+        out = torch.empty(max(self.ncols, 1), dtype=torch.int64, device=self._pix_dev.device)
+        dv.call("cm2_hits_i64", dv.ptr(self._pix_dev), self.nrows, self.ncols, dv.ptr(out), _stream())
+        return dv.to_host(out[:self.ncols])
+
+
+# =============================================================================================
+# noise
+# =============================================================================================
+def _block_starts(blocksize, nblocks):
+    if np.ndim(blocksize):
+        sizes = np.asarray(blocksize, dtype=np.int64)
+        if len(sizes) != nblocks:
+            raise ValueError("need one block size per noise value")
+    else:
+        sizes = np.full(nblocks, int(blocksize), dtype=np.int64)
+    return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+
+
+class _Blocks(object):
+    """Device description of the block partition of the TOD."""
+
+    def __init__(self, starts):
+        self.starts = np.asarray(starts, dtype=np.int64)
+        self.n = len(self.starts) - 1
+        sizes = np.diff(self.starts)
+        self.blocksize = int(sizes[0]) if self.n and np.all(sizes == sizes[0]) else 0
+        self.nt = int(self.starts[-1])
+        self._dev = None
+
+    def args(self):
+        """(nblocks, blocksize, blk_start_ptr)"""
+        if self.blocksize == 0 and self._dev is None:
+            self._dev = dv.to_dev(self.starts, torch.int64)
+        return self.n, self.blocksize, dv.ptr(self._dev)
+
+
+class ToeplitzLO(lp.LinearOperator):
+    """Symmetric banded Toeplitz block, zero boundaries -- interfaces/linearoperators.py:560-602."""
+
+    def __init__(self, a, size):
+        self.array = a
+        self._blocks = _Blocks([0, int(size)])
+        self._band_dev = None
+        super(ToeplitzLO, self).__init__(nargin=size, nargout=size, matvec=self.mult, symmetric=True,
+                                         device=True)
+
+    def mult(self, v):                                    # :582-595
+        if self._band_dev is None:
+            self._band_dev = dv.to_dev_f64(np.atleast_1d(np.asarray(self.array, dtype=np.float64)))
+        return _toeplitz_apply(self._band_dev, self._band_dev.numel(), self._blocks, v)
+
+
+def _toeplitz_apply(band_dev, nband, blocks, v):
+    out = torch.empty_like(v)
+    nb, bs, startp = blocks.args()
+    scratch = torch.empty(nb + 1, dtype=torch.int64, device=v.device)
+    dv.call("cm2_noise_toeplitz_apply", dv.ptr(band_dev), int(nband), nb, bs, startp, dv.ptr(v), dv.ptr(out),
+            v.numel(), dv.ptr(scratch), _stream())
+    return out
+
+
+class WeightingLO(lp.LinearOperator):
+    """Per-(CES, detector) scalar weight -- interfaces/linearoperators.py:604-625.
+    The reference scales ``d`` IN PLACE and returns it (:613); so does this."""
+
+    def __init__(self, bolos_per_ces, samples_per_bolopair, weights):
+        self.ndet_pairs = bolos_per_ces
+        self.nsample_per_pair = samples_per_bolopair
+        self.size = int(np.sum([i * j for i, j in zip(samples_per_bolopair, bolos_per_ces)]))
+        self.weights = np.asarray(weights, dtype=np.float64)
+        sizes = np.concatenate([np.full(int(b), int(ns)) for b, ns in zip(bolos_per_ces, samples_per_bolopair)])
+        self._blocks = _Blocks(np.concatenate([[0], np.cumsum(sizes)]))
+        self._w_dev = None
+        super(WeightingLO, self).__init__(nargin=self.size, nargout=self.size, matvec=self.mult,
+                                          symmetric=True, device=True)
+
+    def mult(self, d):
+        if self._w_dev is None:
+            self._w_dev = dv.to_dev_f64(self.weights[:self._blocks.n])
+        nb, bs, startp = self._blocks.args()
+        dv.call("cm2_noise_white_apply", dv.ptr(self._w_dev), nb, bs, startp, dv.ptr(d), dv.ptr(d), d.numel(),
+                _stream())
+        return d
+
+    def matvec(self, x):
+        if isinstance(x, np.ndarray) and x.ndim == 1 and x.dtype == np.float64:
+            y = super(WeightingLO, self).matvec(x)
+            x[...] = y                                     # in-place semantics of the reference
+            return x
+        return super(WeightingLO, self).matvec(x)
+
+
+class BlockDiagonalLinearOperator(lp.LinearOperator):
+    """Generic block-diagonal of operators -- interfaces/blkop.py:140-242 (kept for API
+    compatibility; BlockLO overrides the application with single-launch kernels)."""
+
+    def __init__(self, blocks, **kwargs):
+        try:
+            for block in blocks:
+                block.shape
+        except (TypeError, AttributeError):
+            raise ValueError("blocks should be a flattened list of operators")
+        self._blocks_list = blocks
+        nargin = sum(b.shape[-1] for b in blocks)
+        nargout = sum(b.shape[0] for b in blocks)
+        symmetric = all(b.symmetric for b in blocks)
+        kwargs.pop("symmetric", None)
+        super(BlockDiagonalLinearOperator, self).__init__(
+            nargin, nargout, symmetric=symmetric, matvec=lambda x: self._blk_apply(x, False),
+            rmatvec=lambda x: self._blk_apply(x, True), device=True, **kwargs)
+
+    def _blk_apply(self, x, transpose):
+        outs = []
+        c0 = 0
+        for B in self._blocks_list:
+            op = B.T if transpose else B
+            c1 = c0 + op.shape[-1]
+            outs.append(op._apply(dv.to_dev_f64(x[c0:c1])))
+            c0 = c1
+        return torch.cat(outs)
+
+    @property
+    def blocks(self):
+        return self._blocks_list
+
+    def __getitem__(self, idx):
+        blks = self._blocks_list[idx]
+        if isinstance(idx, slice):
+            return BlockDiagonalLinearOperator(blks)
+        return blks
+
+
+class BlockLO(BlockDiagonalLinearOperator):
+    """N^-1 as a block-diagonal operator -- interfaces/linearoperators.py:627-697.
+
+    ``BlockLO(blocksize, t, offdiag=False)``; attributes ``blocklist, diag, covnoise, isoffdiag,
+    blocksize``.  ``offdiag=False``: block i is ``t[i]`` times the identity and ``diag`` is the
+    per-sample weight vector (a lazy ``BlockWeights``).  ``offdiag=True``: block i is the banded
+    Toeplitz of ``t[i]``.  ``blocksize`` may be a list of per-block sizes (the intent of
+    tests/test_toeplitz_vector_multiplication.py:12).  One kernel launch applies all blocks.
+    """
+
+    def __init__(self, blocksize, t, offdiag=False):
+        self.__isoffdiag = offdiag
+        self.blocksize = blocksize
+        self.covnoise = t
+        nb = len(t)
+        self._blk = _Blocks(_block_starts(blocksize, nb))
+        self._blocklist = None
+        if offdiag:
+            bands = [np.atleast_1d(np.asarray(a, dtype=np.float64)) for a in t]
+            self._nband = max(len(a) for a in bands)
+            band = np.zeros((nb, self._nband))
+            for i, a in enumerate(bands):
+                band[i, :len(a)] = a
+            self._band_host = band
+            self._band_dev = None
+            self.diag = bands[0].copy()                  # linearoperators.py:673 (sic: t[0] only)
+        else:
+            self._w_host = np.asarray([float(v) for v in t], dtype=np.float64)
+            self._w_dev = None
+            self.diag = BlockWeights(self._w_host, self._blk.starts)
+        nt = self._blk.nt
+        lp.LinearOperator.__init__(self, nt, nt, matvec=self._apply_all, rmatvec=self._apply_all,
+                                   symmetric=True, device=True)
+
+    @property
+    def isoffdiag(self):
+        return self.__isoffdiag
+
+    @property
+    def blocklist(self):
+        if self._blocklist is None:
+            sizes = np.diff(self._blk.starts)
+            if self.isoffdiag:
+                self._blocklist = [ToeplitzLO(a, int(sz)) for a, sz in zip(self.covnoise, sizes)]
+            else:
+                self._blocklist = [lp.DiagonalOperator(np.full(int(sz), v)) for v, sz in zip(self._w_host, sizes)]
+        return self._blocklist
+
+    @property
+    def blocks(self):
+        return self.blocklist
+
+    _blocks_list = property(lambda self: self.blocklist)
+
+    def weights_dev(self):
+        if self._w_dev is None:
+            self._w_dev = dv.to_dev_f64(self._w_host)
+        return self._w_dev
+
+    def _apply_all(self, x):
+        if x.numel() != self._blk.nt:
+            raise lp.ShapeError("Multiplying with vector of wrong shape.")
+        nb, bs, startp = self._blk.args()
+        if self.isoffdiag:
+            if self._band_dev is None:
+                self._band_dev = dv.to_dev_f64(self._band_host.reshape(-1))
+            return _toeplitz_apply(self._band_dev, self._nband, self._blk, x)
+        out = torch.empty_like(x)
+        dv.call("cm2_noise_white_apply", dv.ptr(self.weights_dev()), nb, bs, startp, dv.ptr(x), dv.ptr(out),
+                x.numel(), _stream())
+        return out
+
+
+class FilterLO(lp.LinearOperator):
+    """Subscan offset filter (poly_order=0) -- interfaces/linearoperators.py:94-168, 263-282.
+
+    Same constructor; the (CES, detector, subscan) triple loop of the reference is flattened at
+    construction into one list of segments [start, end) and one kernel launch applies them all.
+    """
+
+    def __init__(self, size, subscan_nsample, samples_per_bolopair, bolos_per_ces, pix_samples,
+                 poly_order=0, npool=4):
+        dv.require_cuda()
+        self.n = size
+        self.nsamples = samples_per_bolopair
+        self.nbolos = bolos_per_ces
+        self.subscans = subscan_nsample[0]
+        self.tstart = subscan_nsample[1]
+        if not (type(self.nsamples) is list):
+            self.nsamples = [self.nsamples]
+            self.nbolos = [self.nbolos]
+            self.subscans = [self.subscans]
+            self.tstart = [self.tstart]
+        self.pixels = pix_samples
+        self.poly_order = poly_order
+        if poly_order != 0:
+            raise NotImplementedError("Legendre filtering (poly_order>0) is outside the accelerated hot path")
+        starts, ends = [], []
+        offset = 0
+        for subsc, ts, ns, nb in zip(self.subscans, self.tstart, self.nsamples, self.nbolos):
+            subsc = np.asarray(subsc, dtype=np.int64)
+            ts = np.asarray(ts, dtype=np.int64)
+            det0 = offset + int(ns) * np.arange(int(nb), dtype=np.int64)       # :139
+            s = (det0[:, None] + ts[None, :]).reshape(-1)
+            starts.append(s)
+            ends.append(s + np.tile(subsc, int(nb)))
+            offset += int(nb) * int(ns)
+        self._seg_start_host = np.concatenate(starts) if starts else np.zeros(0, dtype=np.int64)
+        self._seg_end_host = np.concatenate(ends) if ends else np.zeros(0, dtype=np.int64)
+        if len(self._seg_end_host) and (self._seg_end_host.max() > size or self._seg_start_host.min() < 0):
+            raise lp.ShapeError("subscan table exceeds the TOD size")
+        self._seg_start = dv.to_dev(self._seg_start_host, torch.int64)
+        self._seg_end = dv.to_dev(self._seg_end_host, torch.int64)
+        self.nseg = len(self._seg_start_host)
+        self._pix_dev = dv.pix_to_dev(pix_samples)
+        super(FilterLO, self).__init__(nargin=size, nargout=size, matvec=self.mult, symmetric=False,
+                                       device=True)
+
+    def mult(self, d):                                    # :129-168
+        out = torch.empty_like(d)
+        dv.call("cm2_filter_offset_apply", dv.ptr(self._pix_dev), dv.ptr(self._seg_start), dv.ptr(self._seg_end),
+                self.nseg, dv.ptr(d), dv.ptr(out), d.numel(), _stream())
+        return out
+
+
+# =============================================================================================
+# fused A-matvecs: the factor chains [P.T, P], [P.T, N_white, P], [P.T, F, P] collapse to one
+# kernel without a TOD temporary
+# =============================================================================================
+class _FusedWhiteA(lp.LinearOperator):
+    def __init__(self, P, N):
+        self.P, self.N = P, N
+        n = P.pol * P.ncols
+        super(_FusedWhiteA, self).__init__(n, n, matvec=self._run, symmetric=True, device=True)
+
+    def _run(self, x):
+        P = self.P
+        y = dv.empty_f64(P.ncols * P.pol)
+        if self.N is None:
+            w, nb, bs, startp = None, 0, 0, None
+        else:
+            w = dv.ptr(self.N.weights_dev())
+            nb, bs, startp = self.N._blk.args()
+        dv.call("cm2_amatvec_white", dv.ptr(P._pix_dev), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.nrows, P.pol,
+                w, nb, bs, startp, dv.ptr(x), dv.ptr(y), P.ncols, _stream())
+        return y
+
+
+class _FusedFilterA(lp.LinearOperator):
+    def __init__(self, P, F):
+        self.P, self.F = P, F
+        n = P.pol * P.ncols
+        super(_FusedFilterA, self).__init__(n, n, matvec=self._run, symmetric=True, device=True)
+
+    def _run(self, x):
+        P, F = self.P, self.F
+        y = dv.empty_f64(P.ncols * P.pol)
+        dv.call("cm2_amatvec_filter", dv.ptr(P._pix_dev), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.nrows, P.pol,
+                dv.ptr(F._seg_start), dv.ptr(F._seg_end), F.nseg, dv.ptr(x), dv.ptr(y), P.ncols, _stream())
+        return y
+
+
+def _is_pt(op):
+    return getattr(op, "_adjoint_of", None) is not None and isinstance(op._adjoint_of, SparseLO)
+
+
+fusion_enabled = True
+
+
+@lp.register_fuser
+def _fuse_pointing(factors):
+    if not fusion_enabled:
+        return None
+    n = len(factors)
+    for i in range(n):
+        if not _is_pt(factors[i]):
+            continue
+        P = factors[i]._adjoint_of
+        # [P.T, P]
+        if i + 1 < n and factors[i + 1] is P:
+            return factors[:i] + [_FusedWhiteA(P, None)] + factors[i + 2:]
+        if i + 2 < n and factors[i + 2] is P:
+            mid = factors[i + 1]
+            if isinstance(mid, BlockLO) and not mid.isoffdiag and mid.shape[0] == P.nrows:
+                return factors[:i] + [_FusedWhiteA(P, mid)] + factors[i + 3:]
+            if (isinstance(mid, FilterLO) and mid.shape[0] == P.nrows
+                    and mid._pix_dev.data_ptr() == P._pix_dev.data_ptr()):
+                return factors[:i] + [_FusedFilterA(P, mid)] + factors[i + 3:]
+    return None
+
+
+# =============================================================================================
+# block-diagonal preconditioner
+# =============================================================================================
+def _moments_from(CES, n, pol):
+    """Device [n][6] moment table {h,c,s,c2,cs,s2} from a ProcessTimeSamples (device-resident)
+    or from any object exposing the reference's attribute arrays."""
+    mom = getattr(CES, "_mom_dev", None)
+    if mom is not None and getattr(CES, "pol", pol) == pol and mom.numel() >= 6 * n:
+        return mom
+    tab = np.zeros((max(n, 1), 6))
+    if pol in (1, 3):
+        tab[:n, 0] = np.asarray(CES.counts)[:n]
+    if pol == 3:
+        tab[:n, 1] = np.asarray(CES.cosine)[:n]
+        tab[:n, 2] = np.asarray(CES.sine)[:n]
+    if pol in (2, 3):
+        tab[:n, 3] = np.asarray(CES.cos2)[:n]
+        tab[:n, 4] = np.asarray(CES.sincos)[:n]
+        tab[:n, 5] = np.asarray(CES.sin2)[:n]
+    return dv.to_dev_f64(tab.reshape(-1))
+
+
+class _PixelBlockLO(lp.LinearOperator):
+    def _attrs_from(self, CES, n, pol):
+        self.size = pol * n
+        self.pixels = np.arange(n)
+        self.pol = pol
+        self._n = int(n)
+        self._ces = CES
+        self._mom_dev = _moments_from(CES, n, pol)
+
+    # reference attribute names (linearoperators.py:717-726, 847-856)
+    counts = property(lambda self: self._ces.counts)
+    sin2 = property(lambda self: self._ces.sin2)
+    cos2 = property(lambda self: self._ces.cos2)
+    sincos = property(lambda self: self._ces.sincos)
+    cos = property(lambda self: self._ces.cosine)
+    sin = property(lambda self: self._ces.sine)
+
+
+class BlockDiagonalLO(_PixelBlockLO):
+    """Explicit P^T diag(N^-1) P, one small block per pixel -- linearoperators.py:700-746."""
+
+    def __init__(self, CES, n, pol=1):
+        dv.require_cuda()
+        self._attrs_from(CES, n, pol)
+        super(BlockDiagonalLO, self).__init__(nargin=self.size, nargout=self.size, matvec=self.mult,
+                                              symmetric=True, device=True)
+
+    def mult(self, x):
+        y = torch.empty_like(x)
+        dv.call("cm2_bdfwd_apply", dv.ptr(self._mom_dev), self._n, self.pol, dv.ptr(x), dv.ptr(y), _stream())
+        return y
+
+
+class BlockDiagonalPreconditionerLO(_PixelBlockLO):
+    """M_BD = (P^T diag(N^-1) P)^-1, closed-form per-pixel inverse -- linearoperators.py:749-859.
+    The inverse blocks are computed once at construction (the reference recomputes the determinant
+    and the mask at every call, :792-795) with the same absolute threshold |det| > 1e-5."""
+
+    def __init__(self, CES, n, pol=1):
+        dv.require_cuda()
+        self._attrs_from(CES, n, pol)
+        self._inv_dev = torch.empty(max(self._n, 1) * 6, dtype=torch.float64, device=self._mom_dev.device)
+        dv.call("cm2_bd_build", dv.ptr(self._mom_dev), self._n, pol, dv.ptr(self._inv_dev), _stream())
+        super(BlockDiagonalPreconditionerLO, self).__init__(nargin=self.size, nargout=self.size,
+                                                            matvec=self.mult, symmetric=True, device=True)
+
+    def mult(self, x):                                    # :775-841
+        y = torch.empty_like(x)
+        dv.call("cm2_bd_apply", dv.ptr(self._inv_dev), self._n, self.pol, dv.ptr(x), dv.ptr(y), _stream())
+        return y
+
+
+class InverseLO(lp.LinearOperator):
+    """A solver wrapped as the operator A^-1 -- interfaces/linearoperators.py:861-941."""
+
+    def mult(self, x):
+        y, info = self.method(self.A, x, M=self.preconditioner)
+        self.isconverged(info)
+        return y
+
+    def isconverged(self, info):
+        self.__converged = info
+        return info == 0
+
+    def __init__(self, A, method=None, preconditioner=None):
+        super(InverseLO, self).__init__(nargin=A.shape[0], nargout=A.shape[1], matvec=self.mult,
+                                        symmetric=True, device=True)
+        self.A = A
+        self.__method = method
+        self.__preconditioner = preconditioner
+        self.__converged = None
+
+    method = property(lambda self: self.__method)
+    converged = property(lambda self: self.__converged)
+    preconditioner = property(lambda self: self.__preconditioner)
+
+
+# =============================================================================================
+# deflation / coarse operator / two-level preconditioner
+# =============================================================================================
+def _columns_dev(z):
+    """n x r matrix (NumPy, np.matrix or CUDA tensor) -> (r, n) row-contiguous CUDA tensor, i.e.
+    column-major n x r with ld = n, as the kernels read it."""
+    if isinstance(z, torch.Tensor):
+        return dv.to_dev_f64(z.t())
+    return dv.to_dev_f64(np.ascontiguousarray(np.asarray(z, dtype=np.float64).T))
+
+
+class DeflationLO(lp.LinearOperator):
+    """Z y and Z^T x -- interfaces/linearoperators.py:1029-1065."""
+
+    def __init__(self, z):
+        dv.require_cuda()
+        self.nrows, self.ncols = z.shape
+        self._z_host = None if isinstance(z, torch.Tensor) else np.asarray(z)
+        self._zt = _columns_dev(z)
+        self._work = dv.empty_f64(int(dv.call("cm2_defl_work_doubles", int(self.ncols))))
+        super(DeflationLO, self).__init__(nargin=self.ncols, nargout=self.nrows, matvec=self.mult,
+                                          rmatvec=self.rmult, symmetric=False, device=True)
+
+    @property
+    def z(self):
+        src = self._z_host if self._z_host is not None else dv.to_host(self._zt).T
+        return [src[:, j] for j in range(self.ncols)]
+
+    def mult(self, x):                                    # :1041-1050
+        y = dv.empty_f64(self.nrows)
+        dv.call("cm2_defl_z_apply", dv.ptr(self._zt), self.nrows, self.ncols, self.nrows, dv.ptr(x), 1.0, 0.0,
+                None, dv.ptr(y), _stream())
+        return y
+
+    def rmult(self, x):                                   # :1051-1056
+        out = dv.empty_f64(self.ncols)
+        dv.call("cm2_defl_zt_apply", dv.ptr(self._zt), self.nrows, self.ncols, self.nrows, dv.ptr(x), 1,
+                self.nrows, dv.ptr(out), dv.ptr(self._work), _stream())
+        return out
+
+
+class CoarseLO(lp.LinearOperator):
+    """E = Z^T A Z and the action of E^-1 -- interfaces/linearoperators.py:946-1027.
+
+    E (r x r) is accumulated on the device from Z and AZ; its r x r factorisation (LU, or eigh with
+    eigenvalues |lambda/lambda_max| < 1e-6 discarded, :994-1015) is host LAPACK, and the resulting
+    r x r inverse is applied on the device.
+    """
+
+    def __init__(self, Z, Az, r, apply="LU"):
+        dv.require_cuda()
+        zt = _columns_dev(Z)
+        azt = _columns_dev(Az)
+        n = zt.shape[1]
+        work = dv.empty_f64(int(dv.call("cm2_defl_work_doubles", int(r))))
+        e_dev = dv.empty_f64(r * r)
+        dv.call("cm2_defl_zt_apply", dv.ptr(zt), n, int(r), n, dv.ptr(azt), int(r), n, dv.ptr(e_dev),
+                dv.ptr(work), _stream())
+        self.E = dv.to_host(e_dev).reshape(r, r).T.copy()         # column-major r x r -> E[i, j]
+        self.r = int(r)
+        self.apply = apply
+        if apply == "eig":
+            self.setting_inverse_w_eigenvalues(self.E)
+        elif apply == "LU":
+            self._lu = lu_factor(self.E, check_finite=False)
+            self.invE = lu_solve(self._lu, np.eye(self.r), check_finite=False)
+        else:
+            raise ValueError("apply must be 'LU' or 'eig'")
+        self._einv_dev = dv.to_dev_f64(np.asfortranarray(self.invE).reshape(-1, order="F"))
+        super(CoarseLO, self).__init__(nargin=r, nargout=r, matvec=self.mult, symmetric=True, device=True)
+
+    def setting_inverse_w_eigenvalues(self, E):            # :986-1015
+        eigenvals, W = eigh(E)
+        lambda_max = max(eigenvals)
+        diags = eigenvals * 0.
+        nondegenerate = np.where(abs(eigenvals / lambda_max) > 1.e-6)[0]
+        self.ndiscarded = len(eigenvals) - len(nondegenerate)
+        diags[nondegenerate] = 1. / eigenvals[nondegenerate]
+        self.invE = (W * diags[None, :]).dot(W.T)
+
+    def mult(self, v):                                    # :969-984
+        c = dv.empty_f64(self.r)
+        dv.call("cm2_coarse_apply", dv.ptr(self._einv_dev), self.r, dv.ptr(v), dv.ptr(c), _stream())
+        return c
+
+    mult_eig = mult
+
+
+class TwoLevelPreconditionerLO(lp.LinearOperator):
+    """M_2lvl = M_BD (I - AZ E^-1 Z^T) + Z E^-1 Z^T as ONE fused apply.
+
+    The reference composes it with operator algebra (src/test_M2_precond_onto_real_data.py:109-112),
+    which evaluates ``E*Zd.T*v`` twice; the algebraic composition still works with the classes
+    above, and ``_fuse_two_level`` below rewrites it into this operator.
+    """
+
+    def __init__(self, Mbd, Zd, AZd, E):
+        self.Mbd, self.Zd, self.AZd, self.E = Mbd, Zd, AZd, E
+        n = Zd.nrows
+        self._work = dv.empty_f64(int(dv.call("cm2_defl_work_doubles", int(Zd.ncols))))
+        super(TwoLevelPreconditionerLO, self).__init__(n, n, matvec=self.mult, symmetric=True, device=True)
+
+    def mult(self, v):
+        Zd, M = self.Zd, self.Mbd
+        y = torch.empty_like(v)
+        dv.call("cm2_m2_apply", dv.ptr(Zd._zt), dv.ptr(self.AZd._zt), Zd.nrows, Zd.ncols, Zd.nrows,
+                dv.ptr(self.E._einv_dev), dv.ptr(M._inv_dev), M._n, M.pol, dv.ptr(v), dv.ptr(y),
+                dv.ptr(self._work), _stream())
+        return y
+
+
+def _is_zt(op, Zd=None):
+    z = getattr(op, "_adjoint_of", None)
+    return isinstance(z, DeflationLO) and (Zd is None or z is Zd)
+
+
+@lp.register_sum_fuser
+def _fuse_two_level(sum_op):
+    """Recognise  Mbd*(I - AZd*E*Zd.T) + Zd*E*Zd.T  (src/test_M2_precond_onto_real_data.py:109-112)."""
+    if not fusion_enabled or sum_op.sign != 1.0:
+        return None
+    a, b = sum_op.a, sum_op.b
+    if not (isinstance(a, lp._ProductLO) and isinstance(b, lp._ProductLO)):
+        return None
+    fb = b.factors
+    if not (len(fb) == 3 and isinstance(fb[0], DeflationLO) and isinstance(fb[1], CoarseLO) and _is_zt(fb[2], fb[0])):
+        return None
+    Zd, E = fb[0], fb[1]
+    fa = a.factors
+    if not (len(fa) == 2 and isinstance(fa[0], BlockDiagonalPreconditionerLO) and isinstance(fa[1], lp._SumLO)):
+        return None
+    R = fa[1]
+    if not (R.sign == -1.0 and isinstance(R.a, lp.IdentityOperator) and isinstance(R.b, lp._ProductLO)):
+        return None
+    fr = R.b.factors
+    if not (len(fr) == 3 and isinstance(fr[0], DeflationLO) and fr[1] is E and _is_zt(fr[2], Zd)):
+        return None
+    if fr[0].nrows != Zd.nrows or fr[0].ncols != Zd.ncols or fa[0].size != Zd.nrows:
+        return None
+    return TwoLevelPreconditionerLO(fa[0], Zd, fr[0], E)

@@ -1,0 +1,172 @@
+/*
+ * cosmomap2_b200 -- C ABI of the B200-native map-making hot path.
+ *
+ * The reference (giuspugl/COSMOMAP2) has no C ABI: its inner loops are C++ snippets JIT-compiled
+ * by weave.inline from Python.  Each entry point below replaces one of those loops (or the
+ * NumPy/BLAS code next to it); the reference site is cited as file:line relative to the
+ * reference tree.  INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer (HBM) unless the
+ *     name ends in _host; the library never owns caller buffers;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream;
+ *   - return value: 0 = ok, negative = error (cm2_last_error() gives the text); nothing throws;
+ *   - maps are interleaved per pixel ([I0,Q0,U0,I1,...] for pol=3, [Q0,U0,...] for pol=2),
+ *     fp64; pixel indices are int32, -1 = flagged sample (skipped everywhere);
+ *   - TOD vectors are CES-major, detector-major, time-minor (linearoperators.py:134-140).
+ */
+#ifndef COSMOMAP2_B200_H
+#define COSMOMAP2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CM2_OK 0
+#define CM2_ERR_ARG (-1)
+#define CM2_ERR_CUDA (-2)
+#define CM2_ERR_UNSUPPORTED (-3)
+
+typedef void *cm2_stream_t;
+
+/* ---- library ------------------------------------------------------------------------- */
+int cm2_version(void);
+const char *cm2_last_error(void);
+/* SM count, L2 bytes and compute capability (major*10+minor) of the current device */
+int cm2_device_info(int *sm_count, int64_t *l2_bytes, int *cc);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t cm2_launch_count(void);
+
+/* ---- a1/a2: pointing operator (interfaces/linearoperators.py:356-526) -------------------- */
+/* d[t] = x[p] | x[2p]c+x[2p+1]s | x[3p]+x[3p+1]c+x[3p+2]s ; flagged -> 0   (:368-375,424-430,483-489) */
+int cm2_pointing_apply(const int32_t *pix, const double *cos2phi, const double *sin2phi,
+                       int64_t nt, int pol, const double *x, double *d, cm2_stream_t stream);
+/* y = P^T d, y zero-filled first (:394-401, 447-454, 509-517); warp-aggregated atomics */
+int cm2_pointing_apply_t(const int32_t *pix, const double *cos2phi, const double *sin2phi,
+                         int64_t nt, int pol, const double *d, double *y, int64_t npix,
+                         cm2_stream_t stream);
+/* deterministic P^T d: samples visited in pixel-sorted order (perm = stable argsort of pix with
+ * the flagged samples removed, rowptr[npix+1] = first entry of each pixel); one warp per pixel,
+ * fixed summation order, no atomics */
+int cm2_pointing_apply_t_sorted(const int64_t *rowptr, const int32_t *perm,
+                                const double *cos2phi, const double *sin2phi, int pol,
+                                const double *d, double *y, int64_t npix, cm2_stream_t stream);
+/* integer hit counts, bit-exact (tests/test_matrix_vector_product.py:9-23) */
+int cm2_hits_i64(const int32_t *pix, int64_t nt, int64_t npix, int64_t *hits,
+                 cm2_stream_t stream);
+
+/* ---- a6/a7: ProcessTimeSamples (utilities/process_ces.py:58-555) -------------------------- */
+/* cos2phi = cos(2 phi), sin2phi = sin(2 phi)   (:493-494) */
+int cm2_angles(const double *phi, int64_t nt, double *cos2phi, double *sin2phi,
+               cm2_stream_t stream);
+/* narrow caller pixels (int64 host convention) to the device int32 layout and back */
+int cm2_pix_narrow(const int64_t *pix64, int64_t nt, int32_t *pix32, cm2_stream_t stream);
+int cm2_pix_widen(const int32_t *pix32, int64_t nt, int64_t *pix64, cm2_stream_t stream);
+/* weighted per-pixel moments, interleaved mom[npix][6] = {h, c, s, c2, cs, s2} (the upper
+ * triangle of [[h,c,s],[c,c2,cs],[s,cs,s2]]); mom zero-filled first.  Weights: per-sample `w`
+ * (the reference's w=N.diag), else per-block `wblk` as in cm2_noise_white_apply, else (both
+ * NULL) unit weights   (:480-486, 505-513, 527-538, 125-189) */
+int cm2_weights_moments(const int32_t *pix, const double *cos2phi, const double *sin2phi,
+                        const double *w, const double *wblk, int64_t nblocks, int64_t blocksize,
+                        const int64_t *blk_start, int64_t nt, int pol, double *mom, int64_t npix,
+                        cm2_stream_t stream);
+/* good-pixel flags (:491, 544-555): pol=1 h>0; pol=2 cond<=thr; pol=3 cond<=thr && h>2 */
+int cm2_weights_mask(const double *mom, int64_t npix, int pol, double threshold_cond,
+                     int32_t *good, cm2_stream_t stream);
+/* exclusive scan of good[] -> old2new (-1 where dropped); *npix_new_dev receives the count.
+ * scratch: at least cm2_scan_scratch_bytes(npix) bytes   (replaces the O(Nold*Nmask) search :192-349) */
+int64_t cm2_scan_scratch_bytes(int64_t n);
+int cm2_weights_old2new(const int32_t *good, int64_t npix, int32_t *old2new,
+                        int64_t *npix_new_dev, void *scratch, cm2_stream_t stream);
+/* compact per-pixel rows: dst[old2new[j]][0..width) = src[j][0..width) for kept j (fp64 rows) */
+int cm2_compact_rows_f64(const double *src, const int32_t *old2new, int64_t npix, int width,
+                         double *dst, cm2_stream_t stream);
+int cm2_compact_rows_i64(const int64_t *src, const int32_t *old2new, int64_t npix, int width,
+                         int64_t *dst, cm2_stream_t stream);
+/* pix[t] = old2new[pix[t]] in place, flagged stay -1   (:411-417) */
+int cm2_relabel(int32_t *pix, int64_t nt, const int32_t *old2new, cm2_stream_t stream);
+
+/* ---- a8/a9: block-diagonal preconditioner (interfaces/linearoperators.py:700-859) --------- */
+/* inv[npix][6] = upper triangle of the per-pixel inverse block (or zeros where masked:
+ * pol=1 h<=0, pol=2/3 |det|<=1e-5), from mom[npix][6]   (:789-801, 820-826) */
+int cm2_bd_build(const double *mom, int64_t npix, int pol, double *inv, cm2_stream_t stream);
+/* y = M_BD x with the packed inverse blocks   (:796-806, 822-831) */
+int cm2_bd_apply(const double *inv, int64_t npix, int pol, const double *x, double *y,
+                 cm2_stream_t stream);
+/* y = (P^T diag(N^-1) P) x, the forward per-pixel block   (:728-746) */
+int cm2_bdfwd_apply(const double *mom, int64_t npix, int pol, const double *x, double *y,
+                    cm2_stream_t stream);
+
+/* ---- a3/a4/a5: noise operators ------------------------------------------------------------ */
+/* white: out[t] = w[block(t)] * d[t]; equal blocks of `blocksize` when blk_start is NULL, else
+ * block b = [blk_start[b], blk_start[b+1])   (linearoperators.py:676-683, blkop.py:178-208,
+ * WeightingLO :606-617).  in-place allowed (out == d). */
+int cm2_noise_white_apply(const double *wblk, int64_t nblocks, int64_t blocksize,
+                          const int64_t *blk_start, const double *d, double *out, int64_t nt,
+                          cm2_stream_t stream);
+/* banded symmetric Toeplitz per block, zero boundaries (ToeplitzLO.mult :582-595):
+ * band[b*nband + k] = a_k of block b; blocks as above */
+int64_t cm2_toeplitz_scratch_bytes(int64_t nblocks);
+int cm2_noise_toeplitz_apply(const double *band, int nband, int64_t nblocks, int64_t blocksize,
+                             const int64_t *blk_start, const double *d, double *out, int64_t nt,
+                             void *scratch, cm2_stream_t stream);
+/* subscan offset filter (FilterLO.mult :129-168): out = 0; for each segment [seg_start[k],
+ * seg_end[k]): mu = mean of d over unflagged samples; skipped if none; out = d - mu */
+int cm2_filter_offset_apply(const int32_t *pix, const int64_t *seg_start, const int64_t *seg_end,
+                            int64_t nseg, const double *d, double *out, int64_t nt,
+                            cm2_stream_t stream);
+
+/* ---- fused A-matvecs (no TOD temporary) ---------------------------------------------------- */
+/* y = P^T diag(w) P x   (the composition P.T*N*P at tests/test_toeplitz_vector_multiplication.py:28) */
+int cm2_amatvec_white(const int32_t *pix, const double *cos2phi, const double *sin2phi,
+                      int64_t nt, int pol, const double *wblk, int64_t nblocks,
+                      int64_t blocksize, const int64_t *blk_start, const double *x, double *y,
+                      int64_t npix, cm2_stream_t stream);
+/* y = P^T F P x with the offset filter (src/test_M2_precond_onto_real_data.py:86) */
+int cm2_amatvec_filter(const int32_t *pix, const double *cos2phi, const double *sin2phi,
+                       int64_t nt, int pol, const int64_t *seg_start, const int64_t *seg_end,
+                       int64_t nseg, const double *x, double *y, int64_t npix,
+                       cm2_stream_t stream);
+
+/* ---- a10/a11/a13: deflation, coarse operator, two-level preconditioner ---------------------- */
+/* Z is n x r, column-major (column i at Z + i*ldz), as DeflationLO stores columns (:1058-1062).
+ * `work`: cm2_defl_work_doubles(r) doubles of device scratch. */
+int64_t cm2_defl_work_doubles(int r);
+/* out[i] = Z[:,i] . x  (DeflationLO.rmult :1056); for ncols_x > 1: out = Z^T X, r x ncols_x
+ * column-major (used for E = Z^T (A Z), CoarseLO :1019).  Deterministic reduction. */
+int cm2_defl_zt_apply(const double *Z, int64_t n, int r, int64_t ldz, const double *X,
+                      int ncols_x, int64_t ldx, double *out, double *work, cm2_stream_t stream);
+/* y = beta*y0 + alpha * Z c  (DeflationLO.mult :1047-1050); y0 may be NULL */
+int cm2_defl_z_apply(const double *Z, int64_t n, int r, int64_t ldz, const double *c,
+                     double alpha, double beta, const double *y0, double *y,
+                     cm2_stream_t stream);
+/* c = Einv (r x r, column-major, device) * v  (CoarseLO.mult_eig :984) */
+int cm2_coarse_apply(const double *Einv, int r, const double *v, double *c,
+                     cm2_stream_t stream);
+/* fused two-level apply (src/test_M2_precond_onto_real_data.py:109-112):
+ *   c = Einv Z^T v ;  y = M_BD (v - AZ c) + Z c    (reads Z twice, AZ once) */
+int cm2_m2_apply(const double *Z, const double *AZ, int64_t n, int r, int64_t ld,
+                 const double *Einv, const double *bd_inv, int64_t npix, int pol,
+                 const double *v, double *y, double *work, cm2_stream_t stream);
+
+/* ---- a14: PCG vector work (scipy _isolve/iterative.py:405-431) ------------------------------- */
+/* out[0] = a.b */
+int cm2_dot(const double *a, const double *b, int64_t n, double *out, cm2_stream_t stream);
+/* y = alpha*x + beta*y  (alpha, beta host scalars) */
+int cm2_axpby(double alpha, const double *x, double beta, double *y, int64_t n,
+              cm2_stream_t stream);
+/* device-scalar PCG updates; scal[] is an 8-double device workspace:
+ *   [0]=rho [1]=rho_prev [2]=p.q [3]=|r|^2 [4]=alpha [5]=beta [6],[7] caller-owned
+ * step A: rho = r.z ; beta = rho/rho_prev (0 on first) ; p = z + beta p            */
+int cm2_pcg_update_p(const double *r, const double *z, double *p, int64_t n, double *scal,
+                     int first, cm2_stream_t stream);
+/* step B: pq = p.q ; alpha = rho/pq ; x += alpha p ; r -= alpha q ; |r|^2 ; rho_prev = rho */
+int cm2_pcg_update_xr(const double *p, const double *q, double *x, double *r, int64_t n,
+                      double *scal, cm2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COSMOMAP2_B200_H */

@@ -230,20 +230,44 @@ class ProcessTimeSamples(object):
 # --------------------------------------------------------------------------------------------
 
 
+USE_C_LOOPS = True   # route the per-sample loops through oracle/weave_loops.c when it is built
+
+
+def _c():
+    return USE_C_LOOPS and cloops.available()
+
+
 class SparseLO(lp.LinearOperator):
-    """interfaces/linearoperators.py:326-557 -- pointing operator P and its transpose."""
+    """interfaces/linearoperators.py:326-557 -- pointing operator P and its transpose.
+    Two equivalent restatements: NumPy (bincount adds in sample order) and the plain-C twin of
+    the weave loops (oracle/weave_loops.c); tests/test_oracle_golden.py checks they agree bit for
+    bit.  The C twin is what bench.py times as the CPU baseline."""
+
+    def _cmult(self, v):
+        return cloops.pointing_mult(self.pairs, getattr(self, "cos", None), getattr(self, "sin", None),
+                                    self.pol, np.ascontiguousarray(v, dtype=np.float64))
+
+    def _crmult(self, v):
+        return cloops.pointing_rmult(self.pairs, getattr(self, "cos", None), getattr(self, "sin", None),
+                                     self.pol, np.ascontiguousarray(v, dtype=np.float64), self.ncols)
 
     def mult(self, v):                                   # :356-384
+        if _c():
+            return self._cmult(v)
         x = np.zeros(self.nrows)
         g = self.pairs != -1
         x[g] = v[self.pairs[g]]
         return x
 
     def rmult(self, v):                                  # :385-410
+        if _c():
+            return self._crmult(v)
         g = self.pairs != -1
         return np.bincount(self.pairs[g], weights=v[g], minlength=self.ncols).astype(np.float64)
 
     def mult_qu(self, v):                                # :411-438
+        if _c():
+            return self._cmult(v)
         x = np.zeros(self.nrows)
         g = self.pairs != -1
         p = self.pairs[g]
@@ -251,6 +275,8 @@ class SparseLO(lp.LinearOperator):
         return x
 
     def rmult_qu(self, v):                               # :439-462
+        if _c():
+            return self._crmult(v)
         out = np.zeros(self.ncols * self.pol)
         g = self.pairs != -1
         p = self.pairs[g]
@@ -259,6 +285,8 @@ class SparseLO(lp.LinearOperator):
         return out
 
     def mult_iqu(self, v):                               # :463-497
+        if _c():
+            return self._cmult(v)
         x = np.zeros(self.nrows)
         g = self.pairs != -1
         p = self.pairs[g]
@@ -266,6 +294,8 @@ class SparseLO(lp.LinearOperator):
         return x
 
     def rmult_iqu(self, v):                              # :498-526
+        if _c():
+            return self._crmult(v)
         out = np.zeros(self.ncols * self.pol)
         g = self.pairs != -1
         p = self.pairs[g]
@@ -531,6 +561,11 @@ class BlockDiagonalPreconditionerLO(lp.LinearOperator):
     """interfaces/linearoperators.py:749-859 -- M_BD = (P^T diag(N^-1) P)^-1, closed form."""
 
     def mult(self, x):                                   # :775-841
+        if _c() and self.pol in (2, 3):
+            n = self.size // self.pol
+            g = lambda nm: np.ascontiguousarray(getattr(self, nm), dtype=np.float64) if hasattr(self, nm) else None  # noqa: E731
+            return cloops.bd_apply(n, self.pol, g("counts"), g("cos"), g("sin"), g("cos2"), g("sin2"),
+                                   g("sincos"), np.ascontiguousarray(x, dtype=np.float64))
         y = x * 0.
         if self.pol == 1:
             m = self.counts > 0

@@ -1,0 +1,190 @@
+"""GPU parity against the oracle on seeded inputs at sizes the oracle finishes in seconds, plus
+size-independent properties (hit counts, symmetry, M_BD A = I for white noise, fused == unfused,
+atomic == sorted P^T) and the edge cases the reference's tests exercise."""
+import numpy as np
+import pytest
+
+import golden_cases as gc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cm():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import cosmomap2_b200
+    return cosmomap2_b200
+
+
+def _raster(nt=400000, ndet=8, seed=3, **kw):
+    from cosmomap2_b200 import synthetic
+    return synthetic.raster_scan(nt, nside=64, ndet=ndet, nx=90, ny=50, samples_per_pixel=6.0, seed=seed, **kw)
+
+
+@pytest.mark.parametrize("pol", [1, 2, 3])
+def test_raster_scan_against_oracle(cm, pol):
+    import oracle
+    sc = _raster(flag_turnarounds=True)
+    res = []
+    for impl in (oracle, cm):
+        pix = sc.pix.astype(np.int64)
+        N = impl.BlockLO(sc.ns, sc.weights, offdiag=False)
+        pts = impl.ProcessTimeSamples(pix, sc.npix_full, pol=pol, phi=sc.phi, w=N.diag)
+        npix = pts.get_new_pixel[0]
+        P = impl.SparseLO(npix, sc.nt, pix, pol=pol, angle_processed=pts)
+        Mbd = impl.BlockDiagonalPreconditionerLO(pts, npix, pol=pol)
+        rng = np.random.default_rng(5)
+        x = rng.standard_normal(pol * npix)
+        A = P.T * N * P
+        res.append(dict(pix=pix, npix=npix, obspix=np.asarray(pts.get_new_pixel[1]), Px=P * x,
+                        Ax=A * x, b=P.T * (N * sc.d), MAx=Mbd * (A * x), x=x))
+    o, g = res
+    assert o["npix"] == g["npix"]
+    gc.exact(g["pix"], o["pix"], "relabelled pixels")
+    gc.exact(g["obspix"], o["obspix"], "obspix")
+    for k in ("Px", "Ax", "b", "MAx"):
+        gc.close(g[k], o[k], what=k)
+    # white noise with w = N.diag: M_BD A = I on every kept pixel (tests/test_matrix_vector_product.py:65-94)
+    gc.close(g["MAx"], g["x"], rtol=1e-9, what="M_BD A x = x")
+
+
+def test_hit_counts_bit_exact(cm):
+    import oracle
+    sc = _raster(nt=300000)
+    pix_o = sc.pix.astype(np.int64)
+    pix_g = sc.pix.astype(np.int64)
+    po = oracle.ProcessTimeSamples(pix_o, sc.npix_full)
+    pg = cm.ProcessTimeSamples(pix_g, sc.npix_full)
+    n = pg.get_new_pixel[0]
+    assert n == po.get_new_pixel[0]
+    ref = np.bincount(pix_o[pix_o >= 0], minlength=n)
+    assert np.array_equal(pg.hits(), ref)
+    assert np.array_equal(np.asarray(pg.counts).astype(np.int64), ref)
+    # P^T P 1 == counts (tests/test_matrix_vector_product.py:9-23)
+    P = cm.SparseLO(n, sc.nt, pix_g)
+    y = P.T * (P * np.ones(n))
+    assert np.array_equal(y, ref.astype(np.float64))
+    assert np.array_equal(P.hits(), ref)
+
+
+@pytest.mark.parametrize("pol", [1, 2, 3])
+def test_fused_equals_unfused_and_sorted(cm, pol):
+    from cosmomap2_b200 import linearoperators as lo
+    sc = _raster(nt=250000, ndet=5, flag_turnarounds=True)
+    pix = sc.pix.astype(np.int64)
+    N = cm.BlockLO(sc.ns, sc.weights)
+    pts = cm.ProcessTimeSamples(pix, sc.npix_full, pol=pol, phi=sc.phi, w=N.diag)
+    npix = pts.get_new_pixel[0]
+    P = cm.SparseLO(npix, sc.nt, pix, pol=pol, angle_processed=pts)
+    F = cm.FilterLO(sc.nt, [sc.sub_len, sc.sub_start], sc.ns, sc.ndet, pix)
+    x = np.random.default_rng(1).standard_normal(pol * npix)
+    for mid in (N, F, None):
+        A = (P.T * mid * P) if mid is not None else (P.T * P)
+        fused = A * x
+        assert any(isinstance(f, (lo._FusedWhiteA, lo._FusedFilterA)) for f in A.planned())
+        unfused = P.T * ((mid * (P * x)) if mid is not None else (P * x))
+        gc.close(fused, unfused, what="fused vs unfused")
+        gc.close(A.T * x, fused, what="A symmetric")
+    d = sc.d
+    gc.close(P.rmult_sorted(d).cpu().numpy(), P.T * d, what="sorted P^T vs atomic P^T")
+    # the sorted path is deterministic: two runs are bit-identical
+    assert np.array_equal(P.rmult_sorted(d).cpu().numpy(), P.rmult_sorted(d).cpu().numpy())
+
+
+def test_edge_cases(cm):
+    # empty TOD
+    pts = cm.ProcessTimeSamples(np.zeros(0, dtype=np.int64), 5)
+    assert pts.get_new_pixel[0] == 0
+    # everything flagged
+    pix = np.full(1000, -1, dtype=np.int64)
+    pts = cm.ProcessTimeSamples(pix, 7, pol=3, phi=np.zeros(1000))
+    assert pts.get_new_pixel[0] == 0 and np.all(pix == -1)
+    # ragged sizes around the 256-sample tile and 8-sample chunk
+    import oracle
+    for nt in (1, 7, 8, 9, 255, 256, 257, 1023):
+        rng = np.random.default_rng(nt)
+        pix = rng.integers(0, 5, nt)
+        phi = rng.random(nt)
+        po, pg = pix.copy(), pix.copy()
+        a = oracle.ProcessTimeSamples(po, 5, pol=3, phi=phi)
+        b = cm.ProcessTimeSamples(pg, 5, pol=3, phi=phi)
+        assert a.get_new_pixel[0] == b.get_new_pixel[0]
+        gc.exact(pg, po)
+        n = a.get_new_pixel[0]
+        if n == 0:
+            continue
+        Po = oracle.SparseLO(n, nt, po, pol=3, angle_processed=a)
+        Pg = cm.SparseLO(n, nt, pg, pol=3, angle_processed=b)
+        x = rng.standard_normal(3 * n)
+        d = rng.standard_normal(nt)
+        gc.close(Pg * x, Po * x)
+        gc.close(Pg.T * d, Po.T * d)
+        gc.close((Pg.T * Pg) * x, Po.T * (Po * x))
+    # errors the reference raises
+    with pytest.raises(RuntimeError):
+        cm.SparseLO(3, 3, np.arange(3), pol=4)
+    P = cm.SparseLO(3, 3, np.arange(3))
+    with pytest.raises(cm.lp.ShapeError):
+        P * np.ones(5)
+    N = cm.BlockLO(4, [1.0, 2.0])
+    with pytest.raises(cm.lp.ShapeError):
+        N * np.ones(9)
+
+
+def test_toeplitz_wide_band_and_variable_blocks(cm):
+    import oracle
+    rng = np.random.default_rng(9)
+    sizes = 2 * [500, 400, 124]                       # tests/test_toeplitz_vector_multiplication.py:11
+    nt = sum(sizes)
+    v = rng.standard_normal(nt)
+    t = [rng.random(3) for _ in sizes]
+    gc.close(cm.BlockLO(sizes, t, offdiag=True) * v, oracle.BlockLO(sizes, t, offdiag=True) * v)
+    tw = rng.random(len(sizes))
+    gc.close(cm.BlockLO(sizes, tw) * v, oracle.BlockLO(sizes, tw) * v)
+    # band wider than the tile and wider than a block
+    n = 5000
+    v = rng.standard_normal(n)
+    for L in (1500, 4096):
+        a = rng.random(L) / L
+        a[0] = 1.0
+        gc.close(cm.ToeplitzLO(a, n) * v, oracle.ToeplitzLO(a, n) * v, what="Toeplitz L=%d" % L)
+    a = rng.random(300)
+    gc.close(cm.ToeplitzLO(a, 100) * v[:100], oracle.ToeplitzLO(a, 100) * v[:100], what="band > block")
+
+
+def test_krypy_style_arnoldi_and_two_level(cm):
+    """Preconditioned Arnoldi (krypy semantics): V^T P = I, M A V_m = V_{m+1} H, Ritz values against
+    dense eigh of the explicit pencil; then M_2lvl built from it deflates the small modes."""
+    import scipy.linalg as la
+    g = gc.load("solve_pol3")
+    pol, npix, P, N, Mbd, B, A, b = gc.build_solve_system(cm, g)
+    n = pol * npix
+    V, H, m = cm.run_krypy_arnoldi(A, np.ones(n), Mbd, 1e-5, maxiter=40)
+    Vg, Hg, Pg = cm.krypy_arnoldi(A, np.ones(n), M=Mbd, maxiter=40)
+    assert np.max(np.abs(Vg.T.dot(Pg) - np.eye(Vg.shape[1]))) < 1e-10
+    k = Hg.shape[1]
+    MAV = np.column_stack([Mbd * (A * Vg[:, j]) for j in range(k)])
+    gc.close(MAV, Vg.dot(Hg), rtol=1e-9, what="M A V_m = V_{m+1} H")
+    theta = la.eigvalsh(Hg[:k, :k])
+    Ad, Bd = A.to_array(), B.to_array()
+    lam = la.eigh(Ad, Bd, eigvals_only=True)
+    assert abs(theta.min() - lam.min()) < 1e-3 * abs(lam.min()) + 1e-8
+    assert theta.max() <= lam.max() * (1 + 1e-8)
+    Z, r, th = cm.find_ritz_eigenvalues(Hg, Vg, threshold=np.sort(theta)[4] * 1.0001, eigenvalues=True)
+    assert r == 5
+    Az = np.column_stack([A * Z[:, i] for i in range(r)])
+    E = cm.CoarseLO(Z, Az, r, apply="eig")
+    Zd, AZd = cm.DeflationLO(Z), cm.DeflationLO(Az)
+    M2 = Mbd * (cm.lp.IdentityOperator(n) - AZd * E * Zd.T) + Zd * E * Zd.T
+    from cosmomap2_b200.linearoperators import TwoLevelPreconditionerLO
+    M2f = TwoLevelPreconditionerLO(Mbd, Zd, AZd, E)
+    v = np.random.default_rng(0).standard_normal(n)
+    gc.close(M2 * v, M2f * v, what="algebraic M2 == fused M2")
+    for i in range(r):
+        assert np.allclose(M2 * Az[:, i], Z[:, i])
+    it_bd, it_m2 = [], []
+    cm.cg(A, b, M=Mbd, rtol=1e-10, maxiter=500, residuals=it_bd)
+    cm.cg(A, b, M=M2, rtol=1e-10, maxiter=500, residuals=it_m2)
+    assert len(it_m2) <= len(it_bd)

@@ -37,8 +37,9 @@ def test_oracle_solve(pol):
 
 def test_c_loops_match_numpy_restatement():
     """oracle/weave_loops.c (the timed CPU baseline) agrees with oracle/operators.py."""
-    from oracle import cloops
+    from oracle import cloops, operators
     assert cloops.available()
+    operators.USE_C_LOOPS = False        # compare the C twin against the pure NumPy restatement
     rng = np.random.default_rng(3)
     nt, npix = 5000, 40
     pix = rng.integers(0, npix, nt)
@@ -65,3 +66,18 @@ def test_c_loops_match_numpy_restatement():
     y = cloops.bd_apply(pts.get_new_pixel[0], 3, pts.counts, pts.cosine, pts.sine, pts.cos2,
                         pts.sin2, pts.sincos, x)
     gc.close(y, Mbd * x, rtol=1e-13, what="bd apply")
+    operators.USE_C_LOOPS = True
+
+
+@pytest.mark.parametrize("use_c", [False, True])
+def test_oracle_golden_both_restatements(use_c):
+    """Both restatements (NumPy and C) reproduce the reference's golden vectors."""
+    from oracle import operators
+    old = operators.USE_C_LOOPS
+    operators.USE_C_LOOPS = use_c
+    try:
+        gc.check_pointing(oracle, "pointing_pol3_w")
+        gc.check_pointing(oracle, "pointing_pol2_u")
+        gc.check_pointing(oracle, "pointing_pol1_w")
+    finally:
+        operators.USE_C_LOOPS = old
