@@ -131,73 +131,96 @@ __device__ __forceinline__ void emit(double *__restrict__ y, int pix, const doub
     }
 }
 
-// Run-compressed, warp-merged scatter-add of K samples per lane.  contrib(j, out[NV]) yields the
-// NV values sample j adds to pixel p[j].  All 32 lanes must call (shuffles use the full mask).
+// Run-compressed, warp-merged scatter-add of K samples per lane, in two phases so that a kernel
+// can issue the next tile's loads between them:
+//   run_compress: each lane folds its K samples into runs; complete interior runs are emitted,
+//                 the first and the last (open) run stay in registers (RunState);
+//   run_merge   : open runs are merged across lanes with a segmented shuffle scan and emitted.
+// contrib(j, out[NV]) yields the NV values sample j adds to pixel p[j].  All 32 lanes must call.
+template <int NV>
+struct RunState {
+    double acc[NV];    // partial of the run open at the end of the lane (== the only run if single)
+    double head[NV];   // partial of the lane's first run (when the lane holds more than one run)
+    int ph, pt;        // pixel of the first / last run
+    bool single;
+};
+
 template <int NV, int STRIDE, class F>
-__device__ __forceinline__ void run_scatter(double *__restrict__ y, const int (&p)[K], F contrib) {
-    const int lane = threadIdx.x & 31;
-    double acc[NV], head[NV];
+__device__ __forceinline__ void run_compress(double *__restrict__ y, const int (&p)[K], F contrib, RunState<NV> &rs) {
     int cur = p[0];
-    bool single = true;
-    contrib(0, acc);
+    rs.single = true;
+    contrib(0, rs.acc);
 #pragma unroll
-    for (int k = 0; k < NV; ++k) head[k] = 0.0;
+    for (int k = 0; k < NV; ++k) rs.head[k] = 0.0;
 #pragma unroll
     for (int j = 1; j < K; ++j) {
         double v[NV];
         contrib(j, v);
         if (p[j] != cur) {
-            if (single) {
+            if (rs.single) {
 #pragma unroll
-                for (int k = 0; k < NV; ++k) head[k] = acc[k];
-                single = false;
+                for (int k = 0; k < NV; ++k) rs.head[k] = rs.acc[k];
+                rs.single = false;
             } else {
-                emit<NV, STRIDE>(y, cur, acc);
+                emit<NV, STRIDE>(y, cur, rs.acc);
             }
             cur = p[j];
 #pragma unroll
-            for (int k = 0; k < NV; ++k) acc[k] = v[k];
+            for (int k = 0; k < NV; ++k) rs.acc[k] = v[k];
         } else {
 #pragma unroll
-            for (int k = 0; k < NV; ++k) acc[k] += v[k];
+            for (int k = 0; k < NV; ++k) rs.acc[k] += v[k];
         }
     }
-    const int ph = p[0], pt = cur;
-    const int pt_prev = __shfl_up_sync(FULL, pt, 1);
-    const int ph_next = __shfl_down_sync(FULL, ph, 1);
-    const bool cont_prev = (lane > 0) && (pt_prev == ph);   // my first run continues the previous lane's last
-    const bool cont_next = (lane < 31) && (ph_next == pt);  // my last run continues into the next lane
-    // segmented inclusive scan of the open partial (acc) over lanes; a lane starts a segment
-    // unless it is one single run that continues the previous lane
-    bool f = !(single && cont_prev);
+    rs.ph = p[0];
+    rs.pt = cur;
+}
+
+template <int NV, int STRIDE>
+__device__ __forceinline__ void run_merge(double *__restrict__ y, RunState<NV> &rs) {
+    const int lane = threadIdx.x & 31;
+    const int pt_prev = __shfl_up_sync(FULL, rs.pt, 1);
+    const int ph_next = __shfl_down_sync(FULL, rs.ph, 1);
+    const bool cont_prev = (lane > 0) && (pt_prev == rs.ph);   // my first run continues the previous lane's last
+    const bool cont_next = (lane < 31) && (ph_next == rs.pt);  // my last run continues into the next lane
+    // segmented inclusive scan of the open partial over lanes; a lane starts a segment unless it
+    // is one single run that continues the previous lane
+    bool f = !(rs.single && cont_prev);
     if (__any_sync(FULL, !f)) {
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             double up[NV];
 #pragma unroll
-            for (int k = 0; k < NV; ++k) up[k] = __shfl_up_sync(FULL, acc[k], d);
+            for (int k = 0; k < NV; ++k) up[k] = __shfl_up_sync(FULL, rs.acc[k], d);
             const int fu = __shfl_up_sync(FULL, (int)f, d);
             if (lane >= d) {
                 if (!f) {
 #pragma unroll
-                    for (int k = 0; k < NV; ++k) acc[k] += up[k];
+                    for (int k = 0; k < NV; ++k) rs.acc[k] += up[k];
                 }
                 f = f || (fu != 0);
             }
         }
     }
-    // acc = partial of the run that is open at the end of this lane (carry-out)
+    // rs.acc = partial of the run that is open at the end of this lane (carry-out)
     double cin[NV];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) cin[k] = __shfl_up_sync(FULL, acc[k], 1);
-    if (!single) {
+    for (int k = 0; k < NV; ++k) cin[k] = __shfl_up_sync(FULL, rs.acc[k], 1);
+    if (!rs.single) {
         if (cont_prev) {
 #pragma unroll
-            for (int k = 0; k < NV; ++k) head[k] += cin[k];
+            for (int k = 0; k < NV; ++k) rs.head[k] += cin[k];
         }
-        emit<NV, STRIDE>(y, ph, head);
+        emit<NV, STRIDE>(y, rs.ph, rs.head);
     }
-    if (!cont_next) emit<NV, STRIDE>(y, pt, acc);
+    if (!cont_next) emit<NV, STRIDE>(y, rs.pt, rs.acc);
+}
+
+template <int NV, int STRIDE, class F>
+__device__ __forceinline__ void run_scatter(double *__restrict__ y, const int (&p)[K], F contrib) {
+    RunState<NV> rs;
+    run_compress<NV, STRIDE>(y, p, contrib, rs);
+    run_merge<NV, STRIDE>(y, rs);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -253,6 +276,8 @@ __global__ void __launch_bounds__(BLOCK) k_pointing_apply_t(const int32_t *__res
     }
 }
 
+// Fused y = P^T diag(w) P x.  The next tile's pix/cos/sin loads are issued between the compress
+// and the merge phase of the current tile, so their DRAM latency overlaps the shuffles and REDs.
 template <int POL>
 __global__ void __launch_bounds__(BLOCK) k_amatvec_white(const int32_t *__restrict__ pix, const double *__restrict__ cs,
                                                          const double *__restrict__ sn, int64_t nt, BlockW bw,
@@ -260,21 +285,37 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_white(const int32_t *__restri
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
     const int64_t ntiles = (nt + TILE - 1) / TILE;
-    for (int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
+    int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+    if (tile >= ntiles) return;
+    int p[K];
+    double c[K], s[K];
+    {
         const int64_t t0 = tile * TILE + (int64_t)lane * K;
-        int p[K];
-        double c[K], s[K], w[K], xv[K][POL], v[K];
         load_pix(pix, t0, nt, p);
         if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
-        gather_x<POL>(x, p, xv);
-        chunk_weights(bw, t0 < nt ? t0 : nt - 1, nt, w);
+    }
+    for (; tile < ntiles; tile += nwarps) {
+        const int64_t t0 = tile * TILE + (int64_t)lane * K;
+        RunState<POL> rs;
+        {
+            double w[K], xv[K][POL], v[K];
+            gather_x<POL>(x, p, xv);
+            chunk_weights(bw, t0 < nt ? t0 : nt - 1, nt, w);
 #pragma unroll
-        for (int j = 0; j < K; ++j) v[j] = w[j] * project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0);
-        run_scatter<POL, POL>(y, p, [&](int j, double (&o)[POL]) {
-            if constexpr (POL == 1) { o[0] = v[j]; }
-            else if constexpr (POL == 2) { o[0] = v[j] * c[j]; o[1] = v[j] * s[j]; }
-            else { o[0] = v[j]; o[1] = v[j] * c[j]; o[2] = v[j] * s[j]; }
-        });
+            for (int j = 0; j < K; ++j) v[j] = w[j] * project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0);
+            run_compress<POL, POL>(y, p, [&](int j, double (&o)[POL]) {
+                if constexpr (POL == 1) { o[0] = v[j]; }
+                else if constexpr (POL == 2) { o[0] = v[j] * c[j]; o[1] = v[j] * s[j]; }
+                else { o[0] = v[j]; o[1] = v[j] * c[j]; o[2] = v[j] * s[j]; }
+            }, rs);
+        }
+        const int64_t nxt = tile + nwarps;
+        if (nxt < ntiles) {   // warp-uniform
+            const int64_t t1 = nxt * TILE + (int64_t)lane * K;
+            load_pix(pix, t1, nt, p);
+            if (POL > 1) { load_f64(cs, t1, nt, c); load_f64(sn, t1, nt, s); }
+        }
+        run_merge<POL, POL>(y, rs);
     }
 }
 

@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Per-kernel timing at the bench workload (development tool; CUDA events, L2-exceeding inputs)."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import cosmomap2_b200 as cm  # noqa: E402
+from cosmomap2_b200 import synthetic, _device as dv  # noqa: E402
+
+
+def timeit(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nt", type=int, default=100000000)
+    ap.add_argument("--spp", type=float, default=8.0)
+    ap.add_argument("--random", action="store_true", help="random pointing instead of a raster scan")
+    ap.add_argument("--pol", type=int, default=3)
+    args = ap.parse_args()
+    pol = args.pol
+    sc = synthetic.raster_scan(args.nt, nside=512, ndet=64, nx=1000, ny=500, samples_per_pixel=args.spp, seed=0,
+                               with_data=False)
+    if args.random:
+        sc.pix = np.random.default_rng(0).permutation(sc.pix)
+    nt = sc.nt
+    N = cm.BlockLO(sc.ns, sc.weights)
+    pts = cm.ProcessTimeSamples(sc.pix, sc.npix_full, pol=pol, phi=sc.phi, w=N.diag)
+    npix = pts.get_new_pixel[0]
+    P = cm.SparseLO(npix, nt, sc.pix, pol=pol, angle_processed=pts)
+    Mbd = cm.BlockDiagonalPreconditionerLO(pts, npix, pol=pol)
+    F = cm.FilterLO(nt, [sc.sub_len, sc.sub_start], sc.ns, sc.ndet, sc.pix)
+    n = pol * npix
+    x = dv.to_dev_f64(np.random.default_rng(1).standard_normal(n))
+    d = dv.to_dev_f64(np.random.default_rng(2).standard_normal(nt))
+    A = P.T * N * P
+    AF = P.T * F * P
+    out = {"nt": nt, "npix": int(npix), "pol": pol}
+    gb = lambda b, ms: b / (ms * 1e-3) / 1e9  # noqa: E731
+    bpp = 4 + (16 if pol > 1 else 0)
+    t = timeit(lambda: A._apply(x)); out["amatvec_white_ms"] = t; out["amatvec_white_GBs"] = gb(bpp * nt + 16 * n, t)
+    t = timeit(lambda: AF._apply(x)); out["amatvec_filter_ms"] = t; out["amatvec_filter_GBs"] = gb(bpp * nt + 16 * n, t)
+    t = timeit(lambda: P._apply(x)); out["P_ms"] = t; out["P_GBs"] = gb((bpp + 8) * nt + 8 * n, t)
+    t = timeit(lambda: P.T._apply(d)); out["Pt_ms"] = t; out["Pt_GBs"] = gb((bpp + 8) * nt + 8 * n, t)
+    t = timeit(lambda: N._apply(d)); out["Nwhite_ms"] = t; out["Nwhite_GBs"] = gb(16 * nt, t)
+    t = timeit(lambda: F._apply(d)); out["F_ms"] = t; out["F_GBs"] = gb(20 * nt, t)
+    t = timeit(lambda: Mbd._apply(x)); out["Mbd_ms"] = t; out["Mbd_GBs"] = gb(48 * npix + 16 * n, t)
+    t = timeit(lambda: pts._moments(npix)); out["moments_ms"] = t
+    bands = synthetic.toeplitz_bands(64, 64)
+    NT = cm.BlockLO(sc.ns, bands, offdiag=True)
+    t = timeit(lambda: NT._apply(d), reps=5, warm=1); out["toeplitz64_ms"] = t
+    out["toeplitz64_GFLOPs"] = 2.0 * (2 * 64 - 1) * nt / (t * 1e-3) / 1e9
+    from cosmomap2_b200.pcg import PCG
+    b = P.T._apply(N._apply(d))
+    solver = PCG(A, Mbd, n)
+
+    def step():
+        solver.start(b, need_norm=False)
+        solver.step()
+    t = timeit(step, reps=50, warm=5); out["pcg_iter_ms"] = t
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
