@@ -51,8 +51,12 @@ SIGNATURES = {
     "cm2_m2_apply": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
     "cm2_dot": (_int, [_vp, _vp, _i64, _vp, _vp]),
     "cm2_axpby": (_int, [_f64, _vp, _f64, _vp, _i64, _vp]),
-    "cm2_pcg_update_p": (_int, [_vp, _vp, _vp, _i64, _vp, _int, _vp]),
+    "cm2_pcg_reset": (_int, [_vp, _i64, _vp, _f64, _vp]),
+    "cm2_pcg_update_p": (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "cm2_pcg_update_xr": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "cm2_pcg_bd_reset": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _f64, _vp]),
+    "cm2_pcg_bd_update_p": (_int, [_vp, _vp, _i64, _vp, _vp]),
+    "cm2_pcg_bd_update": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 # entry points that return a size/count rather than a status

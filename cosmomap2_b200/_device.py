@@ -59,7 +59,8 @@ def to_dev(a, dtype=None):
         arr = arr.astype(np.uint8)
     if not arr.flags.writeable:
         arr = arr.copy()
-    t = torch.from_numpy(arr).to(device())
+    src = torch.from_numpy(arr)
+    t = src.to(device(), non_blocking=src.is_pinned() if arr.nbytes >= (1 << 16) else False)
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     return t
@@ -70,7 +71,25 @@ def to_dev_f64(a):
 
 
 def to_host(t):
-    return t.detach().cpu().numpy()
+    """Device tensor -> NumPy array.  Large results land in page-locked memory (torch's caching
+    host allocator) so the copy is one DMA at PCIe speed."""
+    t = t.detach()
+    if not t.is_cuda:
+        return t.numpy()
+    if t.numel() * t.element_size() < (1 << 16):
+        return t.cpu().numpy()
+    t = t.contiguous()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy()
+
+
+def pinned_array(shape, dtype=np.float64):
+    """A page-locked NumPy array (for callers that want full-speed H2D of their inputs)."""
+    tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32,
+           np.dtype(np.int64): torch.int64}[np.dtype(dtype)]
+    return torch.empty(shape, dtype=tdt, pin_memory=True).numpy()
 
 
 def call(name, *args):

@@ -2,13 +2,16 @@
 //
 // Restates the recurrence of scipy.sparse.linalg.cg (scipy/_isolve/iterative.py:405-431), which the
 // reference calls at src/test_BD_precond_onto_real_data.py:47 and
-// src/test_M2_precond_onto_real_data.py:117, with the scalars kept in an 8-double device
-// workspace so an iteration needs no host round trip for alpha/beta:
-//   scal[0]=rho  [1]=rho_prev  [2]=p.q  [3]=|r|^2  [4]=alpha  [5]=beta  [6],[7] caller-owned
+// src/test_M2_precond_onto_real_data.py:117.  All scalars live in a 16-double device workspace:
+//   scal[0]=rho  [1]=rho_prev  [2]=p.q  [3]=|r|^2  [4]=alpha  [5]=beta  [6]=atol
+//   scal[7]=done flag (||r|| < atol, SciPy's exit test)  [8]=iterations completed  [9..15] spare
+// so an iteration needs no host round trip, and every update kernel is a no-op once `done` is set:
+// the host may launch iterations ahead of reading the flag and x still freezes at exactly the
+// iteration SciPy would have returned.
 //
-// Reductions are deterministic: fixed per-thread order, fixed shuffle tree, per-CTA partials
-// summed in CTA order by the last CTA to finish (ticket).  The partial/ticket scratch is a single
-// device-global area: call these entry points from one stream at a time.
+// Reductions are deterministic: fixed per-thread order, fixed shuffle tree, per-CTA partials summed
+// in CTA order by the last CTA to finish (ticket).  The partial/ticket scratch is one device-global
+// area: call these entry points from one stream at a time.
 #include "cm2_common.cuh"
 
 namespace cm2 {
@@ -16,29 +19,35 @@ namespace cm2 {
 constexpr int VB = 256;
 constexpr int MAXP = 2048;  // max CTAs of a reduction kernel
 
-__device__ double g_part[3][MAXP];
-__device__ unsigned int g_ticket[3];
+__device__ double g_part[2][MAXP];
+__device__ unsigned int g_ticket;
 
-// CTA-level: write partial, last CTA reduces all partials in order; returns true in thread 0 of
-// the last CTA with the total in *total
-__device__ __forceinline__ bool finish_reduce(double v, int slot, double *red, double *total) {
+// CTA-level: write up to two partials, last CTA reduces all partials in order; returns true in
+// thread 0 of the last CTA with the totals in tot[0..NR)
+template <int NR>
+__device__ __forceinline__ bool finish_reduce(const double (&v)[NR], double *red, double (&tot)[NR]) {
     __shared__ bool last;
-    const double t = block_sum(v, red);
+    double t[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) t[k] = block_sum(v[k], red);
     if (threadIdx.x == 0) {
-        g_part[slot][blockIdx.x] = t;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) g_part[k][blockIdx.x] = t[k];
         __threadfence();
-        const unsigned int tk = atomicAdd(&g_ticket[slot], 1u);
+        const unsigned int tk = atomicAdd(&g_ticket, 1u);
         last = (tk == gridDim.x - 1);
     }
     __syncthreads();
     if (!last) return false;
     __threadfence();
-    double s = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += VB) s += ((volatile double *)g_part[slot])[i];
-    const double tot = block_sum(s, red);
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += VB) s += ((volatile double *)g_part[k])[i];
+        tot[k] = block_sum(s, red);
+    }
     if (threadIdx.x == 0) {
-        *total = tot;
-        g_ticket[slot] = 0;
+        g_ticket = 0;
         return true;
     }
     return false;
@@ -47,10 +56,9 @@ __device__ __forceinline__ bool finish_reduce(double v, int slot, double *red, d
 __global__ void __launch_bounds__(VB) k_dot(const double *__restrict__ a, const double *__restrict__ b, int64_t n,
                                             double *__restrict__ out) {
     __shared__ double red[32];
-    double s = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * VB + threadIdx.x; i < n; i += (int64_t)gridDim.x * VB) s = fma(a[i], b[i], s);
-    double tot;
-    if (finish_reduce(s, 0, red, &tot)) *out = tot;
+    double s[1] = {0.0}, tot[1];
+    for (int64_t i = (int64_t)blockIdx.x * VB + threadIdx.x; i < n; i += (int64_t)gridDim.x * VB) s[0] = fma(a[i], b[i], s[0]);
+    if (finish_reduce<1>(s, red, tot)) *out = tot[0];
 }
 
 __global__ void __launch_bounds__(VB) k_axpby(double alpha, const double *__restrict__ x, double beta, double *__restrict__ y,
@@ -61,21 +69,39 @@ __global__ void __launch_bounds__(VB) k_axpby(double alpha, const double *__rest
     }
 }
 
-// rho = r.z ; then (second kernel) p = z + (rho/rho_prev) p
-__global__ void __launch_bounds__(VB) k_rho(const double *__restrict__ r, const double *__restrict__ z, int64_t n,
-                                            double *__restrict__ scal, int first) {
+// ---- generic-M path ------------------------------------------------------------------------
+// reset: |r|^2, atol, done flag, iteration counter
+__global__ void __launch_bounds__(VB) k_reset(const double *__restrict__ r, int64_t n, double *__restrict__ scal, double atol) {
     __shared__ double red[32];
-    double s = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * VB + threadIdx.x; i < n; i += (int64_t)gridDim.x * VB) s = fma(r[i], z[i], s);
-    double tot;
-    if (finish_reduce(s, 0, red, &tot)) {
-        scal[0] = tot;
-        scal[5] = first ? 0.0 : tot / scal[1];
+    double s[1] = {0.0}, tot[1];
+    for (int64_t i = (int64_t)blockIdx.x * VB + threadIdx.x; i < n; i += (int64_t)gridDim.x * VB) s[0] = fma(r[i], r[i], s[0]);
+    if (finish_reduce<1>(s, red, tot)) {
+        scal[0] = 0.0; scal[1] = 0.0; scal[2] = 0.0; scal[4] = 0.0; scal[5] = 0.0;
+        scal[3] = tot[0];
+        scal[6] = atol;
+        scal[7] = (sqrt(tot[0]) < atol) ? 1.0 : 0.0;
+        scal[8] = 0.0;
     }
 }
 
+// rho = r.z ; beta = rho/rho_prev (0 on the first iteration)
+__global__ void __launch_bounds__(VB) k_rho(const double *__restrict__ r, const double *__restrict__ z, int64_t n,
+                                            double *__restrict__ scal) {
+    __shared__ double red[32];
+    if (scal[7] != 0.0) return;
+    double s[1] = {0.0}, tot[1];
+    for (int64_t i = (int64_t)blockIdx.x * VB + threadIdx.x; i < n; i += (int64_t)gridDim.x * VB) s[0] = fma(r[i], z[i], s[0]);
+    if (finish_reduce<1>(s, red, tot)) {
+        scal[0] = tot[0];
+        scal[5] = (scal[8] == 0.0) ? 0.0 : tot[0] / scal[1];
+    }
+}
+
+// p = z + beta p  (p = z on the first iteration: p may be uninitialised)
 __global__ void __launch_bounds__(VB) k_update_p(const double *__restrict__ z, double *__restrict__ p, int64_t n,
-                                                 const double *__restrict__ scal, int first) {
+                                                 const double *__restrict__ scal) {
+    if (scal[7] != 0.0) return;
+    const bool first = scal[8] == 0.0;
     const double beta = scal[5];
     for (int64_t i = (int64_t)blockIdx.x * VB + threadIdx.x; i < n; i += (int64_t)gridDim.x * VB)
         p[i] = first ? z[i] : fma(beta, p[i], z[i]);
@@ -84,12 +110,12 @@ __global__ void __launch_bounds__(VB) k_update_p(const double *__restrict__ z, d
 __global__ void __launch_bounds__(VB) k_pq(const double *__restrict__ p, const double *__restrict__ q, int64_t n,
                                            double *__restrict__ scal) {
     __shared__ double red[32];
-    double s = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * VB + threadIdx.x; i < n; i += (int64_t)gridDim.x * VB) s = fma(p[i], q[i], s);
-    double tot;
-    if (finish_reduce(s, 1, red, &tot)) {
-        scal[2] = tot;
-        scal[4] = scal[0] / tot;
+    if (scal[7] != 0.0) return;
+    double s[1] = {0.0}, tot[1];
+    for (int64_t i = (int64_t)blockIdx.x * VB + threadIdx.x; i < n; i += (int64_t)gridDim.x * VB) s[0] = fma(p[i], q[i], s[0]);
+    if (finish_reduce<1>(s, red, tot)) {
+        scal[2] = tot[0];
+        scal[4] = scal[0] / tot[0];
     }
 }
 
@@ -97,18 +123,105 @@ __global__ void __launch_bounds__(VB) k_update_xr(const double *__restrict__ p, 
                                                   double *__restrict__ x, double *__restrict__ r, int64_t n,
                                                   double *__restrict__ scal) {
     __shared__ double red[32];
+    if (scal[7] != 0.0) return;
     const double alpha = scal[4];
-    double s = 0.0;
+    double s[1] = {0.0}, tot[1];
     for (int64_t i = (int64_t)blockIdx.x * VB + threadIdx.x; i < n; i += (int64_t)gridDim.x * VB) {
         x[i] = fma(alpha, p[i], x[i]);
         const double ri = fma(-alpha, q[i], r[i]);
         r[i] = ri;
-        s = fma(ri, ri, s);
+        s[0] = fma(ri, ri, s[0]);
     }
-    double tot;
-    if (finish_reduce(s, 2, red, &tot)) {
-        scal[3] = tot;
+    if (finish_reduce<1>(s, red, tot)) {
+        scal[3] = tot[0];
         scal[1] = scal[0];
+        scal[8] += 1.0;
+        scal[7] = (sqrt(tot[0]) < scal[6]) ? 1.0 : 0.0;
+    }
+}
+
+// ---- M = M_BD path: the preconditioner apply is pixel-local, so z = M r and rho = r.z ride in
+// the same kernel that updates r (one pass over the pixel-domain vectors per iteration) ---------
+template <int POL>
+__device__ __forceinline__ void bd_z(const double *__restrict__ inv, int64_t j, const double (&r)[POL], double (&z)[POL]) {
+    if constexpr (POL == 1) {
+        z[0] = __ldg(inv + 6 * j) * r[0];
+    } else {
+        const double2 *b2 = reinterpret_cast<const double2 *>(inv + 6 * j);
+        if constexpr (POL == 2) {
+            const double2 q1 = __ldg(b2 + 1), q2 = __ldg(b2 + 2);
+            z[0] = q1.y * r[0] + q2.x * r[1];
+            z[1] = q2.x * r[0] + q2.y * r[1];
+        } else {
+            const double2 q0 = __ldg(b2), q1 = __ldg(b2 + 1), q2 = __ldg(b2 + 2);
+            z[0] = q0.x * r[0] + q0.y * r[1] + q1.x * r[2];
+            z[1] = q0.y * r[0] + q1.y * r[1] + q2.x * r[2];
+            z[2] = q1.x * r[0] + q2.x * r[1] + q2.y * r[2];
+        }
+    }
+}
+
+// start: z = M r, rho = r.z, |r|^2, flags
+template <int POL>
+__global__ void __launch_bounds__(VB) k_bd_reset(const double *__restrict__ inv, int64_t npix, const double *__restrict__ r,
+                                                 double *__restrict__ z, double *__restrict__ scal, double atol) {
+    __shared__ double red[32];
+    double s[2] = {0.0, 0.0}, tot[2];
+    for (int64_t j = (int64_t)blockIdx.x * VB + threadIdx.x; j < npix; j += (int64_t)gridDim.x * VB) {
+        double rv[POL], zv[POL];
+#pragma unroll
+        for (int k = 0; k < POL; ++k) rv[k] = r[POL * j + k];
+        bd_z<POL>(inv, j, rv, zv);
+#pragma unroll
+        for (int k = 0; k < POL; ++k) {
+            z[POL * j + k] = zv[k];
+            s[0] = fma(rv[k], zv[k], s[0]);
+            s[1] = fma(rv[k], rv[k], s[1]);
+        }
+    }
+    if (finish_reduce<2>(s, red, tot)) {
+        scal[0] = tot[0]; scal[1] = 0.0; scal[2] = 0.0; scal[4] = 0.0; scal[5] = 0.0;
+        scal[3] = tot[1];
+        scal[6] = atol;
+        scal[7] = (sqrt(tot[1]) < atol) ? 1.0 : 0.0;
+        scal[8] = 0.0;
+    }
+}
+
+// alpha = rho/pq ; x += alpha p ; r -= alpha q ; z = M r ; rho' = r.z ; |r|^2 ; beta' = rho'/rho
+template <int POL>
+__global__ void __launch_bounds__(VB) k_bd_update(const double *__restrict__ inv, int64_t npix, const double *__restrict__ p,
+                                                  const double *__restrict__ q, double *__restrict__ x,
+                                                  double *__restrict__ r, double *__restrict__ z, double *__restrict__ scal) {
+    __shared__ double red[32];
+    if (scal[7] != 0.0) return;
+    const double alpha = scal[4];
+    double s[2] = {0.0, 0.0}, tot[2];
+    for (int64_t j = (int64_t)blockIdx.x * VB + threadIdx.x; j < npix; j += (int64_t)gridDim.x * VB) {
+        double rv[POL], zv[POL];
+#pragma unroll
+        for (int k = 0; k < POL; ++k) {
+            const int64_t i = POL * j + k;
+            x[i] = fma(alpha, p[i], x[i]);
+            rv[k] = fma(-alpha, q[i], r[i]);
+            r[i] = rv[k];
+        }
+        bd_z<POL>(inv, j, rv, zv);
+#pragma unroll
+        for (int k = 0; k < POL; ++k) {
+            z[POL * j + k] = zv[k];
+            s[0] = fma(rv[k], zv[k], s[0]);
+            s[1] = fma(rv[k], rv[k], s[1]);
+        }
+    }
+    if (finish_reduce<2>(s, red, tot)) {
+        const double rho_old = scal[0];
+        scal[1] = rho_old;
+        scal[0] = tot[0];
+        scal[5] = tot[0] / rho_old;
+        scal[3] = tot[1];
+        scal[8] += 1.0;
+        scal[7] = (sqrt(tot[1]) < scal[6]) ? 1.0 : 0.0;
     }
 }
 
@@ -139,13 +252,20 @@ extern "C" int cm2_axpby(double alpha, const double *x, double beta, double *y, 
     return CM2_OK;
 }
 
-extern "C" int cm2_pcg_update_p(const double *r, const double *z, double *p, int64_t n, double *scal, int first,
+extern "C" int cm2_pcg_reset(const double *r, int64_t n, double *scal, double atol, cm2_stream_t stream) {
+    CM2_REQUIRE(n >= 0, "n < 0");
+    k_reset<<<vgrid(n), VB, 0, as_stream(stream)>>>(r, n, scal, atol);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+extern "C" int cm2_pcg_update_p(const double *r, const double *z, double *p, int64_t n, double *scal,
                                 cm2_stream_t stream) {
     CM2_REQUIRE(n >= 0, "n < 0");
     cudaStream_t st = as_stream(stream);
-    k_rho<<<vgrid(n), VB, 0, st>>>(r, z, n, scal, first);
+    k_rho<<<vgrid(n), VB, 0, st>>>(r, z, n, scal);
     CM2_LAUNCHED();
-    k_update_p<<<vgrid(n), VB, 0, st>>>(z, p, n, scal, first);
+    k_update_p<<<vgrid(n), VB, 0, st>>>(z, p, n, scal);
     CM2_LAUNCHED();
     return CM2_OK;
 }
@@ -157,6 +277,42 @@ extern "C" int cm2_pcg_update_xr(const double *p, const double *q, double *x, do
     k_pq<<<vgrid(n), VB, 0, st>>>(p, q, n, scal);
     CM2_LAUNCHED();
     k_update_xr<<<vgrid(n), VB, 0, st>>>(p, q, x, r, n, scal);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+extern "C" int cm2_pcg_bd_reset(const double *inv, int64_t npix, int pol, const double *r, double *z, double *scal,
+                                double atol, cm2_stream_t stream) {
+    CM2_REQUIRE(npix >= 0 && pol >= 1 && pol <= 3, "bad npix/pol");
+    CM2_REQUIRE(aligned(inv, 16), "inverse blocks must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const int g = vgrid(npix);
+    if (pol == 1) k_bd_reset<1><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol);
+    else if (pol == 2) k_bd_reset<2><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol);
+    else k_bd_reset<3><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+extern "C" int cm2_pcg_bd_update_p(const double *z, double *p, int64_t n, double *scal, cm2_stream_t stream) {
+    CM2_REQUIRE(n >= 0, "n < 0");
+    k_update_p<<<vgrid(n), VB, 0, as_stream(stream)>>>(z, p, n, scal);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+extern "C" int cm2_pcg_bd_update(const double *inv, int64_t npix, int pol, const double *p, const double *q, double *x,
+                                 double *r, double *z, double *scal, cm2_stream_t stream) {
+    CM2_REQUIRE(npix >= 0 && pol >= 1 && pol <= 3, "bad npix/pol");
+    CM2_REQUIRE(aligned(inv, 16), "inverse blocks must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const int64_t n = npix * pol;
+    k_pq<<<vgrid(n), VB, 0, st>>>(p, q, n, scal);
+    CM2_LAUNCHED();
+    const int g = vgrid(npix);
+    if (pol == 1) k_bd_update<1><<<g, VB, 0, st>>>(inv, npix, p, q, x, r, z, scal);
+    else if (pol == 2) k_bd_update<2><<<g, VB, 0, st>>>(inv, npix, p, q, x, r, z, scal);
+    else k_bd_update<3><<<g, VB, 0, st>>>(inv, npix, p, q, x, r, z, scal);
     CM2_LAUNCHED();
     return CM2_OK;
 }

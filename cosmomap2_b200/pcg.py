@@ -10,15 +10,22 @@ src/test_M2_precond_onto_real_data.py:117, tests/test_2level_preconditioner.py:5
                      alpha = rho / p.q ; x += alpha p ; r -= alpha q ; callback(x)
     after maxiter iterations -> return (x, maxiter)
 
-All vectors stay in HBM; alpha/beta/rho live in a device workspace (cm2_pcg_update_*), and the
-only per-iteration host read is ||r||^2 (8 bytes) for the exit test, so the iteration count is
-exactly SciPy's.  NumPy ``b`` in -> NumPy ``x`` out; CUDA tensor in -> CUDA tensor out.
+All vectors and scalars stay in HBM (16-double device workspace, see include/cosmomap2_b200.h).
+SciPy's exit test is evaluated ON THE DEVICE by the kernel that updates r; it raises a `done` flag
+that turns every later update kernel into a no-op.  The host therefore queues iteration k+1 while
+iteration k is still running and reads the flag one iteration late (8 bytes, pinned, async): the
+GPU never idles, yet x, the iteration count and info are exactly SciPy's.
+When M is the block-diagonal preconditioner its apply is pixel-local and is folded into the
+kernel that updates r (cm2_pcg_bd_*): 4 launches per iteration besides the A apply.
+NumPy ``b`` in -> NumPy ``x`` out; CUDA tensor in -> CUDA tensor out.
 """
 import numpy as np
 import torch
 
 from . import _device as dv
 from . import linop as lp
+
+NSCAL = 16
 
 
 class _Identity(object):
@@ -38,37 +45,53 @@ def _as_device_operator(op, n):
 
 
 class PCG(object):
-    """The PCG state machine: ``start(b, x0)`` then ``step()`` per iteration.
-
-    ``rnorm`` is ||r||_2 as SciPy tests it at the top of the next iteration.  ``a_events`` (a list),
-    when set, receives a (start, stop) CUDA-event pair around every A apply -- bench.py uses it
-    to time the dominant kernel inside the timed region.
-    """
+    """The PCG state machine: ``start(b, x0, atol)``, then ``step_async()`` per iteration and
+    ``state()`` / ``poll()`` to read the device scalars."""
 
     def __init__(self, A, M, n):
         dv.require_cuda()
+        from .linearoperators import BlockDiagonalPreconditionerLO
         self.n = int(n)
         self.A = _as_device_operator(A, n)
         self.M = _as_device_operator(M, n)
-        self.scal = dv.zeros_f64(8)
+        self.bd = self.M if isinstance(self.M, BlockDiagonalPreconditionerLO) and self.M.size == self.n else None
+        self.scal = dv.zeros_f64(NSCAL)
         self.x = dv.zeros_f64(n)
         self.r = dv.zeros_f64(n)
         self.p = dv.empty_f64(n)
-        self.iteration = 0
-        self.rnorm = 0.0
-        self.a_events = None
+        self.z = dv.empty_f64(n) if self.bd is not None else None
+        self._pin = [torch.empty(NSCAL, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self._ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self._queued = 0          # iterations launched since start()
+        self._snap = 0            # snapshots enqueued
 
-    def _dot(self, a, b, slot):
-        dv.call("cm2_dot", dv.ptr(a), dv.ptr(b), self.n, dv.ptr(self.scal) + 8 * slot, dv.stream())
-
+    # ---- scalars -----------------------------------------------------------------------------
     def norm(self, v):
-        self._dot(v, v, 6)
-        return float(np.sqrt(self.scal[6].item()))
+        out = self.scal[15:16]
+        dv.call("cm2_dot", dv.ptr(v), dv.ptr(v), self.n, dv.ptr(out), dv.stream())
+        return float(np.sqrt(out.item()))
 
-    def start(self, b, x0=None, need_norm=True):
-        """x <- x0 (or 0), r <- b - A x0.  ``b`` must be a CUDA fp64 tensor."""
-        n = self.n
-        self.iteration = 0
+    def state(self):
+        """Synchronous read of (rnorm, done, iterations) from the device workspace."""
+        s = self.scal.cpu()
+        return float(np.sqrt(s[3].item())), bool(s[7].item() != 0.0), int(s[8].item())
+
+    def _snapshot(self):
+        k = self._snap % 2
+        self._pin[k].copy_(self.scal, non_blocking=True)
+        self._ev[k].record()
+        self._snap += 1
+
+    def _read_snapshot(self, idx):
+        k = idx % 2
+        self._ev[k].synchronize()
+        s = self._pin[k]
+        return float(np.sqrt(s[3].item())), bool(s[7].item() != 0.0), int(s[8].item())
+
+    # ---- recurrence --------------------------------------------------------------------------
+    def start(self, b, x0=None, atol=0.0):
+        """x <- x0 (or 0), r <- b - A x0, device scalars reset.  ``b`` is a CUDA fp64 tensor."""
+        n, st = self.n, dv.stream
         self.r.copy_(b)
         if x0 is None:
             self.x.zero_()
@@ -76,30 +99,42 @@ class PCG(object):
             self.x.copy_(x0)
             if bool(torch.any(self.x != 0).item()):
                 ax = self.A._apply(self.x)
-                dv.call("cm2_axpby", -1.0, dv.ptr(ax), 1.0, dv.ptr(self.r), n, dv.stream())
-        if need_norm:
-            self.rnorm = self.norm(self.r)
-
-    def step(self, read_norm=True):
-        n, st = self.n, dv.stream
-        z = self.M._apply(self.r)
-        dv.call("cm2_pcg_update_p", dv.ptr(self.r), dv.ptr(z), dv.ptr(self.p), n, dv.ptr(self.scal),
-                int(self.iteration == 0), st())
-        if self.a_events is not None:
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            q = self.A._apply(self.p)
-            e1.record()
-            self.a_events.append((e0, e1))
+                dv.call("cm2_axpby", -1.0, dv.ptr(ax), 1.0, dv.ptr(self.r), n, st())
+        if self.bd is not None:
+            dv.call("cm2_pcg_bd_reset", dv.ptr(self.bd._inv_dev), self.bd._n, self.bd.pol, dv.ptr(self.r),
+                    dv.ptr(self.z), dv.ptr(self.scal), float(atol), st())
         else:
+            dv.call("cm2_pcg_reset", dv.ptr(self.r), n, dv.ptr(self.scal), float(atol), st())
+        self._queued = 0
+
+    def step_async(self):
+        """Queue one iteration (no host synchronisation)."""
+        n, st = self.n, dv.stream
+        if self.bd is not None:
+            dv.call("cm2_pcg_bd_update_p", dv.ptr(self.z), dv.ptr(self.p), n, dv.ptr(self.scal), st())
             q = self.A._apply(self.p)
-        dv.call("cm2_pcg_update_xr", dv.ptr(self.p), dv.ptr(q), dv.ptr(self.x), dv.ptr(self.r), n,
-                dv.ptr(self.scal), st())
-        self.iteration += 1
-        if read_norm:
-            self.rnorm = float(np.sqrt(self.scal[3].item()))     # the one 8-byte host read per iteration
-        return self.rnorm
+            dv.call("cm2_pcg_bd_update", dv.ptr(self.bd._inv_dev), self.bd._n, self.bd.pol, dv.ptr(self.p), dv.ptr(q),
+                    dv.ptr(self.x), dv.ptr(self.r), dv.ptr(self.z), dv.ptr(self.scal), st())
+        else:
+            z = self.M._apply(self.r)
+            dv.call("cm2_pcg_update_p", dv.ptr(self.r), dv.ptr(z), dv.ptr(self.p), n, dv.ptr(self.scal), st())
+            q = self.A._apply(self.p)
+            dv.call("cm2_pcg_update_xr", dv.ptr(self.p), dv.ptr(q), dv.ptr(self.x), dv.ptr(self.r), n,
+                    dv.ptr(self.scal), st())
+        self._queued += 1
+
+    def tick(self):
+        """Enqueue an async snapshot of the device scalars and return the PREVIOUS snapshot
+        (rnorm, done, iterations) -- the one-iteration-late read the solve loop uses."""
+        self._snapshot()
+        if self._snap >= 2:
+            return self._read_snapshot(self._snap - 2)
+        return None
+
+    def step(self):
+        """One iteration, synchronous: returns ||r||_2 after it."""
+        self.step_async()
+        return self.state()[0]
 
 
 def cg(A, b, x0=None, *, rtol=1e-5, atol=0., maxiter=None, M=None, callback=None, tol=None,
@@ -107,7 +142,7 @@ def cg(A, b, x0=None, *, rtol=1e-5, atol=0., maxiter=None, M=None, callback=None
     """``x, info = cg(A, b, x0=None, rtol=1e-5, atol=0., maxiter=None, M=None, callback=None)``.
 
     ``tol`` is the legacy name of ``rtol`` used by the reference's call sites.  ``residuals``, if a
-    list, receives ||r||_2 as tested at the top of every iteration (no extra device work).
+    list, receives ||r||_2 as tested at the top of every iteration.
     """
     dv.require_cuda()
     if tol is not None:
@@ -133,17 +168,33 @@ def cg(A, b, x0=None, *, rtol=1e-5, atol=0., maxiter=None, M=None, callback=None
         x0d = dv.to_dev_f64(x0).reshape(-1)
         if x0d.shape[0] != n:
             raise ValueError("shapes of A and x0 are incompatible")
-    solver.start(bd, x0d)
+    solver.start(bd, x0d, atol)
 
     def out(v):
-        return dv.to_host(v) if want_numpy else v
+        return dv.to_host(v) if want_numpy else v.clone()
 
-    for _ in range(maxiter):
-        if residuals is not None:
-            residuals.append(solver.rnorm)
-        if solver.rnorm < atol:
-            return out(solver.x), 0
-        solver.step()
-        if callback:
+    if callback is not None:
+        # the callback wants x after every iteration: synchronous loop
+        rnorm, done, _ = solver.state()
+        for _ in range(maxiter):
+            if residuals is not None:
+                residuals.append(rnorm)
+            if done:
+                return out(solver.x), 0
+            solver.step_async()
+            rnorm, done, _ = solver.state()
             callback(out(solver.x))
+        return out(solver.x), maxiter
+
+    # asynchronous loop: the flag of iteration k is read while iteration k+1 is already queued
+    s0 = solver._snap
+    solver._snapshot()                      # snapshot s0: state before iteration 0
+    for it in range(maxiter):
+        solver.step_async()                 # no-op on the device if `done` was already raised
+        solver._snapshot()                  # snapshot s0+it+1: state after iteration `it`
+        rnorm, done, _iters = solver._read_snapshot(s0 + it)   # state at the TOP of iteration `it`
+        if residuals is not None:
+            residuals.append(rnorm)
+        if done:
+            return out(solver.x), 0         # the queued iteration `it` did nothing
     return out(solver.x), maxiter

@@ -157,14 +157,30 @@ int cm2_dot(const double *a, const double *b, int64_t n, double *out, cm2_stream
 /* y = alpha*x + beta*y  (alpha, beta host scalars) */
 int cm2_axpby(double alpha, const double *x, double beta, double *y, int64_t n,
               cm2_stream_t stream);
-/* device-scalar PCG updates; scal[] is an 8-double device workspace:
- *   [0]=rho [1]=rho_prev [2]=p.q [3]=|r|^2 [4]=alpha [5]=beta [6],[7] caller-owned
- * step A: rho = r.z ; beta = rho/rho_prev (0 on first) ; p = z + beta p            */
+/* Device-scalar PCG.  scal[] is a 16-double device workspace:
+ *   [0]=rho [1]=rho_prev [2]=p.q [3]=|r|^2 [4]=alpha [5]=beta [6]=atol
+ *   [7]=done flag (||r||_2 < atol, SciPy's exit test) [8]=iterations completed [9..15] spare
+ * Every update below is a no-op once the done flag is set, so the host may queue iterations
+ * ahead of reading the flag and x still stops at exactly SciPy's iteration.
+ * reset: |r|^2, atol, done flag, counters (call after r = b - A x0) */
+int cm2_pcg_reset(const double *r, int64_t n, double *scal, double atol, cm2_stream_t stream);
+/* rho = r.z ; beta = rho/rho_prev (0 on the first iteration) ; p = z + beta p */
 int cm2_pcg_update_p(const double *r, const double *z, double *p, int64_t n, double *scal,
-                     int first, cm2_stream_t stream);
-/* step B: pq = p.q ; alpha = rho/pq ; x += alpha p ; r -= alpha q ; |r|^2 ; rho_prev = rho */
+                     cm2_stream_t stream);
+/* pq = p.q ; alpha = rho/pq ; x += alpha p ; r -= alpha q ; |r|^2 ; rho_prev = rho ; flags */
 int cm2_pcg_update_xr(const double *p, const double *q, double *x, double *r, int64_t n,
                       double *scal, cm2_stream_t stream);
+/* M = M_BD fast path (the preconditioner is pixel-local, so z = M r and rho = r.z ride in the
+ * kernel that updates r):
+ *   bd_reset   : z = M r ; rho = r.z ; |r|^2 ; atol ; flags
+ *   bd_update_p: p = z + beta p
+ *   bd_update  : pq ; alpha ; x += alpha p ; r -= alpha q ; z = M r ; rho' ; beta' ; |r|^2 ; flags */
+int cm2_pcg_bd_reset(const double *bd_inv, int64_t npix, int pol, const double *r, double *z,
+                     double *scal, double atol, cm2_stream_t stream);
+int cm2_pcg_bd_update_p(const double *z, double *p, int64_t n, double *scal, cm2_stream_t stream);
+int cm2_pcg_bd_update(const double *bd_inv, int64_t npix, int pol, const double *p,
+                      const double *q, double *x, double *r, double *z, double *scal,
+                      cm2_stream_t stream);
 
 #ifdef __cplusplus
 }

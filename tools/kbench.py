@@ -71,8 +71,9 @@ def main():
     solver = PCG(A, Mbd, n)
 
     def step():
-        solver.start(b, need_norm=False)
-        solver.step()
+        solver.start(b)
+        solver.step_async()
+        solver.tick()
     t = timeit(step, reps=50, warm=5); out["pcg_iter_ms"] = t
     print(json.dumps(out))
 
