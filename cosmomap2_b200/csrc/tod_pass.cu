@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(BLOCK) k_hits(const int32_t *__restrict__ pix,
 // unflagged samples.  pix/cos/sin are read from HBM once (pass 1 leaves them in L2 for pass 2).
 // Tiles are aligned to multiples of TILE in the global sample index so the 256-bit loads stay
 // aligned; samples of a tile outside [a, b) are treated as flagged.
-constexpr int SEG_SMEM = 8192;   // d_t values kept on chip per segment (64 kB dynamic smem); longer -> recompute
+constexpr int SEG_SMEM = 12288;  // d_t values kept on chip per segment (96 kB dynamic smem, 2 CTAs/SM); longer -> recompute
 
 __device__ __forceinline__ void load_pix_keep(const int32_t *__restrict__ pix, int64_t t0, int64_t nt, int (&p)[K]) {
     if (t0 + K <= nt) {
