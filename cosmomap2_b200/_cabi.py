@@ -57,11 +57,14 @@ SIGNATURES = {
     "cm2_pcg_bd_reset": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _f64, _vp]),
     "cm2_pcg_bd_update_p": (_int, [_vp, _vp, _i64, _vp, _vp]),
     "cm2_pcg_bd_update": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cm2_allreduce_p2p_signal_bytes": (_i64, []),
+    "cm2_allreduce_p2p": (_int, [_vp, _vp, _vp, _int, _int, _i64, ctypes.c_uint32, _vp]),
+    "cm2_enable_peer_access": (_int, [_int]),
 }
 
 # entry points that return a size/count rather than a status
 _NOT_STATUS = {"cm2_version", "cm2_last_error", "cm2_launch_count", "cm2_scan_scratch_bytes",
-               "cm2_toeplitz_scratch_bytes", "cm2_defl_work_doubles"}
+               "cm2_toeplitz_scratch_bytes", "cm2_defl_work_doubles", "cm2_allreduce_p2p_signal_bytes"}
 
 
 def _load():

@@ -1,0 +1,137 @@
+// cosmomap2_b200 -- map-domain all-reduce over NVLink peer memory (sm_100a, one process per GPU).
+//
+// After the local A-matvec every rank holds its own contribution y_g (npix*pol fp64, 12 MB at
+// configs[1]).  One kernel per rank does the whole exchange over NVSwitch peer mappings:
+//   1. start barrier (per CTA, flags in peer memory): every peer's y_g is complete;
+//   2. rank r reduces ITS slice of the vector from all peers' buffers (peer loads, fixed rank order
+//      -> deterministic, and every element is summed by exactly one rank, so all ranks end with
+//      bit-identical q) and writes the sum straight into every peer's output buffer (peer stores);
+//   3. end barrier: all slices of my output buffer have landed.
+// Traffic per GPU: (G-1)/G * n * 8 B in and the same out, versus 2x that for a ring; latency is two
+// flag round trips instead of NCCL's launch + protocol latency (the payload is small: the TOD stays
+// local, only the pixel-domain vector is exchanged).
+//
+// Buffers and flags are torch CUDA allocations shared through CUDA IPC (torch plumbing); this file
+// only sees pointer tables.  Spin waits carry a clock64() timeout (~2 s) and raise an error word
+// instead of hanging the device.
+#include "cm2_common.cuh"
+
+namespace cm2 {
+
+constexpr int AR_MAX_WORLD = 8;
+constexpr int AR_MAX_BLOCKS = 148;
+constexpr int AR_THREADS = 512;
+
+struct ARSignals {
+    unsigned int start[AR_MAX_BLOCKS][AR_MAX_WORLD];
+    unsigned int end[AR_MAX_BLOCKS][AR_MAX_WORLD];
+    unsigned int error;
+};
+
+struct ARPtrs {
+    const double *send[AR_MAX_WORLD];
+    double *recv[AR_MAX_WORLD];
+    ARSignals *sig[AR_MAX_WORLD];
+};
+
+__device__ __forceinline__ void st_flag(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_flag(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// which = 0: start flags, 1: end flags
+__device__ __forceinline__ void peer_barrier(const ARPtrs &P, int rank, int world, unsigned int gen, int which) {
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        const int t = threadIdx.x;
+        ARSignals *peer = P.sig[t];
+        ARSignals *self = P.sig[rank];
+        unsigned int *dst = which == 0 ? &peer->start[blockIdx.x][rank] : &peer->end[blockIdx.x][rank];
+        const unsigned int *src = which == 0 ? &self->start[blockIdx.x][t] : &self->end[blockIdx.x][t];
+        st_flag(dst, gen);
+        const long long t0 = clock64();
+        while (ld_flag(src) != gen) {
+            if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz: give up loudly instead of hanging
+                self->error = gen;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(AR_THREADS) k_allreduce_p2p(ARPtrs P, int rank, int world, int64_t n, unsigned int gen) {
+    peer_barrier(P, rank, world, gen, 0);
+    // my slice, in units of double2
+    const int64_t n2 = n / 2;
+    const int64_t lo = n2 * rank / world, hi = n2 * (rank + 1) / world;
+    for (int64_t i = lo + (int64_t)blockIdx.x * AR_THREADS + threadIdx.x; i < hi; i += (int64_t)gridDim.x * AR_THREADS) {
+        double2 v[AR_MAX_WORLD];
+#pragma unroll
+        for (int g = 0; g < AR_MAX_WORLD; ++g)
+            if (g < world) v[g] = reinterpret_cast<const double2 *>(P.send[g])[i];
+        double2 s = v[0];
+#pragma unroll
+        for (int g = 1; g < AR_MAX_WORLD; ++g)
+            if (g < world) { s.x += v[g].x; s.y += v[g].y; }
+#pragma unroll
+        for (int g = 0; g < AR_MAX_WORLD; ++g)
+            if (g < world) reinterpret_cast<double2 *>(P.recv[g])[i] = s;
+    }
+    if ((n & 1) && rank == world - 1 && blockIdx.x == 0 && threadIdx.x == 0) {   // odd tail element
+        double s = 0.0;
+        for (int g = 0; g < world; ++g) s += P.send[g][n - 1];
+        for (int g = 0; g < world; ++g) P.recv[g][n - 1] = s;
+    }
+    __threadfence_system();
+    peer_barrier(P, rank, world, gen, 1);
+}
+
+}  // namespace cm2
+
+using namespace cm2;
+
+extern "C" int64_t cm2_allreduce_p2p_signal_bytes(void) { return (int64_t)sizeof(ARSignals); }
+
+extern "C" int cm2_allreduce_p2p(const void *const *send_ptrs_host, void *const *recv_ptrs_host,
+                                 void *const *signal_ptrs_host, int rank, int world, int64_t n, uint32_t generation,
+                                 cm2_stream_t stream) {
+    CM2_REQUIRE(world >= 1 && world <= AR_MAX_WORLD && rank >= 0 && rank < world, "bad rank/world");
+    CM2_REQUIRE(n >= 0, "n < 0");
+    CM2_REQUIRE(generation != 0, "generation must be non-zero");
+    ARPtrs P;
+    for (int g = 0; g < AR_MAX_WORLD; ++g) {
+        P.send[g] = g < world ? reinterpret_cast<const double *>(send_ptrs_host[g]) : nullptr;
+        P.recv[g] = g < world ? reinterpret_cast<double *>(recv_ptrs_host[g]) : nullptr;
+        P.sig[g] = g < world ? reinterpret_cast<ARSignals *>(signal_ptrs_host[g]) : nullptr;
+        if (g < world) CM2_REQUIRE(aligned(P.send[g], 16) && aligned(P.recv[g], 16), "buffers must be 16-byte aligned");
+    }
+    int64_t slice2 = (n / 2 + world - 1) / world;
+    int64_t blocks = (slice2 + AR_THREADS - 1) / AR_THREADS;
+    int cap = sm_count() < AR_MAX_BLOCKS ? sm_count() : AR_MAX_BLOCKS;
+    int grid = (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+    // every rank must launch the SAME grid (per-CTA barriers): it depends only on n and world
+    k_allreduce_p2p<<<grid, AR_THREADS, 0, as_stream(stream)>>>(P, rank, world, n, generation);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+extern "C" int cm2_enable_peer_access(int peer_device) {
+    int dev = 0;
+    CM2_CUDA(cudaGetDevice(&dev));
+    if (peer_device == dev) return CM2_OK;
+    int can = 0;
+    CM2_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) return set_error(CM2_ERR_UNSUPPORTED, "device %d cannot access peer %d", dev, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return CM2_OK;
+    }
+    CM2_CUDA(e);
+    return CM2_OK;
+}

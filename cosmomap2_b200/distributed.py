@@ -45,17 +45,95 @@ def all_reduce_sum_(t, group=None):
     return t
 
 
-class AllReduceLO(lp.LinearOperator):
-    """``sum_g A_g``: applies the local operator, then sums the map-domain result over ranks."""
+class P2PAllReduce(object):
+    """Sum of an n-vector over the ranks of ONE node through NVLink peer memory
+    (cm2_allreduce_p2p: one kernel per rank, reduce-scatter by peer loads + broadcast by peer
+    stores, flag barriers in peer memory).  torch only provides the plumbing: the buffers are torch
+    CUDA allocations exported/imported with torch's CUDA-IPC reductions.
 
-    def __init__(self, local_op, group=None):
+    Deterministic (fixed rank order) and bit-identical on every rank.  ``__call__(y)`` returns a
+    view of the internal receive buffer, valid until the next call.
+    """
+
+    def __init__(self, n, group=None):
+        import ctypes
+        from torch.multiprocessing.reductions import reduce_tensor
+        from . import _device as dv
+        self.n = int(n)
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("P2PAllReduce supports up to 8 ranks (one NVSwitch domain)")
+        dev = dv.device()
+        nsig = int(dv.call("cm2_allreduce_p2p_signal_bytes"))
+        self.send = torch.empty(self.n + (self.n & 1), dtype=torch.float64, device=dev)
+        self.recv = torch.empty(self.n + (self.n & 1), dtype=torch.float64, device=dev)
+        self.sig = torch.zeros(nsig, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        payload = (dev.index, [reduce_tensor(t) for t in (self.send, self.recv, self.sig)])
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, payload, group=group)
+        self._peers = []                       # keep the imported tensors alive
+        send_p, recv_p, sig_p = [], [], []
+        for g, (peer_dev, items) in enumerate(gathered):
+            if g == self.rank:
+                ts = (self.send, self.recv, self.sig)
+            else:
+                dv.call("cm2_enable_peer_access", int(peer_dev))
+                ts = tuple(fn(*args) for fn, args in items)
+                self._peers.append(ts)
+            send_p.append(ts[0].data_ptr())
+            recv_p.append(ts[1].data_ptr())
+            sig_p.append(ts[2].data_ptr())
+        arr = ctypes.c_void_p * self.world
+        self._send_tab, self._recv_tab, self._sig_tab = arr(*send_p), arr(*recv_p), arr(*sig_p)
+        self.gen = 0
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def __call__(self, y):
+        from . import _device as dv
+        self.send[:self.n].copy_(y)
+        self.gen += 1
+        dv.call("cm2_allreduce_p2p", self._send_tab, self._recv_tab, self._sig_tab, self.rank, self.world,
+                self.n, self.gen, dv.stream())
+        return self.recv[:self.n]
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self._peers = []
+
+
+def p2p_enabled():
+    import os
+    return os.environ.get("CM2_P2P_ALLREDUCE", "1") != "0"
+
+
+class AllReduceLO(lp.LinearOperator):
+    """``sum_g A_g``: applies the local operator, then sums the map-domain result over ranks --
+    through NVLink peer memory (P2PAllReduce) when the ranks share a node, else NCCL."""
+
+    def __init__(self, local_op, group=None, p2p=None):
         self.local = local_op
         self.group = group
+        self._p2p = None
+        use = p2p_enabled() if p2p is None else p2p
+        if use and is_distributed(group) and torch.cuda.is_available() and dist.get_backend(group) == "nccl":
+            try:
+                self._p2p = P2PAllReduce(local_op.nargout, group)
+            except Exception as e:                       # no peer access / IPC: NCCL path, loudly noted
+                import warnings
+                warnings.warn("P2P all-reduce unavailable (%s); using NCCL all_reduce" % (e,))
+                self._p2p = None
         super(AllReduceLO, self).__init__(local_op.nargin, local_op.nargout, matvec=self._run,
                                           symmetric=local_op.symmetric, device=True)
 
     def _run(self, x):
         y = self.local._apply(x)
+        if self._p2p is not None:
+            return self._p2p(y)
         if y is x or y.data_ptr() == x.data_ptr():
             y = y.clone()
         return all_reduce_sum_(y, self.group)

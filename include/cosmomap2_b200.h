@@ -182,6 +182,18 @@ int cm2_pcg_bd_update(const double *bd_inv, int64_t npix, int pol, const double 
                       const double *q, double *x, double *r, double *z, double *scal,
                       cm2_stream_t stream);
 
+/* ---- (e) multi-GPU: map-domain all-reduce over NVLink peer memory ------------------------------
+ * One process per GPU.  send/recv/signal tables are HOST arrays of `world` DEVICE pointers (entry g
+ * = rank g's buffer mapped into this process through CUDA IPC; signal buffers are
+ * cm2_allreduce_p2p_signal_bytes() bytes, zero-initialised once).  recv[rank] receives
+ * sum_g send[g][0..n) (fixed rank order, bit-identical on every rank).  `generation` must be the
+ * same non-zero, strictly increasing value on every rank for every call.  All ranks must call. */
+int64_t cm2_allreduce_p2p_signal_bytes(void);
+int cm2_allreduce_p2p(const void *const *send_ptrs_host, void *const *recv_ptrs_host,
+                      void *const *signal_ptrs_host, int rank, int world, int64_t n,
+                      uint32_t generation, cm2_stream_t stream);
+int cm2_enable_peer_access(int peer_device);
+
 #ifdef __cplusplus
 }
 #endif
