@@ -330,7 +330,9 @@ def main():
                        "samples_per_pixel_crossing": sc.samples_per_pixel,
                        "step": "one PCG iteration from a fresh residual (A apply + M_BD apply + CG vector work + ||r|| readback)",
                        "l2": "inputs (2.0 GB TOD per pass) larger than L2 (126 MB); no flush needed",
-                       "parallelism": "tod sharded by detector x%d, map all-reduce (NCCL)" % world if world > 1 else "single GPU",
+                       "parallelism": ("tod sharded by detector x%d, map all-reduce (%s)"
+                                       % (world, "own kernel over NVLink peer memory" if getattr(A, "_p2p", None) is not None
+                                          else "NCCL")) if world > 1 else "single GPU",
                        "check": check},
             "roofline": {"bound": "hbm", "kernel": "k_amatvec_white<3> (cm2_amatvec_white)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -356,6 +358,8 @@ def main():
                 "host_cores_available": os.cpu_count()}
         print(json.dumps(line))
     if world > 1:
+        A.check()
+        A.close()
         dist.destroy_process_group()
 
 

@@ -14,10 +14,12 @@
 namespace cm2 {
 
 constexpr int DB = 256;
-constexpr int RC = 8;          // Z columns accumulated per pass
 constexpr int DG_MAX = 1024;   // max CTAs of the Z^T x reduction
 
-// partial[blockIdx.x * r + c] = sum over this CTA's rows of Z[row, c] * x[row]
+// partial[blockIdx.x * r + c] = sum over this CTA's rows of Z[row, c] * x[row].
+// RC columns are accumulated per pass (RC = 32 covers r <= 32 in ONE pass over x and Z); every
+// thread keeps RC independent column streams in flight per row.
+template <int RC>
 __global__ void __launch_bounds__(DB) k_zt_partial(const double *__restrict__ Z, int64_t n, int r, int64_t ldz,
                                                    const double *__restrict__ x, double *__restrict__ partial) {
     __shared__ double red[32];
@@ -25,18 +27,37 @@ __global__ void __launch_bounds__(DB) k_zt_partial(const double *__restrict__ Z,
         double acc[RC];
 #pragma unroll
         for (int c = 0; c < RC; ++c) acc[c] = 0.0;
-        for (int64_t i = (int64_t)blockIdx.x * DB + threadIdx.x; i < n; i += (int64_t)gridDim.x * DB) {
-            const double xi = x[i];
+        const int nc = r - c0 < RC ? r - c0 : RC;
+        if (nc == RC) {
+            for (int64_t i = (int64_t)blockIdx.x * DB + threadIdx.x; i < n; i += (int64_t)gridDim.x * DB) {
+                const double xi = x[i];
+                double z[RC];
 #pragma unroll
-            for (int c = 0; c < RC; ++c)
-                if (c0 + c < r) acc[c] = fma(Z[i + (int64_t)(c0 + c) * ldz], xi, acc[c]);
+                for (int c = 0; c < RC; ++c) z[c] = __ldcs(Z + i + (int64_t)(c0 + c) * ldz);
+#pragma unroll
+                for (int c = 0; c < RC; ++c) acc[c] = fma(z[c], xi, acc[c]);
+            }
+        } else {
+            for (int64_t i = (int64_t)blockIdx.x * DB + threadIdx.x; i < n; i += (int64_t)gridDim.x * DB) {
+                const double xi = x[i];
+#pragma unroll
+                for (int c = 0; c < RC; ++c)
+                    if (c < nc) acc[c] = fma(__ldcs(Z + i + (int64_t)(c0 + c) * ldz), xi, acc[c]);
+            }
         }
 #pragma unroll
         for (int c = 0; c < RC; ++c) {
             const double t = block_sum(acc[c], red);
-            if (threadIdx.x == 0 && c0 + c < r) partial[(int64_t)blockIdx.x * r + c0 + c] = t;
+            if (threadIdx.x == 0 && c < nc) partial[(int64_t)blockIdx.x * r + c0 + c] = t;
         }
     }
+}
+
+static void launch_zt_partial(int g, cudaStream_t st, const double *Z, int64_t n, int r, int64_t ldz, const double *x,
+                              double *partial) {
+    if (r <= 8) k_zt_partial<8><<<g, DB, 0, st>>>(Z, n, r, ldz, x, partial);
+    else if (r <= 16) k_zt_partial<16><<<g, DB, 0, st>>>(Z, n, r, ldz, x, partial);
+    else k_zt_partial<32><<<g, DB, 0, st>>>(Z, n, r, ldz, x, partial);
 }
 
 // out[c] = sum_b partial[b*r + c] in CTA order (deterministic); optional out = Einv * (that)
@@ -68,7 +89,8 @@ __global__ void __launch_bounds__(DB) k_z_apply(const double *__restrict__ Z, in
     __syncthreads();
     for (int64_t i = (int64_t)blockIdx.x * DB + threadIdx.x; i < n; i += (int64_t)gridDim.x * DB) {
         double s = 0.0;
-        for (int c = 0; c < r; ++c) s = fma(Z[i + (int64_t)c * ldz], sc[c], s);
+#pragma unroll 8
+        for (int c = 0; c < r; ++c) s = fma(__ldcs(Z + i + (int64_t)c * ldz), sc[c], s);
         const double b = (y0 != nullptr && beta != 0.0) ? beta * y0[i] : 0.0;
         y[i] = fma(alpha, s, b);
     }
@@ -98,12 +120,13 @@ __global__ void __launch_bounds__(DB) k_m2_finish(const double *__restrict__ Z, 
         double u[POL], zc[POL];
 #pragma unroll
         for (int k = 0; k < POL; ++k) { u[k] = v[POL * j + k]; zc[k] = 0.0; }
+#pragma unroll 8
         for (int c = 0; c < r; ++c) {
             const double cc = sc[c];
 #pragma unroll
             for (int k = 0; k < POL; ++k) {
-                u[k] = fma(-AZ[POL * j + k + (int64_t)c * ld], cc, u[k]);
-                zc[k] = fma(Z[POL * j + k + (int64_t)c * ld], cc, zc[k]);
+                u[k] = fma(-__ldcs(AZ + POL * j + k + (int64_t)c * ld), cc, u[k]);
+                zc[k] = fma(__ldcs(Z + POL * j + k + (int64_t)c * ld), cc, zc[k]);
             }
         }
         const double *b = inv + 6 * j;
@@ -139,9 +162,9 @@ extern "C" int cm2_defl_zt_apply(const double *Z, int64_t n, int r, int64_t ldz,
     CM2_REQUIRE(n >= 0 && r >= 1 && ncols_x >= 1 && ldz >= n, "bad sizes");
     CM2_REQUIRE(work != nullptr, "work (cm2_defl_work_doubles) required");
     cudaStream_t st = as_stream(stream);
-    const int g = dgrid(n);
+    const int g = dgrid(n, 2);   // 128 regs/thread -> 2 resident CTAs/SM: one wave
     for (int k = 0; k < ncols_x; ++k) {
-        k_zt_partial<<<g, DB, 0, st>>>(Z, n, r, ldz, X + (int64_t)k * ldx, work);
+        launch_zt_partial(g, st, Z, n, r, ldz, X + (int64_t)k * ldx, work);
         CM2_LAUNCHED();
         k_zt_final<<<1, DB, sizeof(double) * r, st>>>(work, g, r, nullptr, out + (int64_t)k * r, nullptr);
         CM2_LAUNCHED();
@@ -171,9 +194,9 @@ extern "C" int cm2_m2_apply(const double *Z, const double *AZ, int64_t n, int r,
     CM2_REQUIRE(pol >= 1 && pol <= 3 && n == npix * pol && r >= 1 && ld >= n, "bad sizes");
     CM2_REQUIRE(work != nullptr, "work (cm2_defl_work_doubles) required");
     cudaStream_t st = as_stream(stream);
-    const int g = dgrid(n);
+    const int g = dgrid(n, 2);
     double *coef = work + (int64_t)DG_MAX * r;   // r doubles: c = Einv Z^T v
-    k_zt_partial<<<g, DB, 0, st>>>(Z, n, r, ld, v, work);
+    launch_zt_partial(g, st, Z, n, r, ld, v, work);
     CM2_LAUNCHED();
     k_zt_final<<<1, DB, sizeof(double) * r, st>>>(work, g, r, Einv, nullptr, coef);
     CM2_LAUNCHED();

@@ -64,31 +64,48 @@ __device__ __forceinline__ void peer_barrier(const ARPtrs &P, int rank, int worl
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(AR_THREADS) k_allreduce_p2p(ARPtrs P, int rank, int world, int64_t n, unsigned int gen) {
-    peer_barrier(P, rank, world, gen, 0);
-    // my slice, in units of double2
-    const int64_t n2 = n / 2;
-    const int64_t lo = n2 * rank / world, hi = n2 * (rank + 1) / world;
-    for (int64_t i = lo + (int64_t)blockIdx.x * AR_THREADS + threadIdx.x; i < hi; i += (int64_t)gridDim.x * AR_THREADS) {
-        double2 v[AR_MAX_WORLD];
+// WORLD and UNROLL are compile-time so that WORLD*UNROLL 16-byte peer loads per thread are in
+// flight without spilling (NVLink load latency is ~2-3 us: the exchange is latency-bound unless
+// enough loads are outstanding).
+template <int WORLD, int UNROLL>
+__global__ void __launch_bounds__(AR_THREADS) k_allreduce_p2p(ARPtrs P, int rank, int64_t n, unsigned int gen) {
+    peer_barrier(P, rank, WORLD, gen, 0);
+    const int64_t n2 = n / 2;   // my slice, in units of double2
+    const int64_t lo = n2 * rank / WORLD, hi = n2 * (rank + 1) / WORLD;
+    const int64_t stride = (int64_t)gridDim.x * AR_THREADS;
+    for (int64_t i0 = lo + (int64_t)blockIdx.x * AR_THREADS + threadIdx.x; i0 < hi; i0 += stride * UNROLL) {
+        double2 v[UNROLL][WORLD];
 #pragma unroll
-        for (int g = 0; g < AR_MAX_WORLD; ++g)
-            if (g < world) v[g] = reinterpret_cast<const double2 *>(P.send[g])[i];
-        double2 s = v[0];
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t i = i0 + u * stride;
 #pragma unroll
-        for (int g = 1; g < AR_MAX_WORLD; ++g)
-            if (g < world) { s.x += v[g].x; s.y += v[g].y; }
+            for (int g = 0; g < WORLD; ++g)
+                if (i < hi) v[u][g] = reinterpret_cast<const double2 *>(P.send[g])[i];
+        }
 #pragma unroll
-        for (int g = 0; g < AR_MAX_WORLD; ++g)
-            if (g < world) reinterpret_cast<double2 *>(P.recv[g])[i] = s;
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < hi) {
+                double2 s = v[u][0];
+#pragma unroll
+                for (int g = 1; g < WORLD; ++g) { s.x += v[u][g].x; s.y += v[u][g].y; }   // fixed rank order
+#pragma unroll
+                for (int g = 0; g < WORLD; ++g) reinterpret_cast<double2 *>(P.recv[g])[i] = s;
+            }
+        }
     }
-    if ((n & 1) && rank == world - 1 && blockIdx.x == 0 && threadIdx.x == 0) {   // odd tail element
+    if ((n & 1) && rank == WORLD - 1 && blockIdx.x == 0 && threadIdx.x == 0) {   // odd tail element
         double s = 0.0;
-        for (int g = 0; g < world; ++g) s += P.send[g][n - 1];
-        for (int g = 0; g < world; ++g) P.recv[g][n - 1] = s;
+        for (int g = 0; g < WORLD; ++g) s += P.send[g][n - 1];
+        for (int g = 0; g < WORLD; ++g) P.recv[g][n - 1] = s;
     }
     __threadfence_system();
-    peer_barrier(P, rank, world, gen, 1);
+    peer_barrier(P, rank, WORLD, gen, 1);
+}
+
+template <int WORLD, int UNROLL>
+static void launch_ar(const ARPtrs &P, int rank, int64_t n, unsigned int gen, int grid, cudaStream_t st) {
+    k_allreduce_p2p<WORLD, UNROLL><<<grid, AR_THREADS, 0, st>>>(P, rank, n, gen);
 }
 
 }  // namespace cm2
@@ -115,7 +132,17 @@ extern "C" int cm2_allreduce_p2p(const void *const *send_ptrs_host, void *const 
     int cap = sm_count() < AR_MAX_BLOCKS ? sm_count() : AR_MAX_BLOCKS;
     int grid = (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
     // every rank must launch the SAME grid (per-CTA barriers): it depends only on n and world
-    k_allreduce_p2p<<<grid, AR_THREADS, 0, as_stream(stream)>>>(P, rank, world, n, generation);
+    cudaStream_t st = as_stream(stream);
+    switch (world) {
+        case 1: launch_ar<1, 4>(P, rank, n, generation, grid, st); break;
+        case 2: launch_ar<2, 8>(P, rank, n, generation, grid, st); break;
+        case 3: launch_ar<3, 4>(P, rank, n, generation, grid, st); break;
+        case 4: launch_ar<4, 4>(P, rank, n, generation, grid, st); break;
+        case 5: launch_ar<5, 2>(P, rank, n, generation, grid, st); break;
+        case 6: launch_ar<6, 2>(P, rank, n, generation, grid, st); break;
+        case 7: launch_ar<7, 2>(P, rank, n, generation, grid, st); break;
+        default: launch_ar<8, 2>(P, rank, n, generation, grid, st); break;
+    }
     CM2_LAUNCHED();
     return CM2_OK;
 }

@@ -81,7 +81,10 @@ class P2PAllReduce(object):
                 ts = (self.send, self.recv, self.sig)
             else:
                 dv.call("cm2_enable_peer_access", int(peer_dev))
-                ts = tuple(fn(*args) for fn, args in items)
+                # open every IPC mapping in THIS rank's device context (argument 6 of torch's
+                # rebuild_cuda_tensor is the storage device): memory imported under the exporter's
+                # device index is not reachable from kernels running on our device
+                ts = tuple(fn(*(list(args[:6]) + [dev.index] + list(args[7:]))) for fn, args in items)
                 self._peers.append(ts)
             send_p.append(ts[0].data_ptr())
             recv_p.append(ts[1].data_ptr())
@@ -99,6 +102,12 @@ class P2PAllReduce(object):
         dv.call("cm2_allreduce_p2p", self._send_tab, self._recv_tab, self._sig_tab, self.rank, self.world,
                 self.n, self.gen, dv.stream())
         return self.recv[:self.n]
+
+    def error(self):
+        """Non-zero if a flag wait timed out (a peer never arrived): results are then invalid."""
+        torch.cuda.synchronize()
+        return int(self.sig[-4:].view(torch.int32).item()) if self.sig.numel() % 4 == 0 else \
+            int.from_bytes(bytes(self.sig[-4:].cpu().numpy().tobytes()), "little")
 
     def close(self):
         torch.cuda.synchronize()
@@ -129,6 +138,17 @@ class AllReduceLO(lp.LinearOperator):
                 self._p2p = None
         super(AllReduceLO, self).__init__(local_op.nargin, local_op.nargout, matvec=self._run,
                                           symmetric=local_op.symmetric, device=True)
+
+    def check(self):
+        """Raise if the peer-memory exchange ever timed out."""
+        if self._p2p is not None and self._p2p.error() != 0:
+            raise RuntimeError("P2P all-reduce: a peer did not arrive within the timeout (generation %d)"
+                               % self._p2p.error())
+
+    def close(self):
+        if self._p2p is not None:
+            self._p2p.close()
+            self._p2p = None
 
     def _run(self, x):
         y = self.local._apply(x)

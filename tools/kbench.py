@@ -66,6 +66,18 @@ def main():
     NT = cm.BlockLO(sc.ns, bands, offdiag=True)
     t = timeit(lambda: NT._apply(d), reps=5, warm=1); out["toeplitz64_ms"] = t
     out["toeplitz64_GFLOPs"] = 2.0 * (2 * 64 - 1) * nt / (t * 1e-3) / 1e9
+    # deflation / two-level preconditioner at r = 32 (rows a10-a13): 8*r*n bytes per pass over Z
+    r = 32
+    Zt = torch.randn((r, n), dtype=torch.float64, device="cuda") / np.sqrt(n)
+    AZt = torch.stack([A._apply(Zt[i]) for i in range(r)])
+    Zd, AZd = cm.DeflationLO(Zt.t()), cm.DeflationLO(AZt.t())
+    E = cm.CoarseLO(Zt.t(), AZt.t(), r, apply="eig")
+    M2 = cm.TwoLevelPreconditionerLO(Mbd, Zd, AZd, E)
+    yv = dv.to_dev_f64(np.random.default_rng(3).standard_normal(r))
+    t = timeit(lambda: Zd.T._apply(x)); out["Zt_x_ms"] = t; out["Zt_x_GBs"] = gb(8.0 * r * n, t)
+    t = timeit(lambda: Zd._apply(yv)); out["Z_y_ms"] = t; out["Z_y_GBs"] = gb(8.0 * r * n, t)
+    t = timeit(lambda: M2._apply(x)); out["M2_ms"] = t; out["M2_GBs"] = gb(3 * 8.0 * r * n + 48.0 * npix + 16.0 * n, t)
+    t = timeit(lambda: cm.CoarseLO(Zt.t(), AZt.t(), r, apply="eig"), reps=3, warm=1); out["coarse_build_ms"] = t
     from cosmomap2_b200.pcg import PCG
     b = P.T._apply(N._apply(d))
     solver = PCG(A, Mbd, n)

@@ -20,11 +20,13 @@ for n in (1500000, 1500001, 7):
         out = ar(y).clone()
         assert torch.equal(out, ref), "rank %d n=%d iter %d mismatch: %g" % (rank, n, it, (out - ref).abs().max().item())
     # timing
+    big = torch.randn(8192, 8192, device="cuda")
     def timeit(fn, reps=50):
         for _ in range(5): fn()
         torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        for _ in range(3): torch.matmul(big, big)      # ~ms of device work: the host runs ahead, so the
+        e0.record()                                     # loop below is timed back-to-back on the device
         for _ in range(reps): fn()
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps * 1e3
