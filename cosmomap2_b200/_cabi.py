@@ -41,6 +41,9 @@ SIGNATURES = {
     "cm2_noise_white_apply": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
     "cm2_toeplitz_scratch_bytes": (_i64, [_i64]),
     "cm2_noise_toeplitz_apply": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "cm2_toeplitz_fft_points": (_int, []),
+    "cm2_toeplitz_fft_scratch_bytes": (_i64, [_i64]),
+    "cm2_noise_toeplitz_fft_apply": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _int, _vp]),
     "cm2_filter_offset_apply": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "cm2_amatvec_white": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
     "cm2_amatvec_filter": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
@@ -64,7 +67,8 @@ SIGNATURES = {
 
 # entry points that return a size/count rather than a status
 _NOT_STATUS = {"cm2_version", "cm2_last_error", "cm2_launch_count", "cm2_scan_scratch_bytes",
-               "cm2_toeplitz_scratch_bytes", "cm2_defl_work_doubles", "cm2_allreduce_p2p_signal_bytes"}
+               "cm2_toeplitz_scratch_bytes", "cm2_defl_work_doubles", "cm2_allreduce_p2p_signal_bytes",
+               "cm2_toeplitz_fft_points", "cm2_toeplitz_fft_scratch_bytes"}
 
 
 def _load():

@@ -1,0 +1,181 @@
+// cosmomap2_b200 -- banded symmetric Toeplitz apply by overlap-save FFT in shared memory (sm_100a).
+//
+// ToeplitzLO.mult (interfaces/linearoperators.py:582-595) is y_j = sum_{|k|<L} a_|k| v_{j-k} with
+// zero boundaries: 2(2L-1) flop/sample done directly, i.e. 16 382 flop/sample at the L = 4096 of
+// configs[2] -- 100x more time than the 16 B/sample of HBM traffic.  Here each CTA takes one window
+// of NF = 2M real samples (M complex points, 128 kB of shared memory), runs an in-place radix-2
+// DIF FFT (output bit-reversed), applies the real, even transfer function of the band in the
+// bit-reversed domain, runs the inverse in-place DIT FFT (input bit-reversed, output natural) and
+// writes the NF - 2(L-1) alias-free outputs.  No reordering pass, no global scratch.
+//
+// Real-input packing: z[n] = x[2n] + i x[2n+1] (the window as it lies in memory).  With
+// E = FFT(even samples), O = FFT(odd samples), w = exp(-2 pi i/NF), H the (real, even) DFT of the
+// circularly arranged band:  Hs = (H[k]+H[k+M])/2, Hd = (H[k]-H[k+M])/2,
+//     W[k] = (Hs + i Hd w^-k) E[k] + (Hd w^k + i Hs) O[k]
+// is the packed spectrum of the filtered window (derivation in DESIGN.md); C1 = Hs + i Hd w^-k and
+// C2 = Hd w^k + i Hs are precomputed per noise block on the host, 1/M folded in.
+//
+// Bound: shared-memory bandwidth (each radix-2 stage moves 64 B per butterfly), ~60x fewer flops
+// than the direct form at L = 4096.
+#include "cm2_common.cuh"
+
+namespace cm2 {
+
+constexpr int FFT_LOG2M = 13;
+constexpr int FFT_M = 1 << FFT_LOG2M;   // complex points per window
+constexpr int FFT_NF = 2 * FFT_M;       // real samples per window (16384)
+constexpr int FFT_THREADS = 512;
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+
+// tw[t] = exp(-2 pi i t / M), t in [0, M/2)
+__global__ void k_fft_twiddles(double2 *__restrict__ tw) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < FFT_M / 2) {
+        double s, c;
+        sincospi(-2.0 * (double)t / (double)FFT_M, &s, &c);
+        tw[t] = make_double2(c, s);
+    }
+}
+
+// one CTA per window.  win_first[b] = first window index of noise block b (prefix, nblocks+1).
+__global__ void __launch_bounds__(FFT_THREADS, 1)
+    k_toeplitz_fft(const double2 *__restrict__ coef,   // [nblocks][2][M]: C1 then C2 (natural k order)
+                   const double2 *__restrict__ tw, int L, int64_t nblocks, int64_t blocksize,
+                   const int64_t *__restrict__ start, const int64_t *__restrict__ win_first,
+                   const double *__restrict__ d, double *__restrict__ out, int64_t nt) {
+    extern __shared__ double2 z[];   // M complex points
+    const int S = FFT_NF - 2 * (L - 1);   // alias-free outputs per window
+    const int64_t nwin = win_first[nblocks];
+    for (int64_t win = blockIdx.x; win < nwin; win += gridDim.x) {
+        int64_t lo = 0, hi = nblocks;
+        while (hi - lo > 1) {
+            int64_t mid = (lo + hi) >> 1;
+            if (win_first[mid] <= win) lo = mid; else hi = mid;
+        }
+        const int64_t b = lo;
+        const int64_t bs = start ? start[b] : b * blocksize;
+        const int64_t be = start ? start[b + 1] : (b + 1 == nblocks ? nt : (b + 1) * blocksize);
+        const int64_t j0 = bs + (win - win_first[b]) * S;     // first output of this window
+        const int64_t w0 = j0 - (L - 1);                      // first input sample of the window
+        __syncthreads();
+        // ---- load the window, zero outside the noise block (non-circulant boundary)
+        for (int i = threadIdx.x; i < FFT_M; i += FFT_THREADS) {
+            const int64_t t = w0 + 2 * (int64_t)i;
+            double2 v;
+            v.x = (t >= bs && t < be) ? d[t] : 0.0;
+            v.y = (t + 1 >= bs && t + 1 < be) ? d[t + 1] : 0.0;
+            z[i] = v;
+        }
+        __syncthreads();
+        // ---- forward FFT: radix-2 decimation in frequency, natural in -> bit-reversed out
+        for (int lm = FFT_LOG2M - 1; lm >= 0; --lm) {
+            const int m = 1 << lm;
+            for (int j = threadIdx.x; j < FFT_M / 2; j += FFT_THREADS) {
+                const int pos = j & (m - 1);
+                const int i = ((j >> lm) << (lm + 1)) + pos;
+                const double2 a = z[i], bb = z[i + m];
+                const double2 w = __ldg(tw + (pos << (FFT_LOG2M - 1 - lm)));
+                z[i] = make_double2(a.x + bb.x, a.y + bb.y);
+                z[i + m] = cmul(make_double2(a.x - bb.x, a.y - bb.y), w);
+            }
+            __syncthreads();
+        }
+        // ---- transfer function on the packed spectrum, pairs (k, M-k) in bit-reversed storage
+        const double2 *c1 = coef + (int64_t)b * 2 * FFT_M;
+        const double2 *c2 = c1 + FFT_M;
+        for (int k = threadIdx.x; k <= FFT_M / 2; k += FFT_THREADS) {
+            const int km = (FFT_M - k) & (FFT_M - 1);
+            const int pk = __brev((unsigned)k) >> (32 - FFT_LOG2M);
+            const int pm = __brev((unsigned)km) >> (32 - FFT_LOG2M);
+            const double2 zk = z[pk], zm = z[pm];
+            // E[k] = (Z[k] + conj Z[M-k])/2 ; O[k] = (Z[k] - conj Z[M-k])/(2i)
+            const double2 Ek = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+            const double2 Ok = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
+            const double2 Em = make_double2(Ek.x, -Ek.y);   // E[M-k] = conj E[k]
+            const double2 Om = make_double2(Ok.x, -Ok.y);   // O[M-k] = conj O[k]
+            const double2 a1 = cmul(__ldg(c1 + k), Ek), a2 = cmul(__ldg(c2 + k), Ok);
+            const double2 b1 = cmul(__ldg(c1 + km), Em), b2 = cmul(__ldg(c2 + km), Om);
+            z[pk] = make_double2(a1.x + a2.x, a1.y + a2.y);
+            if (km != k) z[pm] = make_double2(b1.x + b2.x, b1.y + b2.y);
+        }
+        __syncthreads();
+        // ---- inverse FFT: radix-2 decimation in time, bit-reversed in -> natural out (conj twiddles)
+        for (int lm = 0; lm < FFT_LOG2M; ++lm) {
+            const int m = 1 << lm;
+            for (int j = threadIdx.x; j < FFT_M / 2; j += FFT_THREADS) {
+                const int pos = j & (m - 1);
+                const int i = ((j >> lm) << (lm + 1)) + pos;
+                double2 w = __ldg(tw + (pos << (FFT_LOG2M - 1 - lm)));
+                w.y = -w.y;
+                const double2 a = z[i], bb = cmul(z[i + m], w);
+                z[i] = make_double2(a.x + bb.x, a.y + bb.y);
+                z[i + m] = make_double2(a.x - bb.x, a.y - bb.y);
+            }
+            __syncthreads();
+        }
+        // ---- alias-free outputs: window positions [L-1, L-1+S)
+        const double *zr = reinterpret_cast<const double *>(z);
+        for (int i = threadIdx.x; i < S; i += FFT_THREADS) {
+            const int64_t t = j0 + i;
+            if (t < be) out[t] = zr[L - 1 + i];
+        }
+    }
+}
+
+__global__ void k_win_first(int64_t nblocks, int64_t blocksize, const int64_t *__restrict__ start, int64_t nt, int S,
+                            int64_t *__restrict__ win_first) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int64_t acc = 0;
+        for (int64_t b = 0; b < nblocks; ++b) {
+            win_first[b] = acc;
+            const int64_t bs = start ? start[b] : b * blocksize;
+            const int64_t be = start ? start[b + 1] : (b + 1 == nblocks ? nt : (b + 1) * blocksize);
+            acc += (be - bs + S - 1) / S;
+        }
+        win_first[nblocks] = acc;
+    }
+}
+
+}  // namespace cm2
+
+using namespace cm2;
+
+extern "C" int cm2_toeplitz_fft_points(void) { return FFT_M; }
+
+extern "C" int64_t cm2_toeplitz_fft_scratch_bytes(int64_t nblocks) {
+    return (nblocks + 1) * (int64_t)sizeof(int64_t) + (int64_t)(FFT_M / 2) * (int64_t)sizeof(double2) + 64;
+}
+
+// coef: device, [nblocks][2][M] complex (C1, C2 in natural frequency order, 1/M folded in);
+// scratch: cm2_toeplitz_fft_scratch_bytes(nblocks) bytes, `init` != 0 builds the twiddle table in it
+extern "C" int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
+                                            const int64_t *blk_start, const double *d, double *out, int64_t nt,
+                                            void *scratch, int init, cm2_stream_t stream) {
+    CM2_REQUIRE(nt >= 0 && nblocks > 0 && nband >= 1, "bad sizes");
+    CM2_REQUIRE(blk_start != nullptr || blocksize > 0, "blocksize must be > 0");
+    CM2_REQUIRE(2 * (nband - 1) < FFT_NF / 2, "band too wide for the 16384-point overlap-save window");
+    CM2_REQUIRE(scratch != nullptr && aligned(scratch, 16) && aligned(coef, 16), "scratch/coef must be 16-byte aligned");
+    CM2_REQUIRE(d != out, "in-place Toeplitz apply is not supported");
+    if (nt == 0) return CM2_OK;
+    cudaStream_t st = as_stream(stream);
+    double2 *tw = reinterpret_cast<double2 *>(scratch);
+    int64_t *win_first = reinterpret_cast<int64_t *>(reinterpret_cast<char *>(scratch) + (FFT_M / 2) * sizeof(double2));
+    if (init) {
+        k_fft_twiddles<<<(FFT_M / 2 + 255) / 256, 256, 0, st>>>(tw);
+        CM2_LAUNCHED();
+    }
+    const int S = FFT_NF - 2 * (nband - 1);
+    k_win_first<<<1, 1, 0, st>>>(nblocks, blocksize, blk_start, nt, S, win_first);
+    CM2_LAUNCHED();
+    const size_t smem = sizeof(double2) * FFT_M;
+    CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t nwin_ub = nt / S + nblocks + 1;
+    int grid = (int)(nwin_ub < sm_count() ? nwin_ub : sm_count());
+    k_toeplitz_fft<<<grid, FFT_THREADS, smem, st>>>(reinterpret_cast<const double2 *>(coef), tw, nband, nblocks, blocksize,
+                                                   blk_start, win_first, d, out, nt);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}

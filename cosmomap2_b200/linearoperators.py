@@ -155,11 +155,57 @@ class ToeplitzLO(lp.LinearOperator):
 
     def mult(self, v):                                    # :582-595
         if self._band_dev is None:
-            self._band_dev = dv.to_dev_f64(np.atleast_1d(np.asarray(self.array, dtype=np.float64)))
-        return _toeplitz_apply(self._band_dev, self._band_dev.numel(), self._blocks, v)
+            band = np.atleast_1d(np.asarray(self.array, dtype=np.float64))
+            self._band_dev = dv.to_dev_f64(band)
+            self._fft = _ToeplitzFFT(band, len(band)) if len(band) >= TOEPLITZ_FFT_MIN_BAND else None
+        return _toeplitz_apply(self._band_dev, self._band_dev.numel(), self._blocks, v, self._fft)
 
 
-def _toeplitz_apply(band_dev, nband, blocks, v):
+TOEPLITZ_FFT_MIN_BAND = 128    # bands at least this wide go through the overlap-save FFT kernel
+
+
+class _ToeplitzFFT(object):
+    """Host-built packed transfer functions + device scratch for cm2_noise_toeplitz_fft_apply."""
+
+    def __init__(self, band_host, nband):
+        M = int(dv.call("cm2_toeplitz_fft_points"))
+        NF = 2 * M
+        self.ok = 2 * (nband - 1) < M
+        if not self.ok:
+            return
+        band_host = np.asarray(band_host, dtype=np.float64).reshape(-1, nband)
+        nb = band_host.shape[0]
+        k = np.arange(M)
+        w = np.exp(-2j * np.pi * k / NF)
+        coef = np.empty((nb, 2, M), dtype=np.complex128)
+        for b in range(nb):
+            a = band_host[b]
+            hc = np.zeros(NF)
+            hc[:nband] = a
+            if nband > 1:
+                hc[NF - nband + 1:] = a[1:][::-1]
+            H = np.fft.fft(hc).real                      # real and even: the band is symmetric
+            Hs, Hd = 0.5 * (H[:M] + H[M:]), 0.5 * (H[:M] - H[M:])
+            coef[b, 0] = (Hs + 1j * Hd * np.conj(w)) / M
+            coef[b, 1] = (Hd * w + 1j * Hs) / M
+        self.coef = dv.to_dev_f64(coef.view(np.float64).reshape(-1))
+        self.scratch = torch.empty(int(dv.call("cm2_toeplitz_fft_scratch_bytes", nb)) // 8 + 2, dtype=torch.float64,
+                                   device=self.coef.device)
+        self.init = 1
+        self.nband = int(nband)
+
+    def apply(self, blocks, v):
+        out = torch.empty_like(v)
+        nb, bs, startp = blocks.args()
+        dv.call("cm2_noise_toeplitz_fft_apply", dv.ptr(self.coef), self.nband, nb, bs, startp, dv.ptr(v), dv.ptr(out),
+                v.numel(), dv.ptr(self.scratch), self.init, _stream())
+        self.init = 0
+        return out
+
+
+def _toeplitz_apply(band_dev, nband, blocks, v, fft=None):
+    if fft is not None and fft.ok:
+        return fft.apply(blocks, v)
     out = torch.empty_like(v)
     nb, bs, startp = blocks.args()
     scratch = torch.empty(nb + 1, dtype=torch.int64, device=v.device)
@@ -305,7 +351,9 @@ class BlockLO(BlockDiagonalLinearOperator):
         if self.isoffdiag:
             if self._band_dev is None:
                 self._band_dev = dv.to_dev_f64(self._band_host.reshape(-1))
-            return _toeplitz_apply(self._band_dev, self._nband, self._blk, x)
+                self._fft = (_ToeplitzFFT(self._band_host, self._nband)
+                             if self._nband >= TOEPLITZ_FFT_MIN_BAND else None)
+            return _toeplitz_apply(self._band_dev, self._nband, self._blk, x, self._fft)
         out = torch.empty_like(x)
         dv.call("cm2_noise_white_apply", dv.ptr(self.weights_dev()), nb, bs, startp, dv.ptr(x), dv.ptr(out),
                 x.numel(), _stream())

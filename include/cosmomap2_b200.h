@@ -112,6 +112,16 @@ int64_t cm2_toeplitz_scratch_bytes(int64_t nblocks);
 int cm2_noise_toeplitz_apply(const double *band, int nband, int64_t nblocks, int64_t blocksize,
                              const int64_t *blk_start, const double *d, double *out, int64_t nt,
                              void *scratch, cm2_stream_t stream);
+/* same operator by overlap-save FFT in shared memory (for wide bands: 2(2 nband - 1) flop/sample of
+ * the direct form become ~150).  coef[nblocks][2][M] complex fp64, M = cm2_toeplitz_fft_points():
+ * the packed transfer function C1, C2 of each block's band (see csrc/toeplitz_fft.cu), built on the
+ * host.  Requires 2 (nband-1) < M.  scratch: cm2_toeplitz_fft_scratch_bytes(nblocks) bytes; pass
+ * init != 0 on the first call with a given scratch (twiddle table). */
+int cm2_toeplitz_fft_points(void);
+int64_t cm2_toeplitz_fft_scratch_bytes(int64_t nblocks);
+int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
+                                 const int64_t *blk_start, const double *d, double *out,
+                                 int64_t nt, void *scratch, int init, cm2_stream_t stream);
 /* subscan offset filter (FilterLO.mult :129-168): out = 0; for each segment [seg_start[k],
  * seg_end[k]): mu = mean of d over unflagged samples; skipped if none; out = d - mu */
 int cm2_filter_offset_apply(const int32_t *pix, const int64_t *seg_start, const int64_t *seg_end,

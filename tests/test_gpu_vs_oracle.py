@@ -192,3 +192,27 @@ def test_krypy_style_arnoldi_and_two_level(cm):
     cm.cg(A, b, M=Mbd, rtol=1e-10, maxiter=500, residuals=it_bd)
     cm.cg(A, b, M=M2, rtol=1e-10, maxiter=500, residuals=it_m2)
     assert len(it_m2) <= len(it_bd)
+
+
+def test_toeplitz_fft_path_equals_direct_path(cm):
+    """Overlap-save FFT kernel vs the direct shared-memory kernel vs the oracle, multi-block."""
+    import oracle
+    from cosmomap2_b200 import linearoperators as lo
+    rng = np.random.default_rng(21)
+    for sizes, L in ((3 * [20000], 200), ([30000, 9000, 41000], 1000), ([50000], 4096)):
+        nt = sum(sizes)
+        v = rng.standard_normal(nt)
+        t = [np.concatenate([[1.0 + rng.random()], -0.3 * rng.random(L - 1) / L]) for _ in sizes]
+        old = lo.TOEPLITZ_FFT_MIN_BAND
+        try:
+            lo.TOEPLITZ_FFT_MIN_BAND = 10 ** 9
+            y_direct = cm.BlockLO(sizes, t, offdiag=True) * v
+            lo.TOEPLITZ_FFT_MIN_BAND = 2
+            N = cm.BlockLO(sizes, t, offdiag=True)
+            y_fft = N * v
+            assert N._fft is not None and N._fft.ok
+        finally:
+            lo.TOEPLITZ_FFT_MIN_BAND = old
+        y_ref = oracle.BlockLO(sizes, t, offdiag=True) * v
+        gc.close(y_direct, y_ref, what="direct Toeplitz L=%d" % L)
+        gc.close(y_fft, y_ref, what="FFT Toeplitz L=%d" % L)

@@ -66,6 +66,12 @@ def main():
     NT = cm.BlockLO(sc.ns, bands, offdiag=True)
     t = timeit(lambda: NT._apply(d), reps=5, warm=1); out["toeplitz64_ms"] = t
     out["toeplitz64_GFLOPs"] = 2.0 * (2 * 64 - 1) * nt / (t * 1e-3) / 1e9
+    for L in (256, 4096):
+        NTf = cm.BlockLO(sc.ns, synthetic.toeplitz_bands(64, L), offdiag=True)
+        t = timeit(lambda: NTf._apply(d), reps=3, warm=1)
+        out["toeplitz%d_fft_ms" % L] = t
+        out["toeplitz%d_fft_Msamples_s" % L] = nt / (t * 1e-3) / 1e6
+        out["toeplitz%d_equiv_direct_GFLOPs" % L] = 2.0 * (2 * L - 1) * nt / (t * 1e-3) / 1e9
     # deflation / two-level preconditioner at r = 32 (rows a10-a13): 8*r*n bytes per pass over Z
     r = 32
     Zt = torch.randn((r, n), dtype=torch.float64, device="cuda") / np.sqrt(n)
