@@ -24,7 +24,7 @@ class Scan(object):
 
 def raster_scan(nt, nside=512, ndet=64, nx=1000, ny=500, samples_per_pixel=8.0, seed=0,
                 flag_turnarounds=False, turnaround_frac=0.05, sigma=1.0, with_data=True,
-                sky_seed=1234):
+                sky_seed=1234, hwp_jitter=1e-3):
     """Raster scan of ``ndet`` detectors x ``nt // ndet`` samples over an ``nx x ny`` patch."""
     rng = np.random.default_rng(seed)
     ns = nt // ndet
@@ -57,7 +57,10 @@ def raster_scan(nt, nside=512, ndet=64, nx=1000, ny=500, samples_per_pixel=8.0, 
         if flag_turnarounds:
             p = np.where((frac < ta / 2) | (frac >= 1.0 - ta / 2), -1, p)
         pix[b * ns:(b + 1) * ns] = p
-        phi[b * ns:(b + 1) * ns] = theta0[b] + 2 * np.pi * 2.5 / 200. * t
+        # HWP ramp + encoder jitter.  Without jitter a pixel hit over whole HWP periods has an
+        # exactly isotropic QU block and the reference's condition-number mask evaluates
+        # sqrt(tr^2/4 - det) on +-1e-17: NaN or not depending on rounding.
+        phi[b * ns:(b + 1) * ns] = theta0[b] + 2 * np.pi * 2.5 / 200. * t + hwp_jitter * rng.standard_normal(ns)
     # subscan table shared by all detectors (reference: subscans[ces], tstart[ces])
     s0 = int(np.ceil(ta / 2 * sweep))
     s1 = int(np.floor((1.0 - ta / 2) * sweep))

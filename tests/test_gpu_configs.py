@@ -1,0 +1,153 @@
+"""Small-scale analogues of BASELINE.json's configurations, GPU product vs oracle end to end:
+identical seeded inputs, the same algorithm on both sides (SciPy cg over the oracle vs the device
+PCG), compared on solution, exit code, iteration count (+-1) and residual history."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+import golden_cases as gc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cm():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import cosmomap2_b200
+    return cosmomap2_b200
+
+
+def _build(impl, sc, pol, noise=None, filt=False, w_from_noise=True):
+    pix = sc.pix.astype(np.int64)
+    N = None
+    if noise == "white":
+        N = impl.BlockLO(sc.ns, sc.weights)
+    elif noise is not None:
+        N = impl.BlockLO(sc.ns, noise, offdiag=True)
+    w = N.diag if (noise == "white" and w_from_noise) else None
+    pts = impl.ProcessTimeSamples(pix, sc.npix_full, pol=pol, phi=sc.phi, w=w)
+    npix = pts.get_new_pixel[0]
+    P = impl.SparseLO(npix, sc.nt, pix, pol=pol, angle_processed=pts)
+    Mbd = impl.BlockDiagonalPreconditionerLO(pts, npix, pol=pol)
+    if filt:
+        F = impl.FilterLO(sc.nt, [sc.sub_len, sc.sub_start], sc.ns, sc.ndet, pix)
+        A = P.T * F * P
+        b = P.T * (F * sc.d)
+    elif N is not None:
+        A = P.T * N * P
+        b = P.T * (N * sc.d)
+    else:
+        A = P.T * P
+        b = P.T * sc.d
+    return npix, P, Mbd, A, b, pts
+
+
+def _solve_both(cm, sc, pol, rtol, maxiter, **kw):
+    import oracle
+    out = []
+    for impl, solver in ((oracle, spla.cg), (cm, cm.cg)):
+        npix, P, Mbd, A, b, pts = _build(impl, sc, pol, **kw)
+        hist = []
+        x, info = solver(A, b, M=Mbd, rtol=rtol, maxiter=maxiter,
+                         callback=lambda xk: hist.append(np.linalg.norm(b - A * np.asarray(xk))))
+        out.append((npix, b, x, info, np.array(hist)))
+    (n0, b0, x0, i0, h0), (n1, b1, x1, i1, h1) = out
+    assert n0 == n1 and i0 == i1
+    assert abs(len(h0) - len(h1)) <= 1
+    gc.close(b1, b0, what="rhs")
+    k = min(len(h0), len(h1))
+    if k:
+        floor = 1e-11 * np.linalg.norm(b0)      # residuals at rounding level are not comparable
+        assert np.all(np.abs(h1[:k] - h0[:k]) <= 1e-6 * h0[:k] + floor), "residual history differs"
+    return x0, x1, h0, h1
+
+
+def test_config0_ces_standin_unweighted_bd_pcg(cm):
+    """configs[0]: one CES, IQU nside=128, A = P^T P, cg(tol=1e-3, maxiter=10) -- the reference's
+    src/test_BD_precond_onto_real_data.py:26-47 on the synthetic stand-in for the absent CES file."""
+    from cosmomap2_b200 import synthetic
+    sc = synthetic.raster_scan(600000, nside=128, ndet=4, nx=160, ny=120, samples_per_pixel=12.0, seed=0,
+                               flag_turnarounds=True)
+    for pol in (1, 3):
+        x0, x1, h0, h1 = _solve_both(cm, sc, pol, 1e-3, 10)
+        gc.close(x1, x0, rtol=1e-9, what="map pol=%d" % pol)
+        assert len(h1) == 1          # exactly preconditioned: one iteration (src/test_BD...:52)
+
+
+def test_config1_white_noise_bd_pcg(cm):
+    """configs[1] at reduced size: white noise blocks, weights fed to M_BD -> 1 iteration."""
+    from cosmomap2_b200 import synthetic
+    sc = synthetic.raster_scan(800000, nside=64, ndet=16, nx=100, ny=60, samples_per_pixel=8.0, seed=2)
+    x0, x1, h0, h1 = _solve_both(cm, sc, 3, 1e-10, 20, noise="white")
+    gc.close(x1, x0, rtol=1e-9, what="map")
+    assert len(h1) == 1
+    # mismatched preconditioner (unit-weight M_BD): several iterations, same history on both sides
+    x0, x1, h0, h1 = _solve_both(cm, sc, 3, 1e-10, 100, noise="white", w_from_noise=False)
+    gc.close(x1, x0, rtol=1e-8, what="map (unit-weight M_BD)")
+    assert len(h1) > 3
+
+
+@pytest.mark.parametrize("nband", [16, 200])
+def test_config2_toeplitz_noise_bd_pcg(cm, nband):
+    """configs[2] at reduced size: per-detector banded Toeplitz N^-1 (direct kernel and FFT kernel)."""
+    from cosmomap2_b200 import synthetic
+    sc = synthetic.raster_scan(400000, nside=64, ndet=8, nx=90, ny=50, samples_per_pixel=6.0, seed=4,
+                               flag_turnarounds=True)
+    bands = synthetic.toeplitz_bands(sc.ndet, nband, seed=1)
+    x0, x1, h0, h1 = _solve_both(cm, sc, 3, 1e-9, 200, noise=bands)
+    gc.close(x1, x0, rtol=1e-7, what="map")
+    assert len(h1) > 2
+
+
+def test_config2_subscan_filter_bd_pcg(cm):
+    """configs[2]: subscan offset filtering, A = P^T F P (singular: compare A x and histories)."""
+    from cosmomap2_b200 import synthetic
+    import oracle
+    sc = synthetic.raster_scan(400000, nside=64, ndet=8, nx=90, ny=50, samples_per_pixel=6.0, seed=5,
+                               flag_turnarounds=True)
+    x0, x1, h0, h1 = _solve_both(cm, sc, 1, 1e-4, 25, filt=True)
+    npix, P, Mbd, A, b, pts = _build(oracle, sc, 1, filt=True)
+    gc.close(A * x1, A * x0, rtol=1e-6, what="A x (null space of P^T F P projected out)")
+
+
+def test_config3_two_level_from_arnoldi(cm):
+    """configs[3] at reduced size: deflation space from the preconditioned Arnoldi (krypy semantics),
+    coarse operator by eigendecomposition, M_2lvl PCG; GPU vs oracle on Ritz values, the deflated
+    subspace and the iteration counts."""
+    import oracle
+    from cosmomap2_b200 import synthetic
+    sc = synthetic.raster_scan(300000, nside=64, ndet=6, nx=60, ny=40, samples_per_pixel=6.0, seed=6,
+                               flag_turnarounds=True)
+    bands = synthetic.toeplitz_bands(sc.ndet, 24, seed=3, eps=0.9)
+    res = []
+    for impl, solver in ((oracle, spla.cg), (cm, cm.cg)):
+        npix, P, Mbd, A, b, pts = _build(impl, sc, 3, noise=bands)
+        n = 3 * npix
+        V, H, m = impl.run_krypy_arnoldi(A, np.ones(n), Mbd, 1e-5, maxiter=30, ortho="dmgs")
+        theta = np.sort(np.linalg.eigvalsh(H[:H.shape[1], :]))
+        r = 6
+        thr = 0.5 * (theta[r - 1] + theta[r])
+        Z, rr, th = impl.find_ritz_eigenvalues(H, V, threshold=thr, eigenvalues=True)
+        assert rr == r
+        Az = np.column_stack([A * np.ascontiguousarray(Z[:, i]) for i in range(r)])
+        E = impl.CoarseLO(Z, Az, r, apply="eig")
+        Zd, AZd = impl.DeflationLO(Z), impl.DeflationLO(Az)
+        M2 = Mbd * (impl.lp.IdentityOperator(n) - AZd * E * Zd.T) + Zd * E * Zd.T
+        it_bd, it_m2 = [], []
+        xb, ib = solver(A, b, M=Mbd, rtol=1e-9, maxiter=300, callback=lambda xk: it_bd.append(1))
+        xm, im = solver(A, b, M=M2, rtol=1e-9, maxiter=300, callback=lambda xk: it_m2.append(1))
+        assert ib == 0 and im == 0
+        res.append(dict(theta=theta, Z=np.asarray(Z), xb=xb, xm=xm, nbd=len(it_bd), nm2=len(it_m2)))
+    o, g = res
+    gc.close(g["theta"][:10], o["theta"][:10], rtol=1e-8, what="Ritz values")
+    # same deflation subspace (Z is defined up to rotation/sign): compare projectors on a probe
+    probe = np.random.default_rng(0).standard_normal(o["Z"].shape[0])
+    po = o["Z"].dot(np.linalg.lstsq(o["Z"], probe, rcond=None)[0])
+    pg = g["Z"].dot(np.linalg.lstsq(g["Z"], probe, rcond=None)[0])
+    gc.close(pg, po, rtol=1e-6, what="deflation subspace projector")
+    gc.close(g["xb"], o["xb"], rtol=1e-7, what="M_BD solution")
+    gc.close(g["xm"], o["xm"], rtol=1e-7, what="M_2lvl solution")
+    assert abs(g["nbd"] - o["nbd"]) <= 1 and abs(g["nm2"] - o["nm2"]) <= 1
+    assert g["nm2"] <= g["nbd"] + 3     # Ritz vectors after 30 steps are only roughly converged

@@ -216,3 +216,29 @@ def test_toeplitz_fft_path_equals_direct_path(cm):
         y_ref = oracle.BlockLO(sizes, t, offdiag=True) * v
         gc.close(y_direct, y_ref, what="direct Toeplitz L=%d" % L)
         gc.close(y_fft, y_ref, what="FFT Toeplitz L=%d" % L)
+
+
+def test_mask_differs_only_on_rounding_knife_edge_pixels(cm):
+    """The reference's good-pixel rule evaluates sqrt(tr^2/4 - det) (process_ces.py:544-549).  For a
+    pixel whose QU block is isotropic to rounding (hit over whole HWP periods) that argument is
+    +-1e-17: NaN (pixel dropped) or not, depending on the summation order of the moments.  The
+    GPU mask may differ from the serial oracle ONLY on such pixels."""
+    import oracle
+    from cosmomap2_b200 import synthetic
+    sc = synthetic.raster_scan(600000, nside=128, ndet=4, nx=160, ny=120, samples_per_pixel=12.0, seed=0,
+                               flag_turnarounds=True, hwp_jitter=0.0)
+    po = oracle.ProcessTimeSamples(sc.pix.astype(np.int64), sc.npix_full, pol=3, phi=sc.phi)
+    pg = cm.ProcessTimeSamples(sc.pix.astype(np.int64), sc.npix_full, pol=3, phi=sc.phi)
+    diff = np.setxor1d(np.asarray(po.mask), np.asarray(pg.mask))
+    pix = sc.pix.astype(np.int64)
+    g = pix >= 0
+    c, s = np.cos(2 * sc.phi[g]), np.sin(2 * sc.phi[g])
+    n = sc.npix_full
+    c2 = np.bincount(pix[g], weights=c * c, minlength=n)
+    s2 = np.bincount(pix[g], weights=s * s, minlength=n)
+    cs = np.bincount(pix[g], weights=s * c, minlength=n)
+    tr = c2 + s2
+    arg = tr * tr / 4 - (c2 * s2 - cs * cs)
+    knife = np.abs(arg[diff]) <= 1e-12 * tr[diff] ** 2
+    assert knife.all(), "mask differs on %d well-determined pixels" % int((~knife).sum())
+    assert len(diff) < 0.01 * len(po.mask)
