@@ -161,16 +161,27 @@ __device__ __forceinline__ void bd_z(const double *__restrict__ inv, int64_t j, 
     }
 }
 
-// start: z = M r, rho = r.z, |r|^2, flags
+// start: z = M r, rho = r.z, |r|^2, flags.  With b != nullptr it also performs the x0 = 0 start of
+// the solve in the same pass: r = b, x = 0.
 template <int POL>
-__global__ void __launch_bounds__(VB) k_bd_reset(const double *__restrict__ inv, int64_t npix, const double *__restrict__ r,
-                                                 double *__restrict__ z, double *__restrict__ scal, double atol) {
+__global__ void __launch_bounds__(VB) k_bd_reset(const double *__restrict__ inv, int64_t npix, double *__restrict__ r,
+                                                 double *__restrict__ z, double *__restrict__ scal, double atol,
+                                                 const double *__restrict__ b, double *__restrict__ x) {
     __shared__ double red[32];
     double s[2] = {0.0, 0.0}, tot[2];
     for (int64_t j = (int64_t)blockIdx.x * VB + threadIdx.x; j < npix; j += (int64_t)gridDim.x * VB) {
         double rv[POL], zv[POL];
+        if (b != nullptr) {
 #pragma unroll
-        for (int k = 0; k < POL; ++k) rv[k] = r[POL * j + k];
+            for (int k = 0; k < POL; ++k) {
+                rv[k] = b[POL * j + k];
+                r[POL * j + k] = rv[k];
+                x[POL * j + k] = 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < POL; ++k) rv[k] = r[POL * j + k];
+        }
         bd_z<POL>(inv, j, rv, zv);
 #pragma unroll
         for (int k = 0; k < POL; ++k) {
@@ -281,15 +292,16 @@ extern "C" int cm2_pcg_update_xr(const double *p, const double *q, double *x, do
     return CM2_OK;
 }
 
-extern "C" int cm2_pcg_bd_reset(const double *inv, int64_t npix, int pol, const double *r, double *z, double *scal,
-                                double atol, cm2_stream_t stream) {
+extern "C" int cm2_pcg_bd_reset(const double *inv, int64_t npix, int pol, double *r, double *z, double *scal,
+                                double atol, const double *b, double *x, cm2_stream_t stream) {
     CM2_REQUIRE(npix >= 0 && pol >= 1 && pol <= 3, "bad npix/pol");
     CM2_REQUIRE(aligned(inv, 16), "inverse blocks must be 16-byte aligned");
+    CM2_REQUIRE((b == nullptr) == (x == nullptr), "b and x go together");
     cudaStream_t st = as_stream(stream);
     const int g = vgrid(npix);
-    if (pol == 1) k_bd_reset<1><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol);
-    else if (pol == 2) k_bd_reset<2><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol);
-    else k_bd_reset<3><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol);
+    if (pol == 1) k_bd_reset<1><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol, b, x);
+    else if (pol == 2) k_bd_reset<2><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol, b, x);
+    else k_bd_reset<3><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol, b, x);
     CM2_LAUNCHED();
     return CM2_OK;
 }

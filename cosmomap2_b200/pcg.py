@@ -92,6 +92,12 @@ class PCG(object):
     def start(self, b, x0=None, atol=0.0):
         """x <- x0 (or 0), r <- b - A x0, device scalars reset.  ``b`` is a CUDA fp64 tensor."""
         n, st = self.n, dv.stream
+        if x0 is None and self.bd is not None:
+            # x0 = 0 with M_BD: r = b, x = 0, z = M r, rho, ||r||^2 in ONE pass
+            dv.call("cm2_pcg_bd_reset", dv.ptr(self.bd._inv_dev), self.bd._n, self.bd.pol, dv.ptr(self.r),
+                    dv.ptr(self.z), dv.ptr(self.scal), float(atol), dv.ptr(b), dv.ptr(self.x), st())
+            self._queued = 0
+            return
         self.r.copy_(b)
         if x0 is None:
             self.x.zero_()
@@ -102,7 +108,7 @@ class PCG(object):
                 dv.call("cm2_axpby", -1.0, dv.ptr(ax), 1.0, dv.ptr(self.r), n, st())
         if self.bd is not None:
             dv.call("cm2_pcg_bd_reset", dv.ptr(self.bd._inv_dev), self.bd._n, self.bd.pol, dv.ptr(self.r),
-                    dv.ptr(self.z), dv.ptr(self.scal), float(atol), st())
+                    dv.ptr(self.z), dv.ptr(self.scal), float(atol), None, None, st())
         else:
             dv.call("cm2_pcg_reset", dv.ptr(self.r), n, dv.ptr(self.scal), float(atol), st())
         self._queued = 0

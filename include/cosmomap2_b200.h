@@ -182,11 +182,12 @@ int cm2_pcg_update_xr(const double *p, const double *q, double *x, double *r, in
                       double *scal, cm2_stream_t stream);
 /* M = M_BD fast path (the preconditioner is pixel-local, so z = M r and rho = r.z ride in the
  * kernel that updates r):
- *   bd_reset   : z = M r ; rho = r.z ; |r|^2 ; atol ; flags
+ *   bd_reset   : z = M r ; rho = r.z ; |r|^2 ; atol ; flags.  With b, x non-NULL the x0 = 0 start
+ *                of the solve happens in the same pass (r = b, x = 0); pass both NULL otherwise
  *   bd_update_p: p = z + beta p
  *   bd_update  : pq ; alpha ; x += alpha p ; r -= alpha q ; z = M r ; rho' ; beta' ; |r|^2 ; flags */
-int cm2_pcg_bd_reset(const double *bd_inv, int64_t npix, int pol, const double *r, double *z,
-                     double *scal, double atol, cm2_stream_t stream);
+int cm2_pcg_bd_reset(const double *bd_inv, int64_t npix, int pol, double *r, double *z,
+                     double *scal, double atol, const double *b, double *x, cm2_stream_t stream);
 int cm2_pcg_bd_update_p(const double *z, double *p, int64_t n, double *scal, cm2_stream_t stream);
 int cm2_pcg_bd_update(const double *bd_inv, int64_t npix, int pol, const double *p,
                       const double *q, double *x, double *r, double *z, double *scal,
