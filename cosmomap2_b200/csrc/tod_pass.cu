@@ -15,6 +15,8 @@
 // its 8 samples into runs in registers, (2) the open runs at lane boundaries are merged across the
 // warp with a segmented shuffle scan, (3) one fp64 RED per (run, Stokes component) goes to L2.
 // Random pointing degenerates gracefully to one RED per sample and component.
+#include <cstdint>
+
 #include "cm2_common.cuh"
 
 namespace cm2 {
@@ -319,6 +321,98 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_white(const int32_t *__restri
     }
 }
 
+// Fused y = P^T (P x - mu_seg) over the unflagged samples inside subscans: the offset-filtered
+// A-matvec in ONE pass over the TOD, given the subscan means mu (k_seg_mean, filter_runs.cu).
+// tile_seg[tile] = index of the first segment whose end lies beyond the tile's first sample.
+struct SegInfo {
+    const int64_t *start, *end;   // nseg, sorted, non-overlapping
+    const double *mu;             // nseg
+    const int32_t *tile_seg;      // ntiles: first segment ending beyond the tile's first sample
+    const uint8_t *tile_flag;     // ntiles: 0 = tile outside every segment, 1 = inside one, 2 = mixed
+    int64_t nseg;
+};
+
+template <int POL>
+__global__ void __launch_bounds__(BLOCK) k_amatvec_filter_mu(const int32_t *__restrict__ pix, const double *__restrict__ cs,
+                                                             const double *__restrict__ sn, int64_t nt, SegInfo sg,
+                                                             const double *__restrict__ x, double *__restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
+    const int64_t ntiles = (nt + TILE - 1) / TILE;
+    int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+    if (tile >= ntiles) return;
+    int p[K];
+    double c[K], s[K];
+    int flag, k0;
+    double m0;
+    {
+        const int64_t t0 = tile * TILE + (int64_t)lane * K;
+        load_pix(pix, t0, nt, p);
+        if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
+        flag = __ldg(sg.tile_flag + tile);
+        k0 = __ldg(sg.tile_seg + tile);
+        m0 = flag == 1 ? __ldg(sg.mu + k0) : 0.0;
+    }
+    for (; tile < ntiles; tile += nwarps) {
+        const int64_t t0 = tile * TILE + (int64_t)lane * K;
+        double mu[K];
+        if (flag == 1) {                       // the whole tile lies inside subscan k0 (the common case)
+#pragma unroll
+            for (int j = 0; j < K; ++j) mu[j] = m0;
+        } else if (flag == 0) {                // the whole tile lies in a gap
+#pragma unroll
+            for (int j = 0; j < K; ++j) { mu[j] = 0.0; p[j] = -1; }
+        } else {                               // a subscan boundary falls inside the tile
+            int64_t k = k0;
+            while (k < sg.nseg && __ldg(sg.end + k) <= t0) ++k;
+            int64_t a = k < sg.nseg ? __ldg(sg.start + k) : INT64_MAX, b = k < sg.nseg ? __ldg(sg.end + k) : INT64_MAX;
+            double m = k < sg.nseg ? __ldg(sg.mu + k) : 0.0;
+            if (t0 >= a && t0 + K <= b) {      // this lane's chunk is still inside one subscan
+#pragma unroll
+                for (int j = 0; j < K; ++j) mu[j] = m;
+            } else if (t0 + K <= a) {          // ... or entirely in a gap
+#pragma unroll
+                for (int j = 0; j < K; ++j) { mu[j] = 0.0; p[j] = -1; }
+            } else {                           // the boundary is inside this lane's 8 samples
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int64_t t = t0 + j;
+                    while (k < sg.nseg && t >= b) {
+                        ++k;
+                        a = k < sg.nseg ? __ldg(sg.start + k) : INT64_MAX;
+                        b = k < sg.nseg ? __ldg(sg.end + k) : INT64_MAX;
+                        m = k < sg.nseg ? __ldg(sg.mu + k) : 0.0;
+                    }
+                    if (t < a || k >= sg.nseg) p[j] = -1;
+                    mu[j] = m;
+                }
+            }
+        }
+        RunState<POL> rs;
+        {
+            double xv[K][POL], v[K];
+            gather_x<POL>(x, p, xv);
+#pragma unroll
+            for (int j = 0; j < K; ++j) v[j] = project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0) - mu[j];
+            run_compress<POL, POL>(y, p, [&](int j, double (&o)[POL]) {
+                if constexpr (POL == 1) { o[0] = v[j]; }
+                else if constexpr (POL == 2) { o[0] = v[j] * c[j]; o[1] = v[j] * s[j]; }
+                else { o[0] = v[j]; o[1] = v[j] * c[j]; o[2] = v[j] * s[j]; }
+            }, rs);
+        }
+        const int64_t nxt = tile + nwarps;
+        if (nxt < ntiles) {   // warp-uniform: next tile's TOD loads and subscan info overlap the merge
+            const int64_t t1 = nxt * TILE + (int64_t)lane * K;
+            load_pix(pix, t1, nt, p);
+            if (POL > 1) { load_f64(cs, t1, nt, c); load_f64(sn, t1, nt, s); }
+            flag = __ldg(sg.tile_flag + nxt);
+            k0 = __ldg(sg.tile_seg + nxt);
+            m0 = flag == 1 ? __ldg(sg.mu + k0) : 0.0;
+        }
+        run_merge<POL, POL>(y, rs);
+    }
+}
+
 // moments layout: mom[npix][6] = {h, c, s, c2, cs, s2}; pol=1 fills {h}, pol=2 {c2,cs,s2}, pol=3 all
 template <int POL>
 __global__ void __launch_bounds__(BLOCK) k_moments(const int32_t *__restrict__ pix, const double *__restrict__ cs,
@@ -605,6 +699,24 @@ extern "C" int cm2_amatvec_filter(const int32_t *pix, const double *c, const dou
         CM2_CUDA(cudaFuncSetAttribute(k_amatvec_filter<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_amatvec_filter<3><<<persistent_grid(k_amatvec_filter<3>, BLOCK, smem, nseg), BLOCK, smem, st>>>(pix, c, s, nt, seg_start, seg_end, nseg, x, y);
     }
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+extern "C" int cm2_amatvec_filter_mu(const int32_t *pix, const double *c, const double *s, int64_t nt, int pol,
+                                     const int64_t *seg_start, const int64_t *seg_end, const double *seg_mu,
+                                     const int32_t *tile_seg, const uint8_t *tile_flag, int64_t nseg, const double *x,
+                                     double *y, int64_t npix, cm2_stream_t stream) {
+    int rc = check_tod(pix, c, s, nt, pol);
+    if (rc) return rc;
+    CM2_REQUIRE(npix >= 0 && nseg >= 0, "negative size");
+    cudaStream_t st = as_stream(stream);
+    if (npix > 0) CM2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)npix * pol, st));
+    if (nt == 0 || npix == 0 || nseg == 0) return CM2_OK;
+    SegInfo sg{seg_start, seg_end, seg_mu, tile_seg, tile_flag, nseg};
+    if (pol == 1) k_amatvec_filter_mu<1><<<tod_grid(k_amatvec_filter_mu<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, y);
+    else if (pol == 2) k_amatvec_filter_mu<2><<<tod_grid(k_amatvec_filter_mu<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, y);
+    else k_amatvec_filter_mu<3><<<tod_grid(k_amatvec_filter_mu<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, y);
     CM2_LAUNCHED();
     return CM2_OK;
 }

@@ -435,15 +435,77 @@ class _FusedWhiteA(lp.LinearOperator):
         return y
 
 
+FILTER_RUN_TABLE = True     # single-TOD-pass P^T F P through the run-compressed u_k table
+
+
 class _FusedFilterA(lp.LinearOperator):
+    """P^T F P as one operator.  Default: the subscan means from the run-compressed table of
+    u_k = P^T 1_k (csrc/filter_runs.cu), then ONE fused gather/scatter pass over the TOD; the table
+    is built on the device at first use and is used when the segments are sorted and the scan has
+    runs (>= 2 samples per run on average).  Otherwise: the two-pass kernel cm2_amatvec_filter."""
+
     def __init__(self, P, F):
         self.P, self.F = P, F
+        self._runs = None
         n = P.pol * P.ncols
         super(_FusedFilterA, self).__init__(n, n, matvec=self._run, symmetric=True, device=True)
+
+    def _build_runs(self):
+        P, F = self.P, self.F
+        nt, st = P.nrows, _stream()
+        dev = P._pix_dev.device
+        ss, se = F._seg_start_host, F._seg_end_host
+        if F.nseg == 0 or np.any(ss[1:] < se[:-1]):
+            return False                                    # unsorted / overlapping subscans
+        flags = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
+        pixm = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
+        dv.call("cm2_filter_runs_mark", dv.ptr(P._pix_dev), dv.ptr(F._seg_start), dv.ptr(F._seg_end), F.nseg, nt,
+                dv.ptr(flags), dv.ptr(pixm), st)
+        runidx = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
+        count = torch.zeros(1, dtype=torch.int64, device=dev)
+        scratch = torch.empty(int(dv.call("cm2_scan_scratch_bytes", nt)) // 8 + 1, dtype=torch.int64, device=dev)
+        dv.call("cm2_weights_old2new", dv.ptr(flags), nt, dv.ptr(runidx), dv.ptr(count), dv.ptr(scratch), st)
+        nruns = int(count.item())
+        del flags, scratch
+        if nruns == 0 or 2 * nruns > nt:
+            return False
+        run_pix = torch.empty(nruns, dtype=torch.int32, device=dev)
+        run_mom = torch.empty(3 * nruns, dtype=torch.float64, device=dev)
+        seg_first = torch.empty(max(F.nseg, 1), dtype=torch.int64, device=dev)
+        seg_nruns = torch.empty(max(F.nseg, 1), dtype=torch.int32, device=dev)
+        dv.call("cm2_filter_runs_fill", dv.ptr(pixm), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.pol,
+                dv.ptr(F._seg_start), dv.ptr(F._seg_end), F.nseg, dv.ptr(runidx), dv.ptr(run_pix), dv.ptr(run_mom),
+                dv.ptr(seg_first), dv.ptr(seg_nruns), st)
+        del pixm, runidx
+        # first segment whose end lies beyond the first sample of every 256-sample tile
+        ntiles = (nt + 255) // 256
+        tile_t0 = torch.arange(ntiles, dtype=torch.int64, device=dev) * 256
+        tile_seg = torch.searchsorted(F._seg_end, tile_t0, right=True)
+        kk = torch.clamp(tile_seg, max=F.nseg - 1)
+        a, b = F._seg_start[kk], F._seg_end[kk]
+        t1 = torch.clamp(tile_t0 + 256, max=nt)
+        inside = (tile_seg < F.nseg) & (a <= tile_t0) & (t1 <= b)
+        outside = (tile_seg >= F.nseg) | (a >= t1)
+        tile_flag = torch.full((ntiles,), 2, dtype=torch.uint8, device=dev)
+        tile_flag[inside] = 1
+        tile_flag[outside] = 0
+        mu = torch.empty(max(F.nseg, 1), dtype=torch.float64, device=dev)
+        return dict(run_pix=run_pix, run_mom=run_mom, seg_first=seg_first, seg_nruns=seg_nruns, nruns=nruns,
+                    tile_seg=tile_seg.to(torch.int32), tile_flag=tile_flag, mu=mu)
 
     def _run(self, x):
         P, F = self.P, self.F
         y = dv.empty_f64(P.ncols * P.pol)
+        if self._runs is None:
+            self._runs = self._build_runs() if FILTER_RUN_TABLE else False
+        rt = self._runs
+        if rt:
+            dv.call("cm2_filter_seg_mean", dv.ptr(rt["run_pix"]), dv.ptr(rt["run_mom"]), dv.ptr(rt["seg_first"]),
+                    dv.ptr(rt["seg_nruns"]), F.nseg, P.pol, dv.ptr(x), dv.ptr(rt["mu"]), _stream())
+            dv.call("cm2_amatvec_filter_mu", dv.ptr(P._pix_dev), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.nrows,
+                    P.pol, dv.ptr(F._seg_start), dv.ptr(F._seg_end), dv.ptr(rt["mu"]), dv.ptr(rt["tile_seg"]),
+                    dv.ptr(rt["tile_flag"]), F.nseg, dv.ptr(x), dv.ptr(y), P.ncols, _stream())
+            return y
         dv.call("cm2_amatvec_filter", dv.ptr(P._pix_dev), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.nrows, P.pol,
                 dv.ptr(F._seg_start), dv.ptr(F._seg_end), F.nseg, dv.ptr(x), dv.ptr(y), P.ncols, _stream())
         return y

@@ -140,6 +140,30 @@ int cm2_amatvec_filter(const int32_t *pix, const double *cos2phi, const double *
                        int64_t nseg, const double *x, double *y, int64_t npix,
                        cm2_stream_t stream);
 
+/* Single-TOD-pass P^T F P x (csrc/filter_runs.cu): u_k = P^T 1_k of every subscan is kept
+ * run-compressed -- run_pix[nruns], run_mom[nruns][3] = {n, sum cos, sum sin}, per segment seg_first,
+ * seg_nruns.  Build: runs_mark (flags[nt] at run starts, pix_masked[nt] = pix inside segments else
+ * -1) -> exclusive scan of flags (cm2_weights_old2new) -> runs_fill.  Apply: seg_mean
+ * (mu_k = u_k.x / n_k over the run table) -> amatvec_filter_mu: y = P^T (P x - mu_seg) over the
+ * unflagged samples inside segments in one TOD pass.  Segments must be sorted and non-overlapping;
+ * tile_seg[ceil(nt/256)] = first segment whose end lies beyond sample 256*tile; tile_flag = 0 (tile
+ * in a gap), 1 (tile inside segment tile_seg) or 2 (a boundary falls inside the tile). */
+int cm2_filter_runs_mark(const int32_t *pix, const int64_t *seg_start, const int64_t *seg_end,
+                         int64_t nseg, int64_t nt, int32_t *flags, int32_t *pix_masked,
+                         cm2_stream_t stream);
+int cm2_filter_runs_fill(const int32_t *pix_masked, const double *cos2phi, const double *sin2phi,
+                         int pol, const int64_t *seg_start, const int64_t *seg_end, int64_t nseg,
+                         const int32_t *runidx, int32_t *run_pix, double *run_mom,
+                         int64_t *seg_first, int32_t *seg_nruns, cm2_stream_t stream);
+int cm2_filter_seg_mean(const int32_t *run_pix, const double *run_mom, const int64_t *seg_first,
+                        const int32_t *seg_nruns, int64_t nseg, int pol, const double *x,
+                        double *mu, cm2_stream_t stream);
+int cm2_amatvec_filter_mu(const int32_t *pix, const double *cos2phi, const double *sin2phi,
+                          int64_t nt, int pol, const int64_t *seg_start, const int64_t *seg_end,
+                          const double *seg_mu, const int32_t *tile_seg, const uint8_t *tile_flag,
+                          int64_t nseg, const double *x, double *y, int64_t npix,
+                          cm2_stream_t stream);
+
 /* ---- a10/a11/a13: deflation, coarse operator, two-level preconditioner ---------------------- */
 /* Z is n x r, column-major (column i at Z + i*ldz), as DeflationLO stores columns (:1058-1062).
  * `work`: cm2_defl_work_doubles(r) doubles of device scratch. */

@@ -242,3 +242,36 @@ def test_mask_differs_only_on_rounding_knife_edge_pixels(cm):
     knife = np.abs(arg[diff]) <= 1e-12 * tr[diff] ** 2
     assert knife.all(), "mask differs on %d well-determined pixels" % int((~knife).sum())
     assert len(diff) < 0.01 * len(po.mask)
+
+
+@pytest.mark.parametrize("pol", [1, 2, 3])
+def test_filter_run_table_path_equals_two_pass_path(cm, pol):
+    """P^T F P through the run-compressed table (one TOD pass) == the two-pass kernel == oracle."""
+    import oracle
+    from cosmomap2_b200 import linearoperators as lo
+    sc = _raster(nt=300000, ndet=6, seed=8, flag_turnarounds=True)
+    rng = np.random.default_rng(3)
+    flagged = rng.random(sc.nt) < 0.02                 # flags inside subscans too
+    sc.pix[flagged] = -1
+    res = {}
+    for name, impl, table in (("oracle", oracle, None), ("table", cm, True), ("twopass", cm, False)):
+        pix = sc.pix.astype(np.int64)
+        pts = impl.ProcessTimeSamples(pix, sc.npix_full, pol=pol, phi=sc.phi)
+        npix = pts.get_new_pixel[0]
+        P = impl.SparseLO(npix, sc.nt, pix, pol=pol, angle_processed=pts)
+        F = impl.FilterLO(sc.nt, [sc.sub_len, sc.sub_start], sc.ns, sc.ndet, pix)
+        x = np.random.default_rng(4).standard_normal(pol * npix)
+        if table is None:
+            res[name] = P.T * (F * (P * x))
+            continue
+        old = lo.FILTER_RUN_TABLE
+        lo.FILTER_RUN_TABLE = table
+        try:
+            A = P.T * F * P
+            res[name] = A * x
+            fused = [f for f in A.planned() if isinstance(f, lo._FusedFilterA)][0]
+            assert bool(fused._runs) == table
+        finally:
+            lo.FILTER_RUN_TABLE = old
+    gc.close(res["table"], res["oracle"], what="run-table path")
+    gc.close(res["twopass"], res["oracle"], what="two-pass path")
