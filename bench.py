@@ -233,6 +233,17 @@ def main():
     for _ in range(max(args.warmup, 3)):
         one_step()
     barrier()
+    if world > 1 and getattr(A, "_p2p", None) is not None:
+        # the peer-memory exchange must never have timed out; if it did on any rank, every rank
+        # falls back to NCCL for the measurement (and says so in `config.parallelism`)
+        bad = torch.tensor([1.0 if A._p2p.error() != 0 else 0.0], device="cuda")
+        dist.all_reduce(bad)
+        if bad.item() != 0:
+            sys.stderr.write("[bench] P2P all-reduce timed out on some rank: falling back to NCCL\n")
+            A.close()
+            for _ in range(3):
+                one_step()
+            barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = _cabi.launch_count()
     A_timed.record = True
@@ -360,6 +371,7 @@ def main():
     if world > 1:
         A.check()
         A.close()
+        dist.barrier()
         dist.destroy_process_group()
 
 
