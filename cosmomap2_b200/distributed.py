@@ -151,6 +151,14 @@ class AllReduceLO(lp.LinearOperator):
             self._p2p = None
 
     def _run(self, x):
+        y = self.apply_transient(x)
+        if self._p2p is not None:
+            return y.clone()        # the exchange buffer is reused by the next call: hand out a copy
+        return y
+
+    def apply_transient(self, x):
+        """Like ``_apply`` but the result may alias an internal buffer that the NEXT application
+        overwrites (what the PCG loop wants: q = A p is consumed before A is applied again)."""
         y = self.local._apply(x)
         if self._p2p is not None:
             return self._p2p(y)

@@ -113,18 +113,23 @@ class PCG(object):
             dv.call("cm2_pcg_reset", dv.ptr(self.r), n, dv.ptr(self.scal), float(atol), st())
         self._queued = 0
 
+    def _apply_A(self, p):
+        # q = A p is consumed inside the iteration: a transient (buffer-aliasing) result is fine
+        f = getattr(self.A, "apply_transient", None)
+        return f(p) if f is not None else self.A._apply(p)
+
     def step_async(self):
         """Queue one iteration (no host synchronisation)."""
         n, st = self.n, dv.stream
         if self.bd is not None:
             dv.call("cm2_pcg_bd_update_p", dv.ptr(self.z), dv.ptr(self.p), n, dv.ptr(self.scal), st())
-            q = self.A._apply(self.p)
+            q = self._apply_A(self.p)
             dv.call("cm2_pcg_bd_update", dv.ptr(self.bd._inv_dev), self.bd._n, self.bd.pol, dv.ptr(self.p), dv.ptr(q),
                     dv.ptr(self.x), dv.ptr(self.r), dv.ptr(self.z), dv.ptr(self.scal), st())
         else:
             z = self.M._apply(self.r)
             dv.call("cm2_pcg_update_p", dv.ptr(self.r), dv.ptr(z), dv.ptr(self.p), n, dv.ptr(self.scal), st())
-            q = self.A._apply(self.p)
+            q = self._apply_A(self.p)
             dv.call("cm2_pcg_update_xr", dv.ptr(self.p), dv.ptr(q), dv.ptr(self.x), dv.ptr(self.r), n,
                     dv.ptr(self.scal), st())
         self._queued += 1
