@@ -3,8 +3,8 @@
 // ToeplitzLO.mult (interfaces/linearoperators.py:582-595) is y_j = sum_{|k|<L} a_|k| v_{j-k} with
 // zero boundaries: 2(2L-1) flop/sample done directly, i.e. 16 382 flop/sample at the L = 4096 of
 // configs[2] -- 100x more time than the 16 B/sample of HBM traffic.  Here each CTA takes one window
-// of NF = 2M real samples (M complex points, 128 kB of shared memory), runs an in-place radix-2
-// DIF FFT (output bit-reversed), applies the real, even transfer function of the band in the
+// of NF = 2M real samples (M complex points, 128 kB of shared memory), runs an in-place DIF FFT
+// (radix-2 stages fused in pairs, i.e. radix-4 passes; output bit-reversed), applies the real, even transfer function of the band in the
 // bit-reversed domain, runs the inverse in-place DIT FFT (input bit-reversed, output natural) and
 // writes the NF - 2(L-1) alias-free outputs.  No reordering pass, no global scratch.
 //
@@ -15,8 +15,8 @@
 // is the packed spectrum of the filtered window (derivation in DESIGN.md); C1 = Hs + i Hd w^-k and
 // C2 = Hd w^k + i Hs are precomputed per noise block on the host, 1/M folded in.
 //
-// Bound: shared-memory bandwidth (each radix-2 stage moves 64 B per butterfly), ~60x fewer flops
-// than the direct form at L = 4096.
+// Bound: shared-memory bandwidth (each fused pass moves 128 B per 4-point butterfly, 7 passes per
+// transform), ~60x fewer flops than the direct form at L = 4096.
 #include "cm2_common.cuh"
 
 namespace cm2 {
@@ -70,16 +70,36 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             z[i] = v;
         }
         __syncthreads();
-        // ---- forward FFT: radix-2 decimation in frequency, natural in -> bit-reversed out
-        for (int lm = FFT_LOG2M - 1; lm >= 0; --lm) {
-            const int m = 1 << lm;
+        // ---- forward FFT, decimation in frequency, natural in -> bit-reversed out.  Two radix-2
+        // stages (half-sizes 2q and q) are fused per pass: 4 points per thread stay in registers, so
+        // the shared-memory traffic and the number of barriers are halved.
+        for (int lq = FFT_LOG2M - 2; lq >= 0; lq -= 2) {
+            const int q = 1 << lq;
+            for (int j = threadIdx.x; j < FFT_M / 4; j += FFT_THREADS) {
+                const int pos = j & (q - 1);
+                const int i0 = ((j >> lq) << (lq + 2)) + pos;
+                const double2 z0 = z[i0], z1 = z[i0 + q], z2 = z[i0 + 2 * q], z3 = z[i0 + 3 * q];
+                // stage with half-size 2q: pairs (0,2) and (1,3)
+                const double2 w1a = __ldg(tw + (pos << (FFT_LOG2M - 2 - lq)));
+                const double2 w1b = __ldg(tw + ((pos + q) << (FFT_LOG2M - 2 - lq)));
+                const double2 a0 = make_double2(z0.x + z2.x, z0.y + z2.y);
+                const double2 a2 = cmul(make_double2(z0.x - z2.x, z0.y - z2.y), w1a);
+                const double2 a1 = make_double2(z1.x + z3.x, z1.y + z3.y);
+                const double2 a3 = cmul(make_double2(z1.x - z3.x, z1.y - z3.y), w1b);
+                // stage with half-size q: pairs (0,1) and (2,3)
+                const double2 w2 = __ldg(tw + (pos << (FFT_LOG2M - 1 - lq)));
+                z[i0] = make_double2(a0.x + a1.x, a0.y + a1.y);
+                z[i0 + q] = cmul(make_double2(a0.x - a1.x, a0.y - a1.y), w2);
+                z[i0 + 2 * q] = make_double2(a2.x + a3.x, a2.y + a3.y);
+                z[i0 + 3 * q] = cmul(make_double2(a2.x - a3.x, a2.y - a3.y), w2);
+            }
+            __syncthreads();
+        }
+        if (FFT_LOG2M & 1) {   // odd number of stages: one last radix-2 stage with half-size 1
             for (int j = threadIdx.x; j < FFT_M / 2; j += FFT_THREADS) {
-                const int pos = j & (m - 1);
-                const int i = ((j >> lm) << (lm + 1)) + pos;
-                const double2 a = z[i], bb = z[i + m];
-                const double2 w = __ldg(tw + (pos << (FFT_LOG2M - 1 - lm)));
-                z[i] = make_double2(a.x + bb.x, a.y + bb.y);
-                z[i + m] = cmul(make_double2(a.x - bb.x, a.y - bb.y), w);
+                const double2 a = z[2 * j], bb = z[2 * j + 1];
+                z[2 * j] = make_double2(a.x + bb.x, a.y + bb.y);
+                z[2 * j + 1] = make_double2(a.x - bb.x, a.y - bb.y);
             }
             __syncthreads();
         }
@@ -102,17 +122,37 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             if (km != k) z[pm] = make_double2(b1.x + b2.x, b1.y + b2.y);
         }
         __syncthreads();
-        // ---- inverse FFT: radix-2 decimation in time, bit-reversed in -> natural out (conj twiddles)
-        for (int lm = 0; lm < FFT_LOG2M; ++lm) {
-            const int m = 1 << lm;
+        // ---- inverse FFT, decimation in time, bit-reversed in -> natural out (conjugate twiddles),
+        // again two radix-2 stages (half-sizes q and 2q) per pass
+        int lq0 = 0;
+        if (FFT_LOG2M & 1) {   // the stage with half-size 1 first
             for (int j = threadIdx.x; j < FFT_M / 2; j += FFT_THREADS) {
-                const int pos = j & (m - 1);
-                const int i = ((j >> lm) << (lm + 1)) + pos;
-                double2 w = __ldg(tw + (pos << (FFT_LOG2M - 1 - lm)));
+                const double2 a = z[2 * j], bb = z[2 * j + 1];
+                z[2 * j] = make_double2(a.x + bb.x, a.y + bb.y);
+                z[2 * j + 1] = make_double2(a.x - bb.x, a.y - bb.y);
+            }
+            __syncthreads();
+            lq0 = 1;
+        }
+        for (int lq = lq0; lq < FFT_LOG2M; lq += 2) {
+            const int q = 1 << lq;
+            for (int j = threadIdx.x; j < FFT_M / 4; j += FFT_THREADS) {
+                const int pos = j & (q - 1);
+                const int i0 = ((j >> lq) << (lq + 2)) + pos;
+                double2 w = __ldg(tw + (pos << (FFT_LOG2M - 1 - lq)));       // half-size q
                 w.y = -w.y;
-                const double2 a = z[i], bb = cmul(z[i + m], w);
-                z[i] = make_double2(a.x + bb.x, a.y + bb.y);
-                z[i + m] = make_double2(a.x - bb.x, a.y - bb.y);
+                const double2 z0 = z[i0], z1 = cmul(z[i0 + q], w), z2 = z[i0 + 2 * q], z3 = cmul(z[i0 + 3 * q], w);
+                const double2 a0 = make_double2(z0.x + z1.x, z0.y + z1.y), a1 = make_double2(z0.x - z1.x, z0.y - z1.y);
+                const double2 a2 = make_double2(z2.x + z3.x, z2.y + z3.y), a3 = make_double2(z2.x - z3.x, z2.y - z3.y);
+                double2 wa = __ldg(tw + (pos << (FFT_LOG2M - 2 - lq)));       // half-size 2q, position pos
+                double2 wb = __ldg(tw + ((pos + q) << (FFT_LOG2M - 2 - lq))); // half-size 2q, position pos+q
+                wa.y = -wa.y;
+                wb.y = -wb.y;
+                const double2 b2 = cmul(a2, wa), b3 = cmul(a3, wb);
+                z[i0] = make_double2(a0.x + b2.x, a0.y + b2.y);
+                z[i0 + 2 * q] = make_double2(a0.x - b2.x, a0.y - b2.y);
+                z[i0 + q] = make_double2(a1.x + b3.x, a1.y + b3.y);
+                z[i0 + 3 * q] = make_double2(a1.x - b3.x, a1.y - b3.y);
             }
             __syncthreads();
         }
