@@ -42,7 +42,7 @@ __global__ void k_fft_twiddles(double2 *__restrict__ tw) {
 
 // one CTA per window.  win_first[b] = first window index of noise block b (prefix, nblocks+1).
 __global__ void __launch_bounds__(FFT_THREADS, 1)
-    k_toeplitz_fft(const double2 *__restrict__ coef,   // [nblocks][2][M]: C1 then C2 (natural k order)
+    k_toeplitz_fft(const double2 *__restrict__ coef,   // [nblocks][2][M]: C1 then C2, indexed by PHYSICAL (bit-reversed) position
                    const double2 *__restrict__ tw, int L, int64_t nblocks, int64_t blocksize,
                    const int64_t *__restrict__ start, const int64_t *__restrict__ win_first,
                    const double *__restrict__ d, double *__restrict__ out, int64_t nt) {
@@ -103,12 +103,15 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             }
             __syncthreads();
         }
-        // ---- transfer function on the packed spectrum, pairs (k, M-k) in bit-reversed storage
+        // ---- transfer function on the packed spectrum, pairs (k, M-k) in bit-reversed storage.
+        // Threads walk PHYSICAL positions (pk = t consecutive -> no bank conflicts; walking k made
+        // all 32 lanes hit one bank) and the coefficient tables are stored by physical position.
         const double2 *c1 = coef + (int64_t)b * 2 * FFT_M;
         const double2 *c2 = c1 + FFT_M;
-        for (int k = threadIdx.x; k <= FFT_M / 2; k += FFT_THREADS) {
+        for (int pk = threadIdx.x; pk < FFT_M; pk += FFT_THREADS) {
+            const int k = __brev((unsigned)pk) >> (32 - FFT_LOG2M);
             const int km = (FFT_M - k) & (FFT_M - 1);
-            const int pk = __brev((unsigned)k) >> (32 - FFT_LOG2M);
+            if (k > km) continue;                       // each pair once
             const int pm = __brev((unsigned)km) >> (32 - FFT_LOG2M);
             const double2 zk = z[pk], zm = z[pm];
             // E[k] = (Z[k] + conj Z[M-k])/2 ; O[k] = (Z[k] - conj Z[M-k])/(2i)
@@ -116,8 +119,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             const double2 Ok = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
             const double2 Em = make_double2(Ek.x, -Ek.y);   // E[M-k] = conj E[k]
             const double2 Om = make_double2(Ok.x, -Ok.y);   // O[M-k] = conj O[k]
-            const double2 a1 = cmul(__ldg(c1 + k), Ek), a2 = cmul(__ldg(c2 + k), Ok);
-            const double2 b1 = cmul(__ldg(c1 + km), Em), b2 = cmul(__ldg(c2 + km), Om);
+            const double2 a1 = cmul(__ldg(c1 + pk), Ek), a2 = cmul(__ldg(c2 + pk), Ok);
+            const double2 b1 = cmul(__ldg(c1 + pm), Em), b2 = cmul(__ldg(c2 + pm), Om);
             z[pk] = make_double2(a1.x + a2.x, a1.y + a2.y);
             if (km != k) z[pm] = make_double2(b1.x + b2.x, b1.y + b2.y);
         }
@@ -189,7 +192,7 @@ extern "C" int64_t cm2_toeplitz_fft_scratch_bytes(int64_t nblocks) {
     return (nblocks + 1) * (int64_t)sizeof(int64_t) + (int64_t)(FFT_M / 2) * (int64_t)sizeof(double2) + 64;
 }
 
-// coef: device, [nblocks][2][M] complex (C1, C2 in natural frequency order, 1/M folded in);
+// coef: device, [nblocks][2][M] complex (C1, C2 stored at the bit-reversed position of their frequency, 1/M folded in);
 // scratch: cm2_toeplitz_fft_scratch_bytes(nblocks) bytes, `init` != 0 builds the twiddle table in it
 extern "C" int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
                                             const int64_t *blk_start, const double *d, double *out, int64_t nt,

@@ -177,6 +177,10 @@ class _ToeplitzFFT(object):
         nb = band_host.shape[0]
         k = np.arange(M)
         w = np.exp(-2j * np.pi * k / NF)
+        bits = int(np.log2(M))
+        brev = np.zeros(M, dtype=np.int64)              # the kernel keeps spectra bit-reversed in place
+        for bit in range(bits):
+            brev |= ((k >> bit) & 1) << (bits - 1 - bit)
         coef = np.empty((nb, 2, M), dtype=np.complex128)
         for b in range(nb):
             a = band_host[b]
@@ -186,8 +190,8 @@ class _ToeplitzFFT(object):
                 hc[NF - nband + 1:] = a[1:][::-1]
             H = np.fft.fft(hc).real                      # real and even: the band is symmetric
             Hs, Hd = 0.5 * (H[:M] + H[M:]), 0.5 * (H[:M] - H[M:])
-            coef[b, 0] = (Hs + 1j * Hd * np.conj(w)) / M
-            coef[b, 1] = (Hd * w + 1j * Hs) / M
+            coef[b, 0] = ((Hs + 1j * Hd * np.conj(w)) / M)[brev]     # table[position] = C[brev(position)]
+            coef[b, 1] = ((Hd * w + 1j * Hs) / M)[brev]
         self.coef = dv.to_dev_f64(coef.view(np.float64).reshape(-1))
         self.scratch = torch.empty(int(dv.call("cm2_toeplitz_fft_scratch_bytes", nb)) // 8 + 2, dtype=torch.float64,
                                    device=self.coef.device)

@@ -114,8 +114,8 @@ int cm2_noise_toeplitz_apply(const double *band, int nband, int64_t nblocks, int
                              void *scratch, cm2_stream_t stream);
 /* same operator by overlap-save FFT in shared memory (for wide bands: 2(2 nband - 1) flop/sample of
  * the direct form become ~150).  coef[nblocks][2][M] complex fp64, M = cm2_toeplitz_fft_points():
- * the packed transfer function C1, C2 of each block's band (see csrc/toeplitz_fft.cu), built on the
- * host.  Requires 2 (nband-1) < M.  scratch: cm2_toeplitz_fft_scratch_bytes(nblocks) bytes; pass
+ * the packed transfer function C1, C2 of each block's band, stored at the bit-reversed position of
+ * each frequency (see csrc/toeplitz_fft.cu), built on the host.  Requires 2 (nband-1) < M.  scratch: cm2_toeplitz_fft_scratch_bytes(nblocks) bytes; pass
  * init != 0 on the first call with a given scratch (twiddle table). */
 int cm2_toeplitz_fft_points(void);
 int64_t cm2_toeplitz_fft_scratch_bytes(int64_t nblocks);
