@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                    const double2 *__restrict__ tw, int L, int64_t nblocks, int64_t blocksize,
                    const int64_t *__restrict__ start, const int64_t *__restrict__ win_first,
                    const double *__restrict__ d, double *__restrict__ out, int64_t nt) {
-    extern __shared__ double2 z[];   // M complex points
+    extern __shared__ double2 zs[];   // M complex points, one pad element per 8 (bank-conflict relief)
+#define z(i) zs[(i) + ((i) >> 3)]
     const int S = FFT_NF - 2 * (L - 1);   // alias-free outputs per window
     const int64_t nwin = win_first[nblocks];
     for (int64_t win = blockIdx.x; win < nwin; win += gridDim.x) {
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             double2 v;
             v.x = (t >= bs && t < be) ? d[t] : 0.0;
             v.y = (t + 1 >= bs && t + 1 < be) ? d[t + 1] : 0.0;
-            z[i] = v;
+            z(i) = v;
         }
         __syncthreads();
         // ---- forward FFT, decimation in frequency, natural in -> bit-reversed out.  Two radix-2
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             for (int j = threadIdx.x; j < FFT_M / 4; j += FFT_THREADS) {
                 const int pos = j & (q - 1);
                 const int i0 = ((j >> lq) << (lq + 2)) + pos;
-                const double2 z0 = z[i0], z1 = z[i0 + q], z2 = z[i0 + 2 * q], z3 = z[i0 + 3 * q];
+                const double2 z0 = z(i0), z1 = z(i0 + q), z2 = z(i0 + 2 * q), z3 = z(i0 + 3 * q);
                 // stage with half-size 2q: pairs (0,2) and (1,3)
                 const double2 w1a = __ldg(tw + (pos << (FFT_LOG2M - 2 - lq)));
                 const double2 w1b = __ldg(tw + ((pos + q) << (FFT_LOG2M - 2 - lq)));
@@ -88,18 +89,18 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                 const double2 a3 = cmul(make_double2(z1.x - z3.x, z1.y - z3.y), w1b);
                 // stage with half-size q: pairs (0,1) and (2,3)
                 const double2 w2 = __ldg(tw + (pos << (FFT_LOG2M - 1 - lq)));
-                z[i0] = make_double2(a0.x + a1.x, a0.y + a1.y);
-                z[i0 + q] = cmul(make_double2(a0.x - a1.x, a0.y - a1.y), w2);
-                z[i0 + 2 * q] = make_double2(a2.x + a3.x, a2.y + a3.y);
-                z[i0 + 3 * q] = cmul(make_double2(a2.x - a3.x, a2.y - a3.y), w2);
+                z(i0) = make_double2(a0.x + a1.x, a0.y + a1.y);
+                z(i0 + q) = cmul(make_double2(a0.x - a1.x, a0.y - a1.y), w2);
+                z(i0 + 2 * q) = make_double2(a2.x + a3.x, a2.y + a3.y);
+                z(i0 + 3 * q) = cmul(make_double2(a2.x - a3.x, a2.y - a3.y), w2);
             }
             __syncthreads();
         }
         if (FFT_LOG2M & 1) {   // odd number of stages: one last radix-2 stage with half-size 1
             for (int j = threadIdx.x; j < FFT_M / 2; j += FFT_THREADS) {
-                const double2 a = z[2 * j], bb = z[2 * j + 1];
-                z[2 * j] = make_double2(a.x + bb.x, a.y + bb.y);
-                z[2 * j + 1] = make_double2(a.x - bb.x, a.y - bb.y);
+                const double2 a = z(2 * j), bb = z(2 * j + 1);
+                z(2 * j) = make_double2(a.x + bb.x, a.y + bb.y);
+                z(2 * j + 1) = make_double2(a.x - bb.x, a.y - bb.y);
             }
             __syncthreads();
         }
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             const int km = (FFT_M - k) & (FFT_M - 1);
             if (k > km) continue;                       // each pair once
             const int pm = __brev((unsigned)km) >> (32 - FFT_LOG2M);
-            const double2 zk = z[pk], zm = z[pm];
+            const double2 zk = z(pk), zm = z(pm);
             // E[k] = (Z[k] + conj Z[M-k])/2 ; O[k] = (Z[k] - conj Z[M-k])/(2i)
             const double2 Ek = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
             const double2 Ok = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
@@ -121,8 +122,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             const double2 Om = make_double2(Ok.x, -Ok.y);   // O[M-k] = conj O[k]
             const double2 a1 = cmul(__ldg(c1 + pk), Ek), a2 = cmul(__ldg(c2 + pk), Ok);
             const double2 b1 = cmul(__ldg(c1 + pm), Em), b2 = cmul(__ldg(c2 + pm), Om);
-            z[pk] = make_double2(a1.x + a2.x, a1.y + a2.y);
-            if (km != k) z[pm] = make_double2(b1.x + b2.x, b1.y + b2.y);
+            z(pk) = make_double2(a1.x + a2.x, a1.y + a2.y);
+            if (km != k) z(pm) = make_double2(b1.x + b2.x, b1.y + b2.y);
         }
         __syncthreads();
         // ---- inverse FFT, decimation in time, bit-reversed in -> natural out (conjugate twiddles),
@@ -130,9 +131,9 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
         int lq0 = 0;
         if (FFT_LOG2M & 1) {   // the stage with half-size 1 first
             for (int j = threadIdx.x; j < FFT_M / 2; j += FFT_THREADS) {
-                const double2 a = z[2 * j], bb = z[2 * j + 1];
-                z[2 * j] = make_double2(a.x + bb.x, a.y + bb.y);
-                z[2 * j + 1] = make_double2(a.x - bb.x, a.y - bb.y);
+                const double2 a = z(2 * j), bb = z(2 * j + 1);
+                z(2 * j) = make_double2(a.x + bb.x, a.y + bb.y);
+                z(2 * j + 1) = make_double2(a.x - bb.x, a.y - bb.y);
             }
             __syncthreads();
             lq0 = 1;
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                 const int i0 = ((j >> lq) << (lq + 2)) + pos;
                 double2 w = __ldg(tw + (pos << (FFT_LOG2M - 1 - lq)));       // half-size q
                 w.y = -w.y;
-                const double2 z0 = z[i0], z1 = cmul(z[i0 + q], w), z2 = z[i0 + 2 * q], z3 = cmul(z[i0 + 3 * q], w);
+                const double2 z0 = z(i0), z1 = cmul(z(i0 + q), w), z2 = z(i0 + 2 * q), z3 = cmul(z(i0 + 3 * q), w);
                 const double2 a0 = make_double2(z0.x + z1.x, z0.y + z1.y), a1 = make_double2(z0.x - z1.x, z0.y - z1.y);
                 const double2 a2 = make_double2(z2.x + z3.x, z2.y + z3.y), a3 = make_double2(z2.x - z3.x, z2.y - z3.y);
                 double2 wa = __ldg(tw + (pos << (FFT_LOG2M - 2 - lq)));       // half-size 2q, position pos
@@ -152,21 +153,24 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                 wa.y = -wa.y;
                 wb.y = -wb.y;
                 const double2 b2 = cmul(a2, wa), b3 = cmul(a3, wb);
-                z[i0] = make_double2(a0.x + b2.x, a0.y + b2.y);
-                z[i0 + 2 * q] = make_double2(a0.x - b2.x, a0.y - b2.y);
-                z[i0 + q] = make_double2(a1.x + b3.x, a1.y + b3.y);
-                z[i0 + 3 * q] = make_double2(a1.x - b3.x, a1.y - b3.y);
+                z(i0) = make_double2(a0.x + b2.x, a0.y + b2.y);
+                z(i0 + 2 * q) = make_double2(a0.x - b2.x, a0.y - b2.y);
+                z(i0 + q) = make_double2(a1.x + b3.x, a1.y + b3.y);
+                z(i0 + 3 * q) = make_double2(a1.x - b3.x, a1.y - b3.y);
             }
             __syncthreads();
         }
         // ---- alias-free outputs: window positions [L-1, L-1+S)
-        const double *zr = reinterpret_cast<const double *>(z);
         for (int i = threadIdx.x; i < S; i += FFT_THREADS) {
             const int64_t t = j0 + i;
-            if (t < be) out[t] = zr[L - 1 + i];
+            const int r = L - 1 + i;
+            const double2 v = z(r >> 1);
+            if (t < be) out[t] = (r & 1) ? v.y : v.x;
         }
     }
 }
+
+#undef z
 
 __global__ void k_win_first(int64_t nblocks, int64_t blocksize, const int64_t *__restrict__ start, int64_t nt, int S,
                             int64_t *__restrict__ win_first) {
@@ -213,7 +217,7 @@ extern "C" int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64
     const int S = FFT_NF - 2 * (nband - 1);
     k_win_first<<<1, 1, 0, st>>>(nblocks, blocksize, blk_start, nt, S, win_first);
     CM2_LAUNCHED();
-    const size_t smem = sizeof(double2) * FFT_M;
+    const size_t smem = sizeof(double2) * (FFT_M + FFT_M / 8);
     CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t nwin_ub = nt / S + nblocks + 1;
     int grid = (int)(nwin_ub < sm_count() ? nwin_ub : sm_count());
