@@ -164,6 +164,33 @@ class ToeplitzLO(lp.LinearOperator):
 TOEPLITZ_FFT_MIN_BAND = 128    # bands at least this wide go through the overlap-save FFT kernel
 
 
+def toeplitz_fft_tables(band_host, nband, M):
+    """Packed transfer functions C1, C2 of cm2_noise_toeplitz_fft_apply for every noise block
+    (host, NumPy): [nblocks][2][M] complex, stored at the bit-reversed position of each frequency,
+    1/M folded in.  See csrc/toeplitz_fft.cu for the derivation."""
+    NF = 2 * M
+    band_host = np.asarray(band_host, dtype=np.float64).reshape(-1, nband)
+    nb = band_host.shape[0]
+    k = np.arange(M)
+    w = np.exp(-2j * np.pi * k / NF)
+    bits = int(np.log2(M))
+    brev = np.zeros(M, dtype=np.int64)              # the kernel keeps spectra bit-reversed in place
+    for bit in range(bits):
+        brev |= ((k >> bit) & 1) << (bits - 1 - bit)
+    coef = np.empty((nb, 2, M), dtype=np.complex128)
+    for b in range(nb):
+        a = band_host[b]
+        hc = np.zeros(NF)
+        hc[:nband] = a
+        if nband > 1:
+            hc[NF - nband + 1:] = a[1:][::-1]
+        H = np.fft.fft(hc).real                      # real and even: the band is symmetric
+        Hs, Hd = 0.5 * (H[:M] + H[M:]), 0.5 * (H[:M] - H[M:])
+        coef[b, 0] = ((Hs + 1j * Hd * np.conj(w)) / M)[brev]     # table[position] = C[brev(position)]
+        coef[b, 1] = ((Hd * w + 1j * Hs) / M)[brev]
+    return coef
+
+
 class _ToeplitzFFT(object):
     """Host-built packed transfer functions + device scratch for cm2_noise_toeplitz_fft_apply."""
 
@@ -173,25 +200,8 @@ class _ToeplitzFFT(object):
         self.ok = 2 * (nband - 1) < M
         if not self.ok:
             return
-        band_host = np.asarray(band_host, dtype=np.float64).reshape(-1, nband)
-        nb = band_host.shape[0]
-        k = np.arange(M)
-        w = np.exp(-2j * np.pi * k / NF)
-        bits = int(np.log2(M))
-        brev = np.zeros(M, dtype=np.int64)              # the kernel keeps spectra bit-reversed in place
-        for bit in range(bits):
-            brev |= ((k >> bit) & 1) << (bits - 1 - bit)
-        coef = np.empty((nb, 2, M), dtype=np.complex128)
-        for b in range(nb):
-            a = band_host[b]
-            hc = np.zeros(NF)
-            hc[:nband] = a
-            if nband > 1:
-                hc[NF - nband + 1:] = a[1:][::-1]
-            H = np.fft.fft(hc).real                      # real and even: the band is symmetric
-            Hs, Hd = 0.5 * (H[:M] + H[M:]), 0.5 * (H[:M] - H[M:])
-            coef[b, 0] = ((Hs + 1j * Hd * np.conj(w)) / M)[brev]     # table[position] = C[brev(position)]
-            coef[b, 1] = ((Hd * w + 1j * Hs) / M)[brev]
+        coef = toeplitz_fft_tables(band_host, nband, M)
+        nb = coef.shape[0]
         self.coef = dv.to_dev_f64(coef.view(np.float64).reshape(-1))
         self.scratch = torch.empty(int(dv.call("cm2_toeplitz_fft_scratch_bytes", nb)) // 8 + 2, dtype=torch.float64,
                                    device=self.coef.device)
@@ -364,6 +374,24 @@ class BlockLO(BlockDiagonalLinearOperator):
         return out
 
 
+def flatten_subscans(subscans, tstart, nsamples, nbolos):
+    """The reference's (CES, detector, subscan) triple loop (linearoperators.py:134-140, 167) as one
+    sorted list of segments [start, end) in the CES-major, detector-major, time-minor TOD."""
+    starts, ends = [], []
+    offset = 0
+    for subsc, ts, ns, nb in zip(subscans, tstart, nsamples, nbolos):
+        subsc = np.asarray(subsc, dtype=np.int64)
+        ts = np.asarray(ts, dtype=np.int64)
+        det0 = offset + int(ns) * np.arange(int(nb), dtype=np.int64)       # :139
+        s = (det0[:, None] + ts[None, :]).reshape(-1)
+        starts.append(s)
+        ends.append(s + np.tile(subsc, int(nb)))
+        offset += int(nb) * int(ns)
+    if not starts:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    return np.concatenate(starts), np.concatenate(ends)
+
+
 class FilterLO(lp.LinearOperator):
     """Subscan offset filter (poly_order=0) -- interfaces/linearoperators.py:94-168, 263-282.
 
@@ -388,18 +416,8 @@ class FilterLO(lp.LinearOperator):
         self.poly_order = poly_order
         if poly_order != 0:
             raise NotImplementedError("Legendre filtering (poly_order>0) is outside the accelerated hot path")
-        starts, ends = [], []
-        offset = 0
-        for subsc, ts, ns, nb in zip(self.subscans, self.tstart, self.nsamples, self.nbolos):
-            subsc = np.asarray(subsc, dtype=np.int64)
-            ts = np.asarray(ts, dtype=np.int64)
-            det0 = offset + int(ns) * np.arange(int(nb), dtype=np.int64)       # :139
-            s = (det0[:, None] + ts[None, :]).reshape(-1)
-            starts.append(s)
-            ends.append(s + np.tile(subsc, int(nb)))
-            offset += int(nb) * int(ns)
-        self._seg_start_host = np.concatenate(starts) if starts else np.zeros(0, dtype=np.int64)
-        self._seg_end_host = np.concatenate(ends) if ends else np.zeros(0, dtype=np.int64)
+        self._seg_start_host, self._seg_end_host = flatten_subscans(self.subscans, self.tstart, self.nsamples,
+                                                                    self.nbolos)
         if len(self._seg_end_host) and (self._seg_end_host.max() > size or self._seg_start_host.min() < 0):
             raise lp.ShapeError("subscan table exceeds the TOD size")
         self._seg_start = dv.to_dev(self._seg_start_host, torch.int64)

@@ -63,11 +63,11 @@ def raster_scan(nt, nside=512, ndet=64, nx=1000, ny=500, samples_per_pixel=8.0, 
         phi[b * ns:(b + 1) * ns] = theta0[b] + 2 * np.pi * 2.5 / 200. * t + hwp_jitter * rng.standard_normal(ns)
     # subscan table shared by all detectors (reference: subscans[ces], tstart[ces])
     s0 = int(np.ceil(ta / 2 * sweep))
-    s1 = int(np.floor((1.0 - ta / 2) * sweep))
+    s1 = int(np.ceil((1.0 - ta / 2) * sweep))             # offsets with ta/2 <= frac < 1 - ta/2
     sub_start = (np.arange(nsweeps, dtype=np.int64) * sweep + s0)
     sub_len = np.full(nsweeps, s1 - s0, dtype=np.int64)
-    keep = sub_start + sub_len <= ns
-    sub_start, sub_len = sub_start[keep], sub_len[keep]
+    keep = sub_start < ns                                  # the last sweep may be cut by the timeline's end
+    sub_start, sub_len = sub_start[keep], np.minimum(sub_len[keep], ns - sub_start[keep])
     scan = Scan(nt=nt, ndet=ndet, ns=ns, nside=nside, npix_full=npix_full, pix=pix, phi=phi,
                 weights=weights, sub_len=sub_len, sub_start=sub_start, nx=nx, ny=ny,
                 samples_per_pixel=samples_per_pixel, seed=seed)

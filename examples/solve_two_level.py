@@ -51,7 +51,7 @@ def make_scan(nt, nside, nx, ny, ndet, spp, seed, turnaround=0.05):
             2 * np.pi * 2.5 / 200. * t.to(torch.float64) + 1e-3 * torch.randn(ns, generator=g, device=dev, dtype=torch.float64)
     nsweeps = int(ns // sweep)
     s0 = int(np.ceil(turnaround / 2 * sweep))
-    s1 = int(np.floor((1 - turnaround / 2) * sweep))
+    s1 = int(np.ceil((1 - turnaround / 2) * sweep))
     sub_start = np.arange(nsweeps, dtype=np.int64) * sweep + s0
     sub_len = np.full(nsweeps, s1 - s0, dtype=np.int64)
     return nt, ns, pix, phi, sub_len, sub_start, g

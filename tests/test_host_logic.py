@@ -1,0 +1,138 @@
+"""CPU tests of the product's host-side logic (no GPU, no kernels): subscan flattening, noise-block
+partition, lazy block weights, the host-built FFT transfer-function tables (checked by emulating the
+kernel's in-place bit-reversed algorithm in NumPy), the synthetic generators and the operator
+algebra's planning of fused chains."""
+import numpy as np
+import pytest
+
+import oracle
+from cosmomap2_b200 import linearoperators as lo
+from cosmomap2_b200 import synthetic
+from cosmomap2_b200.process_ces import BlockWeights
+
+
+def test_flatten_subscans_matches_reference_triple_loop():
+    rng = np.random.default_rng(0)
+    nsamples, nbolos = [400, 300, 250], [3, 2, 4]
+    subs = [np.array([50, 60, 70]), np.array([40, 100]), np.array([30, 30, 30, 30])]
+    tst = [np.array([5, 100, 250]), np.array([10, 120]), np.array([0, 50, 110, 200])]
+    s, e = lo.flatten_subscans(subs, tst, nsamples, nbolos)
+    ref_s, ref_e = [], []
+    offset = 0
+    for subsc, ts, ns, nb in zip(subs, tst, nsamples, nbolos):       # linearoperators.py:134-167
+        for bolo in range(nb):
+            for i, j in zip(subsc, ts):
+                start = j + ns * bolo + offset
+                ref_s.append(start)
+                ref_e.append(start + i)
+        offset += nb * ns
+    assert np.array_equal(s, ref_s) and np.array_equal(e, ref_e)
+    assert np.all(s[1:] >= e[:-1])          # sorted, non-overlapping: the run-table path applies
+    # and the flattened filter equals the oracle's FilterLO
+    nt = offset
+    pix = rng.integers(0, 9, nt)
+    pix[rng.random(nt) < 0.1] = -1
+    d = rng.standard_normal(nt)
+    F = oracle.FilterLO(nt, [subs, tst], nsamples, nbolos, pix)
+    from oracle import cloops
+    assert np.allclose(cloops.filter_offset(pix, d, s, e), F * d, rtol=0, atol=1e-13)
+
+
+def test_block_starts_and_lazy_weights():
+    st = lo._block_starts(100, 4)
+    assert np.array_equal(st, [0, 100, 200, 300, 400])
+    st = lo._block_starts([5, 7, 3], 3)
+    assert np.array_equal(st, [0, 5, 12, 15])
+    with pytest.raises(ValueError):
+        lo._block_starts([5, 7], 3)
+    w = BlockWeights([2.0, 3.0, 4.0], st)
+    assert len(w) == 15 and w.shape == (15,) and w.equal_blocksize() == 0
+    assert np.array_equal(np.asarray(w), np.repeat([2.0, 3.0, 4.0], [5, 7, 3]))
+    assert np.array_equal(np.asarray(w), oracle.BlockLO([5, 7, 3], [2.0, 3.0, 4.0]).diag)
+    assert BlockWeights([1.0, 2.0], [0, 8, 16]).equal_blocksize() == 8
+
+
+def _emulate_fft_kernel(coef_block, a, v, log2m):
+    """NumPy twin of k_toeplitz_fft for one noise block (in-place DIF -> tables by physical
+    position -> in-place DIT), used to pin the host-built tables without a GPU."""
+    M = 1 << log2m
+    NF = 2 * M
+    L = len(a)
+    n = len(v)
+    tw = np.exp(-2j * np.pi * np.arange(M // 2) / M)
+    brev = np.array([int(format(k, "0%db" % log2m)[::-1], 2) for k in range(M)])
+    S = NF - 2 * (L - 1)
+    out = np.zeros(n)
+    for win in range((n + S - 1) // S):
+        j0 = win * S
+        x = np.zeros(NF)
+        t = j0 - (L - 1) + np.arange(NF)
+        ok = (t >= 0) & (t < n)
+        x[ok] = v[t[ok]]
+        z = x[0::2] + 1j * x[1::2]
+        for lm in range(log2m - 1, -1, -1):           # DIF, natural -> bit-reversed
+            m = 1 << lm
+            j = np.arange(M // 2)
+            pos = j & (m - 1)
+            i = ((j >> lm) << (lm + 1)) + pos
+            A, B = z[i].copy(), z[i + m].copy()
+            z[i] = A + B
+            z[i + m] = (A - B) * tw[pos << (log2m - 1 - lm)]
+        pk = np.arange(M)
+        k = brev[pk]
+        km = (M - k) & (M - 1)
+        pm = brev[km]
+        zk, zm = z[pk].copy(), z[pm].copy()
+        E = 0.5 * (zk + np.conj(zm))
+        O = (zk - np.conj(zm)) / 2j
+        z = coef_block[0][pk] * E + coef_block[1][pk] * O      # W at physical position pk
+        for lm in range(log2m):                        # DIT, bit-reversed -> natural
+            m = 1 << lm
+            j = np.arange(M // 2)
+            pos = j & (m - 1)
+            i = ((j >> lm) << (lm + 1)) + pos
+            A, B = z[i].copy(), z[i + m] * np.conj(tw[pos << (log2m - 1 - lm)])
+            z[i] = A + B
+            z[i + m] = A - B
+        zr = np.empty(NF)
+        zr[0::2], zr[1::2] = z.real, z.imag
+        idx = j0 + np.arange(S)
+        keep = idx < n
+        out[idx[keep]] = zr[L - 1 + np.arange(S)][keep]
+    return out
+
+
+@pytest.mark.parametrize("L", [1, 2, 9, 40])
+def test_fft_transfer_tables_reproduce_the_toeplitz_product(L):
+    rng = np.random.default_rng(L)
+    log2m = 7
+    a = rng.random(L)
+    a[0] += 2.0
+    v = rng.standard_normal(700)
+    coef = lo.toeplitz_fft_tables(a[None, :], L, 1 << log2m)
+    y = _emulate_fft_kernel(coef[0], a, v, log2m)
+    ref = oracle.ToeplitzLO(a, len(v)) * v
+    assert np.max(np.abs(y - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+def test_synthetic_scan_properties():
+    sc = synthetic.raster_scan(120000, nside=64, ndet=6, nx=50, ny=30, samples_per_pixel=7.0, seed=3,
+                               flag_turnarounds=True)
+    assert sc.nt == 120000 and len(sc.pix) == sc.nt and sc.pix.dtype == np.int32
+    good = sc.pix >= 0
+    assert 0.9 < good.mean() < 0.97                          # 5 % turnarounds flagged
+    assert sc.pix[good].max() < sc.npix_full
+    runs = np.count_nonzero(np.diff(sc.pix[good]) != 0)
+    assert 5.0 < good.sum() / runs < 8.0                      # ~samples_per_pixel samples per pixel crossing
+    # every unflagged sample lies inside a subscan of its detector, every flagged one outside
+    inside = np.zeros(sc.nt, dtype=bool)
+    s, e = lo.flatten_subscans([sc.sub_len], [sc.sub_start], [sc.ns], [sc.ndet])
+    for a, b in zip(s, e):
+        inside[a:b] = True
+    assert np.all(inside[good])
+    sc2 = synthetic.raster_scan(120000, nside=64, ndet=6, nx=50, ny=30, samples_per_pixel=7.0, seed=3,
+                                flag_turnarounds=True)
+    assert np.array_equal(sc.pix, sc2.pix) and np.array_equal(sc.phi, sc2.phi) and np.array_equal(sc.d, sc2.d)
+    bands = synthetic.toeplitz_bands(3, 16)
+    for a in bands:                                            # diagonally dominant -> SPD Toeplitz
+        assert a[0] > 2 * np.abs(a[1:]).sum()
