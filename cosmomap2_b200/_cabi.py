@@ -29,6 +29,7 @@ SIGNATURES = {
     "cm2_pix_narrow": (_int, [_vp, _i64, _vp, _vp]),
     "cm2_pix_widen": (_int, [_vp, _i64, _vp, _vp]),
     "cm2_weights_moments": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _int, _vp, _i64, _vp]),
+    "cm2_weights_moments_sorted": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _int, _vp, _i64, _vp]),
     "cm2_weights_mask": (_int, [_vp, _i64, _int, _f64, _vp, _vp]),
     "cm2_scan_scratch_bytes": (_i64, [_i64]),
     "cm2_weights_old2new": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),

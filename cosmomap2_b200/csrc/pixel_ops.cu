@@ -40,16 +40,60 @@ __global__ void __launch_bounds__(PB) k_mask(const double *__restrict__ mom, int
         if (pol == 1) {
             g = m[0] > 0.0;
         } else {
+            // exactly the reference's operation order, every operation rounded on its own (no FMA
+            // contraction): with bit-identical moments the mask is bit-identical to NumPy's
             const double c2 = m[3], cs = m[4], s2 = m[5];
-            const double det = (c2 * s2) - (cs * cs);
-            const double tr = c2 + s2;
-            const double sq = sqrt(tr * tr / 4. - det);
-            const double lmax = tr / 2. + sq, lmin = tr / 2. - sq;
-            const double cond = fabs(lmax / lmin);
+            const double det = __dsub_rn(__dmul_rn(c2, s2), __dmul_rn(cs, cs));
+            const double tr = __dadd_rn(c2, s2);
+            const double sq = __dsqrt_rn(__dsub_rn(__ddiv_rn(__dmul_rn(tr, tr), 4.), det));
+            const double lmax = __dadd_rn(__ddiv_rn(tr, 2.), sq), lmin = __dsub_rn(__ddiv_rn(tr, 2.), sq);
+            const double cond = fabs(__ddiv_rn(lmax, lmin));
             g = cond <= thr;
             if (pol == 3) g = g && (m[0] > 2.0);
         }
         good[j] = g;
+    }
+}
+
+// Deterministic moments in the reference's own summation order: one thread per pixel walks the
+// pixel's samples in time order (perm = stable argsort of pix) and accumulates with the serial
+// loop's association and rounding -- (w*c)*c etc., no FMA -- so every moment is bit-identical to
+// process_ces.py:480-542 run on the same inputs.  One-off set-up pass; gathers are uncoalesced.
+__global__ void __launch_bounds__(PB) k_moments_sorted(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ perm,
+                                                       const double *__restrict__ cs, const double *__restrict__ sn,
+                                                       const double *__restrict__ wsamp, const double *__restrict__ wblk,
+                                                       int64_t nblocks, int64_t blocksize, const int64_t *__restrict__ bstart,
+                                                       int pol, double *__restrict__ mom, int64_t npix) {
+    for (int64_t j = (int64_t)blockIdx.x * PB + threadIdx.x; j < npix; j += (int64_t)gridDim.x * PB) {
+        double h = 0., c1 = 0., s1 = 0., c2 = 0., cs2 = 0., s2 = 0.;
+        for (int64_t e = rowptr[j]; e < rowptr[j + 1]; ++e) {
+            const int64_t t = perm[e];
+            double w = 1.0;
+            if (wsamp) w = wsamp[t];
+            else if (wblk) {
+                int64_t b;
+                if (bstart == nullptr) b = t / blocksize;
+                else {
+                    int64_t lo = 0, hi = nblocks;
+                    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (bstart[mid] <= t) lo = mid; else hi = mid; }
+                    b = lo;
+                }
+                w = wblk[b < nblocks ? b : nblocks - 1];
+            }
+            if (pol == 1) { h = __dadd_rn(h, w); continue; }
+            const double c = cs[t], s = sn[t];
+            const double wc = __dmul_rn(w, c), ws = __dmul_rn(w, s);
+            if (pol == 3) {
+                h = __dadd_rn(h, w);
+                c1 = __dadd_rn(c1, wc);
+                s1 = __dadd_rn(s1, ws);
+            }
+            c2 = __dadd_rn(c2, __dmul_rn(wc, c));
+            s2 = __dadd_rn(s2, __dmul_rn(ws, s));
+            cs2 = __dadd_rn(cs2, __dmul_rn(ws, c));
+        }
+        double *m = mom + 6 * j;
+        m[0] = h; m[1] = c1; m[2] = s1; m[3] = c2; m[4] = cs2; m[5] = s2;
     }
 }
 
@@ -250,6 +294,19 @@ extern "C" int cm2_weights_mask(const double *mom, int64_t npix, int pol, double
     CM2_REQUIRE(npix >= 0 && pol >= 1 && pol <= 3, "bad npix/pol");
     if (npix == 0) return CM2_OK;
     k_mask<<<grid_for(npix), PB, 0, as_stream(stream)>>>(mom, npix, pol, threshold_cond, good);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+extern "C" int cm2_weights_moments_sorted(const int64_t *rowptr, const int32_t *perm, const double *c, const double *s,
+                                          const double *w, const double *wblk, int64_t nblocks, int64_t blocksize,
+                                          const int64_t *blk_start, int pol, double *mom, int64_t npix,
+                                          cm2_stream_t stream) {
+    CM2_REQUIRE(npix >= 0 && pol >= 1 && pol <= 3, "bad npix/pol");
+    CM2_REQUIRE(wblk == nullptr || nblocks > 0, "nblocks must be > 0 when block weights are given");
+    if (npix == 0) return CM2_OK;
+    k_moments_sorted<<<grid_for(npix), PB, 0, as_stream(stream)>>>(rowptr, perm, c, s, w, wblk, nblocks, blocksize, blk_start,
+                                                                 pol, mom, npix);
     CM2_LAUNCHED();
     return CM2_OK;
 }

@@ -14,6 +14,14 @@ import torch
 from . import _device as dv
 
 
+# Strict parity: cos/sin of 2 phi taken from NumPy on the host and the moments accumulated in the
+# serial loop's order and rounding, so counts/cosine/.../sincos, the mask, old2new and the relabelled
+# pixels are BIT-IDENTICAL to the reference on the same inputs (the default path sums with atomics:
+# equal to ~1e-16, masks equal except on rounding knife edges).  One-off set-up cost:
+# a stable sort of the samples by pixel and a host cos/sin.
+STRICT_PARITY = bool(int(__import__("os").environ.get("CM2_STRICT_PARITY", "0")))
+
+
 class BlockWeights(object):
     """Per-sample white-noise weights described by per-block scalars (``BlockLO.diag``).
 
@@ -105,11 +113,16 @@ class ProcessTimeSamples(object):
         if pol > 1:
             if phi is None:
                 raise ValueError("phi is required for pol=2,3")
-            phi_dev = dv.to_dev_f64(phi)
-            self._cos_dev = dv.empty_f64(nt)
-            self._sin_dev = dv.empty_f64(nt)
-            dv.call("cm2_angles", dv.ptr(phi_dev), nt, dv.ptr(self._cos_dev), dv.ptr(self._sin_dev), st)
-            del phi_dev
+            if STRICT_PARITY:
+                phi_h = dv.to_host(phi) if isinstance(phi, torch.Tensor) else np.asarray(phi, dtype=np.float64)
+                self._host["cos"], self._host["sin"] = np.cos(2. * phi_h), np.sin(2. * phi_h)   # :493-494
+                self._cos_dev, self._sin_dev = dv.to_dev_f64(self._host["cos"]), dv.to_dev_f64(self._host["sin"])
+            else:
+                phi_dev = dv.to_dev_f64(phi)
+                self._cos_dev = dv.empty_f64(nt)
+                self._sin_dev = dv.empty_f64(nt)
+                dv.call("cm2_angles", dv.ptr(phi_dev), nt, dv.ptr(self._cos_dev), dv.ptr(self._sin_dev), st)
+                del phi_dev
         self._w = w
         if obspix2 is None:
             self.threshold = threshold_cond
@@ -143,6 +156,16 @@ class ProcessTimeSamples(object):
             if keep.numel() != self.nsamples:
                 raise ValueError("w must have one weight per sample")
             wptr = dv.ptr(keep)
+        if STRICT_PARITY:
+            pix = self._pix_dev
+            order = torch.sort(pix, stable=True).indices
+            nflag = int((pix < 0).sum().item())
+            perm = order[nflag:].to(torch.int32).contiguous()
+            rowptr = torch.zeros(npix + 1, dtype=torch.int64, device=pix.device)
+            rowptr[1:] = torch.cumsum(torch.bincount(pix[pix >= 0].to(torch.int64), minlength=npix), 0)
+            dv.call("cm2_weights_moments_sorted", dv.ptr(rowptr), dv.ptr(perm), dv.ptr(self._cos_dev),
+                    dv.ptr(self._sin_dev), wptr, blk[0], blk[1], blk[2], blk[3], self.pol, dv.ptr(mom), npix, st)
+            return mom
         dv.call("cm2_weights_moments", dv.ptr(self._pix_dev), dv.ptr(self._cos_dev), dv.ptr(self._sin_dev),
                 wptr, blk[0], blk[1], blk[2], blk[3], self.nsamples, self.pol, dv.ptr(mom), npix, st)
         return mom

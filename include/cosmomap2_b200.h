@@ -72,6 +72,14 @@ int cm2_weights_moments(const int32_t *pix, const double *cos2phi, const double 
                         const double *w, const double *wblk, int64_t nblocks, int64_t blocksize,
                         const int64_t *blk_start, int64_t nt, int pol, double *mom, int64_t npix,
                         cm2_stream_t stream);
+/* the same moments in the reference's own summation order (one thread per pixel, samples in time
+ * order through the stable pixel-sorted permutation, serial association, no FMA): bit-identical to
+ * the serial loops on the same inputs.  rowptr[npix+1], perm[nvalid] as for
+ * cm2_pointing_apply_t_sorted. */
+int cm2_weights_moments_sorted(const int64_t *rowptr, const int32_t *perm, const double *cos2phi,
+                               const double *sin2phi, const double *w, const double *wblk,
+                               int64_t nblocks, int64_t blocksize, const int64_t *blk_start,
+                               int pol, double *mom, int64_t npix, cm2_stream_t stream);
 /* good-pixel flags (:491, 544-555): pol=1 h>0; pol=2 cond<=thr; pol=3 cond<=thr && h>2 */
 int cm2_weights_mask(const double *mom, int64_t npix, int pol, double threshold_cond,
                      int32_t *good, cm2_stream_t stream);
