@@ -12,14 +12,18 @@
 // Reductions are deterministic: fixed per-thread order, fixed shuffle tree, per-CTA partials summed
 // in CTA order by the last CTA to finish (ticket).  The partial/ticket scratch is one device-global
 // area: call these entry points from one stream at a time.
+#include <cooperative_groups.h>
+
 #include "cm2_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace cm2 {
 
 constexpr int VB = 256;
 constexpr int MAXP = 2048;  // max CTAs of a reduction kernel
 
-__device__ double g_part[2][MAXP];
+__device__ double g_part[3][MAXP];   // rows 0,1: reduction partials; row 2: p.q partials of k_bd_iter
 __device__ unsigned int g_ticket;
 
 // CTA-level: write up to two partials, last CTA reduces all partials in order; returns true in
@@ -166,7 +170,8 @@ __device__ __forceinline__ void bd_z(const double *__restrict__ inv, int64_t j, 
 template <int POL>
 __global__ void __launch_bounds__(VB) k_bd_reset(const double *__restrict__ inv, int64_t npix, double *__restrict__ r,
                                                  double *__restrict__ z, double *__restrict__ scal, double atol,
-                                                 const double *__restrict__ b, double *__restrict__ x) {
+                                                 const double *__restrict__ b, double *__restrict__ x,
+                                                 double *__restrict__ p0) {
     __shared__ double red[32];
     double s[2] = {0.0, 0.0}, tot[2];
     for (int64_t j = (int64_t)blockIdx.x * VB + threadIdx.x; j < npix; j += (int64_t)gridDim.x * VB) {
@@ -186,6 +191,7 @@ __global__ void __launch_bounds__(VB) k_bd_reset(const double *__restrict__ inv,
 #pragma unroll
         for (int k = 0; k < POL; ++k) {
             z[POL * j + k] = zv[k];
+            if (p0 != nullptr) p0[POL * j + k] = zv[k];     // first search direction p = z
             s[0] = fma(rv[k], zv[k], s[0]);
             s[1] = fma(rv[k], rv[k], s[1]);
         }
@@ -233,6 +239,87 @@ __global__ void __launch_bounds__(VB) k_bd_update(const double *__restrict__ inv
         scal[3] = tot[1];
         scal[8] += 1.0;
         scal[7] = (sqrt(tot[1]) < scal[6]) ? 1.0 : 0.0;
+    }
+}
+
+// ---- the whole pixel-domain tail of an M_BD iteration in ONE cooperative launch -----------------
+//   pq = p.q ; alpha = rho/pq ; x += alpha p ; r -= alpha q ; z = M r ; rho' = r.z ; |r|^2 ;
+//   beta' = rho'/rho ; p = z + beta' p   (the NEXT iteration's search direction) ; flags
+// Two grid-wide barriers replace two kernel boundaries; reductions stay deterministic (per-CTA
+// partials summed in CTA order, by every CTA identically).
+__device__ __forceinline__ double sum_partials(const double *part, int nb, double *red) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nb; i += VB) s += ((volatile const double *)part)[i];
+    __shared__ double bc;
+    const double t = block_sum(s, red);
+    if (threadIdx.x == 0) bc = t;
+    __syncthreads();
+    const double out = bc;
+    __syncthreads();
+    return out;
+}
+
+template <int POL>
+__global__ void __launch_bounds__(VB) k_bd_iter(const double *__restrict__ inv, int64_t npix, double *__restrict__ p,
+                                                const double *__restrict__ q, double *__restrict__ x, double *__restrict__ r,
+                                                double *__restrict__ z, double *__restrict__ scal) {
+    __shared__ double red[32];
+    if (scal[7] != 0.0) return;     // uniform over the grid: nobody reaches a grid barrier
+    cg::grid_group grid = cg::this_grid();
+    const double rho = scal[0];
+    const int64_t n = npix * POL;
+    const int64_t stride = (int64_t)gridDim.x * VB;
+    // phase 1: p.q
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * VB + threadIdx.x; i < n; i += stride) s = fma(p[i], q[i], s);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) g_part[2][blockIdx.x] = s;
+    grid.sync();
+    const double pq = sum_partials(g_part[2], gridDim.x, red);
+    const double alpha = rho / pq;
+    // phase 2: x, r, z and the two reductions
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * VB + threadIdx.x; j < npix; j += stride) {
+        double rv[POL], zv[POL];
+#pragma unroll
+        for (int k = 0; k < POL; ++k) {
+            const int64_t i = POL * j + k;
+            x[i] = fma(alpha, p[i], x[i]);
+            rv[k] = fma(-alpha, q[i], r[i]);
+            r[i] = rv[k];
+        }
+        bd_z<POL>(inv, j, rv, zv);
+#pragma unroll
+        for (int k = 0; k < POL; ++k) {
+            z[POL * j + k] = zv[k];
+            s0 = fma(rv[k], zv[k], s0);
+            s1 = fma(rv[k], rv[k], s1);
+        }
+    }
+    s0 = block_sum(s0, red);
+    s1 = block_sum(s1, red);
+    if (threadIdx.x == 0) { g_part[0][blockIdx.x] = s0; g_part[1][blockIdx.x] = s1; }
+    grid.sync();
+    const double rho_new = sum_partials(g_part[0], gridDim.x, red);
+    const double rr = sum_partials(g_part[1], gridDim.x, red);
+    const double beta = rho_new / rho;
+    // phase 3: next search direction (same pixel -> thread mapping as phase 2: z is this thread's own)
+    for (int64_t j = (int64_t)blockIdx.x * VB + threadIdx.x; j < npix; j += stride) {
+#pragma unroll
+        for (int k = 0; k < POL; ++k) {
+            const int64_t i = POL * j + k;
+            p[i] = fma(beta, p[i], z[i]);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        scal[1] = rho;
+        scal[0] = rho_new;
+        scal[2] = pq;
+        scal[3] = rr;
+        scal[4] = alpha;
+        scal[5] = beta;
+        scal[8] += 1.0;
+        scal[7] = (sqrt(rr) < scal[6]) ? 1.0 : 0.0;
     }
 }
 
@@ -293,15 +380,15 @@ extern "C" int cm2_pcg_update_xr(const double *p, const double *q, double *x, do
 }
 
 extern "C" int cm2_pcg_bd_reset(const double *inv, int64_t npix, int pol, double *r, double *z, double *scal,
-                                double atol, const double *b, double *x, cm2_stream_t stream) {
+                                double atol, const double *b, double *x, double *p0, cm2_stream_t stream) {
     CM2_REQUIRE(npix >= 0 && pol >= 1 && pol <= 3, "bad npix/pol");
     CM2_REQUIRE(aligned(inv, 16), "inverse blocks must be 16-byte aligned");
     CM2_REQUIRE((b == nullptr) == (x == nullptr), "b and x go together");
     cudaStream_t st = as_stream(stream);
     const int g = vgrid(npix);
-    if (pol == 1) k_bd_reset<1><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol, b, x);
-    else if (pol == 2) k_bd_reset<2><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol, b, x);
-    else k_bd_reset<3><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol, b, x);
+    if (pol == 1) k_bd_reset<1><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol, b, x, p0);
+    else if (pol == 2) k_bd_reset<2><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol, b, x, p0);
+    else k_bd_reset<3><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol, b, x, p0);
     CM2_LAUNCHED();
     return CM2_OK;
 }
@@ -327,4 +414,32 @@ extern "C" int cm2_pcg_bd_update(const double *inv, int64_t npix, int pol, const
     else k_bd_update<3><<<g, VB, 0, st>>>(inv, npix, p, q, x, r, z, scal);
     CM2_LAUNCHED();
     return CM2_OK;
+}
+
+template <int POL>
+static int launch_bd_iter(const double *inv, int64_t npix, double *p, const double *q, double *x, double *r, double *z,
+                          double *scal, cudaStream_t st) {
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bd_iter<POL>, VB, 0);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int64_t g = (int64_t)sm_count() * per_sm;            // all CTAs co-resident: grid barriers are safe
+    if (g > MAXP) g = MAXP;
+    const int64_t need = (npix + VB - 1) / VB;
+    if (need < g) g = need < 1 ? 1 : need;
+    void *args[] = {(void *)&inv, (void *)&npix, (void *)&p, (void *)&q, (void *)&x, (void *)&r, (void *)&z, (void *)&scal};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_bd_iter<POL>, dim3((unsigned)g), dim3(VB), args, 0, st);
+    if (e != cudaSuccess) return set_error(CM2_ERR_CUDA, "cm2_pcg_bd_iter: %s", cudaGetErrorString(e));
+    count_launch();
+    return CM2_OK;
+}
+
+extern "C" int cm2_pcg_bd_iter(const double *inv, int64_t npix, int pol, double *p, const double *q, double *x,
+                               double *r, double *z, double *scal, cm2_stream_t stream) {
+    CM2_REQUIRE(npix >= 0 && pol >= 1 && pol <= 3, "bad npix/pol");
+    CM2_REQUIRE(aligned(inv, 16), "inverse blocks must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    if (pol == 1) return launch_bd_iter<1>(inv, npix, p, q, x, r, z, scal, st);
+    if (pol == 2) return launch_bd_iter<2>(inv, npix, p, q, x, r, z, scal, st);
+    return launch_bd_iter<3>(inv, npix, p, q, x, r, z, scal, st);
 }

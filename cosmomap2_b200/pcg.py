@@ -16,7 +16,8 @@ that turns every later update kernel into a no-op.  The host therefore queues it
 iteration k is still running and reads the flag one iteration late (8 bytes, pinned, async): the
 GPU never idles, yet x, the iteration count and info are exactly SciPy's.
 When M is the block-diagonal preconditioner its apply is pixel-local and is folded into the
-kernel that updates r (cm2_pcg_bd_*): 4 launches per iteration besides the A apply.
+kernel that updates r, together with the next search direction: an iteration is the A apply plus
+ONE cooperative launch (cm2_pcg_bd_iter).
 NumPy ``b`` in -> NumPy ``x`` out; CUDA tensor in -> CUDA tensor out.
 """
 import numpy as np
@@ -62,6 +63,7 @@ class PCG(object):
         self.z = dv.empty_f64(n) if self.bd is not None else None
         self._pin = [torch.empty(NSCAL, dtype=torch.float64).pin_memory() for _ in range(2)]
         self._ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self._coop = True         # one cooperative launch for the pixel-domain tail (falls back if refused)
         self._queued = 0          # iterations launched since start()
         self._snap = 0            # snapshots enqueued
 
@@ -95,7 +97,7 @@ class PCG(object):
         if x0 is None and self.bd is not None:
             # x0 = 0 with M_BD: r = b, x = 0, z = M r, rho, ||r||^2 in ONE pass
             dv.call("cm2_pcg_bd_reset", dv.ptr(self.bd._inv_dev), self.bd._n, self.bd.pol, dv.ptr(self.r),
-                    dv.ptr(self.z), dv.ptr(self.scal), float(atol), dv.ptr(b), dv.ptr(self.x), st())
+                    dv.ptr(self.z), dv.ptr(self.scal), float(atol), dv.ptr(b), dv.ptr(self.x), dv.ptr(self.p), st())
             self._queued = 0
             return
         self.r.copy_(b)
@@ -108,7 +110,7 @@ class PCG(object):
                 dv.call("cm2_axpby", -1.0, dv.ptr(ax), 1.0, dv.ptr(self.r), n, st())
         if self.bd is not None:
             dv.call("cm2_pcg_bd_reset", dv.ptr(self.bd._inv_dev), self.bd._n, self.bd.pol, dv.ptr(self.r),
-                    dv.ptr(self.z), dv.ptr(self.scal), float(atol), None, None, st())
+                    dv.ptr(self.z), dv.ptr(self.scal), float(atol), None, None, dv.ptr(self.p), st())
         else:
             dv.call("cm2_pcg_reset", dv.ptr(self.r), n, dv.ptr(self.scal), float(atol), st())
         self._queued = 0
@@ -122,10 +124,18 @@ class PCG(object):
         """Queue one iteration (no host synchronisation)."""
         n, st = self.n, dv.stream
         if self.bd is not None:
-            dv.call("cm2_pcg_bd_update_p", dv.ptr(self.z), dv.ptr(self.p), n, dv.ptr(self.scal), st())
+            # p already holds this iteration's search direction (bd_reset / the previous bd_iter)
             q = self._apply_A(self.p)
-            dv.call("cm2_pcg_bd_update", dv.ptr(self.bd._inv_dev), self.bd._n, self.bd.pol, dv.ptr(self.p), dv.ptr(q),
-                    dv.ptr(self.x), dv.ptr(self.r), dv.ptr(self.z), dv.ptr(self.scal), st())
+            if self._coop:
+                try:
+                    dv.call("cm2_pcg_bd_iter", dv.ptr(self.bd._inv_dev), self.bd._n, self.bd.pol, dv.ptr(self.p),
+                            dv.ptr(q), dv.ptr(self.x), dv.ptr(self.r), dv.ptr(self.z), dv.ptr(self.scal), st())
+                except dv._cabi.Cm2Error:
+                    self._coop = False          # cooperative launch refused (e.g. GPU shared): 3-kernel tail
+            if not self._coop:
+                dv.call("cm2_pcg_bd_update", dv.ptr(self.bd._inv_dev), self.bd._n, self.bd.pol, dv.ptr(self.p),
+                        dv.ptr(q), dv.ptr(self.x), dv.ptr(self.r), dv.ptr(self.z), dv.ptr(self.scal), st())
+                dv.call("cm2_pcg_bd_update_p", dv.ptr(self.z), dv.ptr(self.p), n, dv.ptr(self.scal), st())
         else:
             z = self.M._apply(self.r)
             dv.call("cm2_pcg_update_p", dv.ptr(self.r), dv.ptr(z), dv.ptr(self.p), n, dv.ptr(self.scal), st())

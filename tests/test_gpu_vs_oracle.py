@@ -309,3 +309,28 @@ def test_strict_parity_setup_is_bit_identical(cm, pol, weighted):
              3: ["counts", "cosine", "sine", "cos2", "sin2", "sincos", "cos", "sin"]}[pol]
     for nm in names:
         assert np.array_equal(np.asarray(getattr(a, nm)), np.asarray(getattr(b, nm))), nm
+
+
+def test_pcg_cooperative_tail_equals_three_kernel_tail(cm):
+    """cm2_pcg_bd_iter (one cooperative launch) and the three-kernel fallback give the same iterates."""
+    import torch
+    from cosmomap2_b200.pcg import PCG
+    from cosmomap2_b200 import _device as dv
+    g = gc.load("solve_pol3")
+    pol, npix, P, N, Mbd, B, A, b = gc.build_solve_system(cm, g)
+    n = pol * npix
+    bd = dv.to_dev_f64(b)
+    outs = []
+    for coop in (True, False):
+        s = PCG(A, Mbd, n)
+        s._coop = coop
+        s.start(bd, None, 0.0)
+        hist = []
+        for _ in range(12):
+            s.step_async()
+            hist.append(s.state()[0])
+        assert s._coop == coop
+        outs.append((dv.to_host(s.x), np.array(hist)))
+    gc.close(outs[0][0], outs[1][0], rtol=1e-12, what="x after 12 iterations")
+    gc.close(outs[0][1], outs[1][1], rtol=1e-9, what="residual history")
+    gc.close(outs[0][1], g["cg_hist"][:12], rtol=1e-6, what="history vs the reference's SciPy run")
