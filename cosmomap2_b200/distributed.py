@@ -93,7 +93,6 @@ class P2PAllReduce(object):
         self._send_tab, self._recv_tab, self._sig_tab = arr(*send_p), arr(*recv_p), arr(*sig_p)
         self.gen = 0
         torch.cuda.synchronize()
-        dist.barrier(group=group)
 
     def __call__(self, y):
         from . import _device as dv
@@ -129,12 +128,21 @@ class AllReduceLO(lp.LinearOperator):
         self.group = group
         self._p2p = None
         use = p2p_enabled() if p2p is None else p2p
-        if use and is_distributed(group) and torch.cuda.is_available() and dist.get_backend(group) == "nccl":
+        if (use and is_distributed(group) and torch.cuda.is_available() and dist.get_backend(group) == "nccl"
+                and dist.get_world_size(group) <= 8):
+            # the set-up can fail on ONE rank only (no peer access, IPC refused): all ranks then agree
+            # to use NCCL, otherwise some would wait in the peer exchange for ranks that never come
+            err = None
             try:
                 self._p2p = P2PAllReduce(local_op.nargout, group)
-            except Exception as e:                       # no peer access / IPC: NCCL path, loudly noted
-                import warnings
-                warnings.warn("P2P all-reduce unavailable (%s); using NCCL all_reduce" % (e,))
+            except Exception as e:
+                err, self._p2p = e, None
+            ok = torch.tensor([0.0 if self._p2p is None else 1.0], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if ok.item() == 0.0:
+                if err is not None or dist.get_rank(group) == 0:
+                    import warnings
+                    warnings.warn("P2P all-reduce unavailable (%s); all ranks use NCCL all_reduce" % (err,))
                 self._p2p = None
         super(AllReduceLO, self).__init__(local_op.nargin, local_op.nargout, matvec=self._run,
                                           symmetric=local_op.symmetric, device=True)
