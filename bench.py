@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--cpu-iters", type=int, default=10)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --nt samples per GPU (default, the contract); strong: --nt samples in total")
     return ap.parse_args()
 
 
@@ -177,7 +179,8 @@ def main():
 
     # ---- inputs: this rank's detectors of configs[1] -----------------------------------------------
     pol = 3
-    sc = synthetic.config_c2(nt=args.nt, seed=rank)
+    nt_rank = args.nt if args.scaling == "weak" else max(args.nt // world, 64 * 256)
+    sc = synthetic.config_c2(nt=nt_rank, seed=rank)
     nt = sc.nt
     N = cm.BlockLO(sc.ns, sc.weights)
     pix = sc.pix                                     # int32 HEALPix ids, relabelled in place
@@ -334,7 +337,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "configs[1]: synthetic raster scan, 1e8 samples/GPU, IQU nside=512, white noise "
                                    "(64 detector blocks), M_BD PCG on A=P^T N^-1 P",
                        "nt_per_gpu": nt, "npix_observed": int(npix), "pol": pol, "nside": 512,
