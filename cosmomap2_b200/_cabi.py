@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcosmomap2_b200.so")
+LIB_PATH = os.environ.get("CM2_LIB") or os.path.join(_HERE, "csrc", "libcosmomap2_b200.so")
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64
