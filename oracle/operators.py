@@ -35,6 +35,17 @@ def dgemm(A, B):
     return matdot(alpha=1.0, a=A.T, b=B, trans_b=True, trans_a=False)
 
 
+def get_legendre_polynomials(polyorder, size):
+    """utilities/linear_algebra_funcs.py:47-59 -- columns L_k(x)/||L_k(x)||, x = linspace(-1, 1, size)."""
+    from scipy.special import legendre
+    legendres = np.empty([size, polyorder + 1])
+    x = np.linspace(-1, 1, size)
+    for i in range(polyorder + 1):
+        L = legendre(i)
+        legendres[:, i] = L(x) / norm2(L(x))
+    return legendres
+
+
 def norm2(q):
     """utilities/linear_algebra_funcs.py:31-37."""
     q = np.asarray(q)
@@ -505,11 +516,49 @@ class FilterLO(lp.LinearOperator):
             self.tstart = [self.tstart]
         self.pixels = pix_samples
         self.poly_order = poly_order
-        if poly_order != 0:
-            raise NotImplementedError("Legendre filtering (poly_order>0) is outside the hot path "
-                                      "(SURVEY.md section 8(f))")
-        super(FilterLO, self).__init__(nargin=size, nargout=size, matvec=self.mult,
-                                       symmetric=False)
+        if poly_order == 0:
+            super(FilterLO, self).__init__(nargin=size, nargout=size, matvec=self.mult,
+                                           symmetric=False)
+        else:                                            # :279-282 (the Pool is an implementation detail)
+            self.compute_legendres()
+            super(FilterLO, self).__init__(nargin=size, nargout=size, matvec=self.polyfilter,
+                                           symmetric=False)
+
+    def compute_legendres(self):                         # :206-213
+        sizes = []
+        for array in self.subscans:
+            for i in array:
+                if int(i) not in sizes:
+                    sizes.append(int(i))
+        self.legendres = {size: get_legendre_polynomials(self.poly_order, size) for size in sizes}
+
+    def polyfilter(self, d):                             # :170-204 (== procsfilter/globalprocsfilter per CES)
+        vec_out = d * 0.
+        mask = np.asarray(self.pixels) >= 0
+        offset = 0
+        for subsc, ts, ns, nb in zip(self.subscans, self.tstart, self.nsamples, self.nbolos):
+            n = nb * ns
+            for bolo_iter in range(nb):
+                for i, j in zip(subsc, ts):
+                    start = int(j + (ns * bolo_iter) + offset)
+                    end = int(start + i)
+                    tmpmask = mask[start:end]
+                    size = int(np.count_nonzero(tmpmask))
+                    if size <= self.poly_order:
+                        continue
+                    legendres = self.legendres[int(i)]
+                    if size != i:
+                        q, r = np.linalg.qr(legendres[tmpmask])
+                        legendres = q
+                    p = np.zeros(size)
+                    seg = d[start:end][tmpmask]
+                    for k in range(self.poly_order + 1):
+                        filterbasis = legendres[:, k]
+                        p += scalprod(np.ascontiguousarray(filterbasis), np.ascontiguousarray(seg)) * filterbasis
+                    out = vec_out[start:end]
+                    out[tmpmask] = seg - p
+            offset += n
+        return vec_out
 
 
 def _seq_sum(a):
@@ -692,6 +741,47 @@ class DeflationLO(lp.LinearOperator):
             self.z.append(z[:, j])
         super(DeflationLO, self).__init__(nargin=self.ncols, nargout=self.nrows,
                                           matvec=self.mult, symmetric=False, rmatvec=self.rmult)
+
+
+class GroundFilterLO(lp.LinearOperator):
+    """interfaces/linearoperators.py:24-61 -- I - G (G^T G)^-1 G^T over ground-template bins."""
+
+    def counts_in_groundbins(self, g):                   # :26-46
+        g = np.asarray(g)
+        return np.bincount(g[g != -1], minlength=self.nbins).astype(np.float64)
+
+    def mult(self, v):                                   # :48-49
+        return v - self.Pg * v
+
+    def __init__(self, ground):                          # :51-61
+        self.nbins = int(max(ground)) + 1
+        self.n = len(ground)
+        counts = self.counts_in_groundbins(ground)
+        G = SparseLO(self.nbins, self.n, ground)
+        G.counts = counts
+        invGtG = BlockDiagonalPreconditionerLO(G, self.nbins)
+        self.Pg = (G * invGtG * G.T)
+        super(GroundFilterLO, self).__init__(nargin=self.n, nargout=self.n, matvec=self.mult,
+                                             symmetric=True)
+
+
+def reorganize_map(mapin, obspix, npix, nside, pol, fname=None):
+    """utilities/healpy_functions.py:50-105 -- de-interleave the solution and expand the observed
+    pixels to full-sky HEALPix arrays (hp.nside2npix(nside) = 12 nside^2); writing to file is out
+    of scope."""
+    healpix_npix = 12 * nside * nside
+    obspix = np.asarray(obspix)
+    if pol == 3:
+        m = np.zeros((healpix_npix, 3))
+        m[obspix, 0], m[obspix, 1], m[obspix, 2] = mapin[::3], mapin[1::3], mapin[2::3]
+        return [m[:, 0], m[:, 1], m[:, 2]]
+    if pol == 2:
+        m = np.zeros((healpix_npix, 2))
+        m[obspix, 0], m[obspix, 1] = mapin[::2], mapin[1::2]
+        return [m[:, 0], m[:, 1]]
+    m = np.zeros(healpix_npix)
+    m[obspix] = mapin
+    return [m]
 
 
 def two_level_preconditioner(Mbd, A_or_AZd, Zd, E, n):

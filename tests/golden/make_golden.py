@@ -260,6 +260,45 @@ def case_pcg_and_deflation():
         save("solve_pol%d" % pol, **out)
 
 
+def case_next_rows():
+    """GroundFilterLO (linearoperators.py:24-61), the Legendre path of FilterLO
+    (:170-204, serial polyfilter; the multiprocessing wrapper is Python-2 only) and reorganize_map
+    (healpy_functions.py:50-105, restated without healpy in the oracle; not run here)."""
+    rng = np.random.default_rng(21)
+    out = {}
+    nt = 3000
+    ground = rng.integers(0, 25, size=nt).astype(np.int64)
+    ground[rng.random(nt) < 0.07] = -1
+    v = rng.standard_normal(nt)
+    G = R.GroundFilterLO(ground.copy())
+    out.update(ground=ground, gv=v, gFv=G * v, g_nbins=G.nbins)
+    # Legendre filter: 2 CES, flags, one subscan with fewer unflagged samples than the order
+    nsamples, nbolos = [400, 300], [2, 2]
+    subs, tst = [], []
+    for ns in nsamples:
+        L, S = make_subscans(rng, ns, 5)
+        subs.append(L)
+        tst.append(S)
+    ntl = sum(a * b for a, b in zip(nsamples, nbolos))
+    pix = rng.integers(0, 30, size=ntl).astype(np.int64)
+    pix[rng.random(ntl) < 0.15] = -1
+    s0 = nsamples[0] * 1 + tst[0][1]
+    pix[s0:s0 + subs[0][1]] = -1
+    pix[s0] = 3                                          # 1 unflagged sample <= poly_order
+    s1 = tst[0][2]
+    pix[s1:s1 + subs[0][2]] = np.abs(pix[s1:s1 + subs[0][2]])   # a subscan without any flag
+    d = rng.standard_normal(ntl) + np.linspace(0, 5, ntl)
+    out.update(l_nsamples=np.array(nsamples), l_nbolos=np.array(nbolos), l_pix=pix, l_d=d)
+    for i in range(2):
+        out["l_sub_len%d" % i] = subs[i]
+        out["l_sub_start%d" % i] = tst[i]
+    for order in (1, 2, 3):
+        F = R.FilterLO(ntl, [subs, tst], nsamples, nbolos, pix, poly_order=order, npool=1)
+        out["l_Fd_order%d" % order] = F.polyfilter(d)
+        F.procs.terminate()
+    save("next_rows", **out)
+
+
 if __name__ == "__main__":
     print("scipy", scipy.__version__, "numpy", np.__version__)
     case_process_and_pointing()
@@ -267,3 +306,4 @@ if __name__ == "__main__":
     case_toeplitz()
     case_filter()
     case_pcg_and_deflation()
+    case_next_rows()

@@ -209,3 +209,19 @@ def check_solve(impl, name, cg, hist_rtol=1e-6, strict_arnoldi_m=True):
         lhs = MA * V[j]
         rhs = sum(hs[j][i] * V[i] for i in range(j + 2))
         close(lhs, rhs, rtol=1e-9, what="Arnoldi relation column %d" % j)
+
+
+def check_next_rows(impl, orders=(1, 2, 3)):
+    """GroundFilterLO and the Legendre path of FilterLO against the reference."""
+    g = load("next_rows")
+    G = impl.GroundFilterLO(g["ground"].copy())
+    assert G.nbins == int(g["g_nbins"])
+    close(G * g["gv"], g["gFv"], what="GroundFilterLO v")
+    nsamples = [int(i) for i in g["l_nsamples"]]
+    nbolos = [int(i) for i in g["l_nbolos"]]
+    subs = [g["l_sub_len0"], g["l_sub_len1"]]
+    tst = [g["l_sub_start0"], g["l_sub_start1"]]
+    nt = len(g["l_d"])
+    for order in orders:
+        F = impl.FilterLO(nt, [subs, tst], nsamples, nbolos, g["l_pix"].copy(), poly_order=order, npool=1)
+        close(F * g["l_d"], g["l_Fd_order%d" % order], rtol=1e-9, what="Legendre filter order %d" % order)

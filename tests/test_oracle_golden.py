@@ -30,6 +30,23 @@ def test_oracle_filter_ops():
     gc.check_filter_ops(oracle)
 
 
+def test_oracle_next_rows_ground_and_legendre_filters():
+    gc.check_next_rows(oracle)
+
+
+def test_oracle_reorganize_map():
+    rng = np.random.default_rng(0)
+    nside, npix = 8, 40
+    obspix = np.sort(rng.choice(12 * nside * nside, npix, replace=False))
+    for pol in (1, 2, 3):
+        m = rng.standard_normal(pol * npix)
+        out = oracle.reorganize_map(m, obspix, npix, nside, pol)
+        assert len(out) == pol and all(len(o) == 12 * nside * nside for o in out)
+        for k in range(pol):
+            assert np.array_equal(out[k][obspix], m[k::pol])
+            assert np.count_nonzero(out[k]) == np.count_nonzero(m[k::pol])
+
+
 @pytest.mark.parametrize("pol", [1, 2, 3])
 def test_oracle_solve(pol):
     gc.check_solve(oracle, "solve_pol%d" % pol, spla.cg)
