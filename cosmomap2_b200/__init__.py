@@ -17,13 +17,14 @@ from . import linearoperators as blk  # noqa: F401  (BlockDiagonalLinearOperator
 from .linearoperators import (SparseLO, ToeplitzLO, WeightingLO, BlockLO, FilterLO,  # noqa: F401
                               BlockDiagonalLinearOperator, BlockDiagonalLO,
                               BlockDiagonalPreconditionerLO, InverseLO, CoarseLO, DeflationLO,
+                              GroundFilterLO,
                               TwoLevelPreconditionerLO)
 from .process_ces import ProcessTimeSamples, BlockWeights  # noqa: F401
 from .deflationlib import (arnoldi, build_hess, build_Z, run_krypy_arnoldi,  # noqa: F401
                            find_ritz_eigenvalues, krypy_arnoldi, krypy_ritz)
 from .utilities import (dgemm, norm2, scalprod, get_legendre_polynomials, is_sorted,  # noqa: F401
                         bash_colors, filter_warnings, angles_gen, pairs_gen, checking_output,
-                        noise_val, subscan_resize, system_setup)
+                        noise_val, subscan_resize, system_setup, reorganize_map)
 from .pcg import cg  # noqa: F401
 
 __version__ = "0.1.0"

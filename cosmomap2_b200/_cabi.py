@@ -52,6 +52,12 @@ SIGNATURES = {
     "cm2_filter_runs_fill": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cm2_filter_seg_mean": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
     "cm2_amatvec_filter_mu": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "cm2_filter_poly_max_order": (_int, []),
+    "cm2_filter_poly_apply": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _int, _vp, _vp, _i64, _vp]),
+    "cm2_amatvec_filter_poly_max_order": (_int, []),
+    "cm2_amatvec_filter_poly": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _i64, _i64, _int, _vp, _vp, _i64, _vp]),
+    "cm2_ground_filter_apply": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "cm2_reorganize_map": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp]),
     "cm2_defl_work_doubles": (_i64, [_int]),
     "cm2_defl_zt_apply": (_int, [_vp, _i64, _int, _i64, _vp, _int, _i64, _vp, _vp, _vp]),
     "cm2_defl_z_apply": (_int, [_vp, _i64, _int, _i64, _vp, _f64, _f64, _vp, _vp, _vp]),
@@ -74,7 +80,8 @@ SIGNATURES = {
 # entry points that return a size/count rather than a status
 _NOT_STATUS = {"cm2_version", "cm2_last_error", "cm2_launch_count", "cm2_scan_scratch_bytes",
                "cm2_toeplitz_scratch_bytes", "cm2_defl_work_doubles", "cm2_allreduce_p2p_signal_bytes",
-               "cm2_toeplitz_fft_points", "cm2_toeplitz_fft_scratch_bytes"}
+               "cm2_toeplitz_fft_points", "cm2_toeplitz_fft_scratch_bytes", "cm2_filter_poly_max_order",
+               "cm2_amatvec_filter_poly_max_order"}
 
 
 def _load():

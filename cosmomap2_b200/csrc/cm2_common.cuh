@@ -114,6 +114,102 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
     }
     return t;  // valid in warp 0
 }
+// ---- Legendre subscan filter helpers (filter_poly.cu, tod_pass.cu) ------------------------------
+// Legendre P_0..P_{NK-1} at x by the three-term recurrence
+template <int NK>
+__device__ __forceinline__ void legendre(double x, double (&L)[NK]) {
+    L[0] = 1.0;
+    if constexpr (NK > 1) L[1] = x;
+#pragma unroll
+    for (int n = 1; n + 1 < NK; ++n) L[n + 1] = ((2 * n + 1) * x * L[n] - n * L[n - 1]) * (1.0 / (n + 1));
+}
+
+// c = G^-1 S for the symmetric positive definite NK x NK Gram matrix G (upper triangle packed row by
+// row in g), by Cholesky on the diagonally scaled system.  One thread; every loop has compile-time
+// bounds so the factor lives in registers.  Returns the smallest pivot of the scaled factorisation
+// (1 = orthogonal basis; small = ill-conditioned: the caller then refines, see filter_refine_steps).
+template <int NK>
+__device__ __forceinline__ double gram_solve(const double *g, const double *S, double (&c)[NK]) {
+    double A[NK][NK], dsc[NK], y[NK];
+    double minpiv = 1.0;
+    {
+        int q = 0;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+#pragma unroll
+            for (int l = k; l < NK; ++l) { A[k][l] = g[q]; ++q; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NK; ++k) dsc[k] = A[k][k] > 0.0 ? rsqrt(A[k][k]) : 0.0;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+#pragma unroll
+        for (int l = k; l < NK; ++l) A[k][l] *= dsc[k] * dsc[l];
+    }
+    // A = R^T R, R upper triangular, stored in place of the upper triangle
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        double piv = A[k][k];
+#pragma unroll
+        for (int m = 0; m < k; ++m) piv -= A[m][k] * A[m][k];
+        minpiv = fmin(minpiv, piv);
+        const double rkk = piv > 0.0 ? sqrt(piv) : 0.0;
+        const double inv = rkk > 0.0 ? 1.0 / rkk : 0.0;
+        A[k][k] = inv;                      // keep 1/r_kk on the diagonal
+#pragma unroll
+        for (int l = k + 1; l < NK; ++l) {
+            double v = A[k][l];
+#pragma unroll
+            for (int m = 0; m < k; ++m) v -= A[m][k] * A[m][l];
+            A[k][l] = v * inv;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {          // R^T y = D S
+        double v = S[k] * dsc[k];
+#pragma unroll
+        for (int m = 0; m < k; ++m) v -= A[m][k] * y[m];
+        y[k] = v * A[k][k];
+    }
+#pragma unroll
+    for (int k = NK - 1; k >= 0; --k) {     // R z = y ; c = D z
+        double v = y[k];
+#pragma unroll
+        for (int l = k + 1; l < NK; ++l) v -= A[k][l] * c[l];
+        c[k] = v * A[k][k];
+    }
+#pragma unroll
+    for (int k = 0; k < NK; ++k) c[k] *= dsc[k];
+    return minpiv;
+}
+
+// The normal equations square the condition number of the basis.  With the Legendre basis of the
+// interval spanned by the unflagged samples the Gram matrix is close to diagonal for any realistic
+// flag pattern (pivots 0.3..1); a handful of unflagged samples at scattered positions can make it
+// nearly singular.  Below this pivot the fit is corrected by refinement steps on the residual
+// (c += G^-1 L^T (d - L c)): each step squares the relative error of the fitted values.
+__device__ __forceinline__ int filter_refine_steps(double minpiv) { return minpiv < 1e-3 ? 2 : 0; }
+
+// Deterministic CTA-wide sum of N values per thread: fixed shuffle tree, then warps in order.
+// red: NW*N doubles, tot: N doubles of shared memory; tot is valid after the call (barrier inside).
+template <int N, int NW>
+__device__ __forceinline__ void block_sum_n(const double (&acc)[N], double *red, double *tot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double w = warp_sum(acc[i]);
+        if (lane == 0) red[warp * N + i] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) t += red[w * N + threadIdx.x];
+        tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+}
 #endif
 
 }  // namespace cm2

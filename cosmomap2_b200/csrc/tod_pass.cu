@@ -571,6 +571,192 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter(const int32_t *__restr
     }
 }
 
+// Fused y = P^T F_K P x with the Legendre subscan filter F_K (FilterLO.polyfilter,
+// linearoperators.py:170-204; NK = poly_order + 1 >= 2): one CTA per subscan, no TOD temporary.
+//   pass 0: the subscan's pixels -> shared memory; number / first / last unflagged sample
+//   pass 1: d = P x of the subscan -> shared memory; S_k = sum L_k d, G_kl = sum L_k L_l
+//   solve : c_k = S_k / G_kk without flags (the reference's literal sum over the sampled,
+//           not exactly orthogonal, basis), else G c = S (QR re-orthonormalised basis, :190-194)
+//   pass 2: scatter-add of d - sum_k c_k L_k over the unflagged samples
+// cap = shared-memory window in samples (a multiple of TILE covering the longest subscan).
+template <int POL, int NK>
+__global__ void __launch_bounds__(BLOCK) k_amatvec_filter_poly(const int32_t *__restrict__ pix, const double *__restrict__ cs,
+                                                               const double *__restrict__ sn, int64_t nt,
+                                                               const int64_t *__restrict__ seg_start,
+                                                               const int64_t *__restrict__ seg_end, int64_t nseg,
+                                                               const double *__restrict__ x, double *__restrict__ y, int cap) {
+    constexpr int NR = NK + NK * (NK + 1) / 2;
+    constexpr int NW = BLOCK / 32;
+    extern __shared__ double sd[];                          // cap doubles, then cap ints
+    int *sp = reinterpret_cast<int *>(sd + cap);
+    __shared__ double red[NW * NR];
+    __shared__ double tot[NR];
+    __shared__ double coef[NK];
+    __shared__ int s_cnt, s_jmin, s_jmax, s_refine;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t k = blockIdx.x; k < nseg; k += gridDim.x) {
+        const int64_t a = seg_start[k], b = seg_end[k];
+        const int64_t tile0 = a / TILE, tile1 = (b + TILE - 1) / TILE;   // [tile0, tile1)
+        const int64_t base = tile0 * TILE;
+        if (threadIdx.x == 0) { s_cnt = 0; s_jmin = INT32_MAX; s_jmax = -1; }
+        __syncthreads();
+        int cnt = 0, jmin = INT32_MAX, jmax = -1;
+        for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
+            const int64_t t0 = tile * TILE + (int64_t)lane * K;
+            int p[K];
+            load_pix_keep(pix, t0, nt, p);
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                if (t0 + j < a || t0 + j >= b || p[j] < 0) p[j] = -1;
+                sp[t0 + j - base] = p[j];
+                if (p[j] >= 0) {
+                    const int jj = (int)(t0 + j - a);
+                    ++cnt;
+                    jmin = min(jmin, jj);
+                    jmax = max(jmax, jj);
+                }
+            }
+        }
+        cnt = __reduce_add_sync(FULL, cnt);
+        jmin = __reduce_min_sync(FULL, jmin);
+        jmax = __reduce_max_sync(FULL, jmax);
+        if (lane == 0 && cnt > 0) { atomicAdd(&s_cnt, cnt); atomicMin(&s_jmin, jmin); atomicMax(&s_jmax, jmax); }
+        __syncthreads();
+        const int n = s_cnt;
+        if (n > NK - 1) {                                    // block-uniform
+            const bool full = (int64_t)n == b - a;
+            const int j0 = full ? 0 : s_jmin;
+            const int j1 = full ? (int)(b - a - 1) : s_jmax;
+            const double step = 2.0 / (double)(j1 - j0);
+            double acc[NR];
+#pragma unroll
+            for (int i = 0; i < NR; ++i) acc[i] = 0.0;
+            for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
+                const int64_t t0 = tile * TILE + (int64_t)lane * K;
+                int p[K];
+                double c[K], s[K], xv[K][POL];
+#pragma unroll
+                for (int j = 0; j < K; ++j) p[j] = sp[t0 + j - base];
+                if (POL > 1) { load_f64_keep(cs, t0, nt, c); load_f64_keep(sn, t0, nt, s); }
+                gather_x<POL>(x, p, xv);
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    double dv = 0.0;
+                    if (p[j] >= 0) {
+                        dv = project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0);
+                        double L[NK];
+                        legendre<NK>(fma((double)((int)(t0 + j - a) - j0), step, -1.0), L);
+                        int q = NK;
+#pragma unroll
+                        for (int r = 0; r < NK; ++r) {
+                            acc[r] = fma(L[r], dv, acc[r]);
+#pragma unroll
+                            for (int l = r; l < NK; ++l) { acc[q] = fma(L[r], L[l], acc[q]); ++q; }
+                        }
+                    }
+                    sd[t0 + j - base] = dv;
+                }
+            }
+            block_sum_n<NR, NW>(acc, red, tot);
+            if (threadIdx.x == 0) {
+                s_refine = 0;
+                if (full) {
+                    int q = NK;
+#pragma unroll
+                    for (int r = 0; r < NK; ++r) {
+                        coef[r] = tot[q] > 0.0 ? tot[r] / tot[q] : 0.0;
+                        q += NK - r;
+                    }
+                } else {
+                    double cc[NK];
+                    s_refine = filter_refine_steps(gram_solve<NK>(tot + NK, tot, cc));
+#pragma unroll
+                    for (int r = 0; r < NK; ++r) coef[r] = cc[r];
+                }
+            }
+            __syncthreads();
+            const int nref = s_refine;                       // block-uniform, 0 unless ill-conditioned
+            for (int it = 0; it < nref; ++it) {
+                double cc[NK], racc[NK];
+#pragma unroll
+                for (int r = 0; r < NK; ++r) { cc[r] = coef[r]; racc[r] = 0.0; }
+                for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
+                    const int64_t t0 = tile * TILE + (int64_t)lane * K;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        if (sp[t0 + j - base] < 0) continue;
+                        double L[NK];
+                        legendre<NK>(fma((double)((int)(t0 + j - a) - j0), step, -1.0), L);
+                        double res = sd[t0 + j - base];
+#pragma unroll
+                        for (int r = 0; r < NK; ++r) res = fma(-cc[r], L[r], res);
+#pragma unroll
+                        for (int r = 0; r < NK; ++r) racc[r] = fma(L[r], res, racc[r]);
+                    }
+                }
+                block_sum_n<NK, NW>(racc, red, tot);
+                if (threadIdx.x == 0) {
+                    double dc[NK];
+                    gram_solve<NK>(tot + NK, tot, dc);
+#pragma unroll
+                    for (int r = 0; r < NK; ++r) coef[r] += dc[r];
+                }
+                __syncthreads();
+            }
+            double cf[NK];
+#pragma unroll
+            for (int r = 0; r < NK; ++r) cf[r] = coef[r];
+            for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
+                const int64_t t0 = tile * TILE + (int64_t)lane * K;
+                int p[K];
+                double c[K], s[K], v[K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) p[j] = sp[t0 + j - base];
+                if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    double L[NK];
+                    legendre<NK>(fma((double)((int)(t0 + j - a) - j0), step, -1.0), L);
+                    double pj = 0.0;
+#pragma unroll
+                    for (int r = 0; r < NK; ++r) pj = fma(cf[r], L[r], pj);
+                    v[j] = sd[t0 + j - base] - pj;
+                }
+                run_scatter<POL, POL>(y, p, [&](int j, double (&o)[POL]) {
+                    if constexpr (POL == 1) { o[0] = v[j]; }
+                    else if constexpr (POL == 2) { o[0] = v[j] * c[j]; o[1] = v[j] * s[j]; }
+                    else { o[0] = v[j]; o[1] = v[j] * c[j]; o[2] = v[j] * s[j]; }
+                });
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int POL, int NK>
+static int launch_amatvec_filter_poly(const int32_t *pix, const double *c, const double *s, int64_t nt,
+                                      const int64_t *seg_start, const int64_t *seg_end, int64_t nseg, const double *x,
+                                      double *y, int cap, cudaStream_t st) {
+    const size_t smem = (size_t)cap * 12;
+    auto kern = k_amatvec_filter_poly<POL, NK>;
+    CM2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<persistent_grid(kern, BLOCK, smem, nseg), BLOCK, smem, st>>>(pix, c, s, nt, seg_start, seg_end, nseg, x, y, cap);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+template <int POL>
+static int dispatch_amatvec_filter_poly(int nk, const int32_t *pix, const double *c, const double *s, int64_t nt,
+                                        const int64_t *seg_start, const int64_t *seg_end, int64_t nseg, const double *x,
+                                        double *y, int cap, cudaStream_t st) {
+    switch (nk) {
+        case 2: return launch_amatvec_filter_poly<POL, 2>(pix, c, s, nt, seg_start, seg_end, nseg, x, y, cap, st);
+        case 3: return launch_amatvec_filter_poly<POL, 3>(pix, c, s, nt, seg_start, seg_end, nseg, x, y, cap, st);
+        case 4: return launch_amatvec_filter_poly<POL, 4>(pix, c, s, nt, seg_start, seg_end, nseg, x, y, cap, st);
+        default: return launch_amatvec_filter_poly<POL, 5>(pix, c, s, nt, seg_start, seg_end, nseg, x, y, cap, st);
+    }
+}
+
 template <class Kern>
 static int tod_grid(Kern k, int64_t nt) {
     int64_t ntiles = (nt + TILE - 1) / TILE;
@@ -719,4 +905,30 @@ extern "C" int cm2_amatvec_filter_mu(const int32_t *pix, const double *c, const 
     else k_amatvec_filter_mu<3><<<tod_grid(k_amatvec_filter_mu<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, y);
     CM2_LAUNCHED();
     return CM2_OK;
+}
+
+/* fused P^T F_K P, Legendre subscan filter of order 1..4 */
+extern "C" int cm2_amatvec_filter_poly_max_order(void) { return 4; }
+
+extern "C" int cm2_amatvec_filter_poly(const int32_t *pix, const double *c, const double *s, int64_t nt, int pol,
+                                       const int64_t *seg_start, const int64_t *seg_end, int64_t nseg,
+                                       int64_t max_seg_len, int poly_order, const double *x, double *y, int64_t npix,
+                                       cm2_stream_t stream) {
+    int rc = check_tod(pix, c, s, nt, pol);
+    if (rc) return rc;
+    CM2_REQUIRE(npix >= 0 && nseg >= 0 && max_seg_len >= 0, "negative size");
+    if (poly_order < 1 || poly_order > 4)
+        return set_error(CM2_ERR_UNSUPPORTED, "fused Legendre A-matvec: poly_order=%d, orders 1..4 are supported", poly_order);
+    // window: every tile the longest subscan can touch
+    const int64_t cap = (max_seg_len / TILE + 2) * TILE;
+    if (cap * 12 > 200 * 1024)
+        return set_error(CM2_ERR_UNSUPPORTED, "fused Legendre A-matvec: subscan of %lld samples exceeds the shared-memory window",
+                         (long long)max_seg_len);
+    cudaStream_t st = as_stream(stream);
+    if (npix > 0) CM2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)npix * pol, st));
+    if (nt == 0 || npix == 0 || nseg == 0) return CM2_OK;
+    const int nk = poly_order + 1;
+    if (pol == 1) return dispatch_amatvec_filter_poly<1>(nk, pix, c, s, nt, seg_start, seg_end, nseg, x, y, (int)cap, st);
+    if (pol == 2) return dispatch_amatvec_filter_poly<2>(nk, pix, c, s, nt, seg_start, seg_end, nseg, x, y, (int)cap, st);
+    return dispatch_amatvec_filter_poly<3>(nk, pix, c, s, nt, seg_start, seg_end, nseg, x, y, (int)cap, st);
 }

@@ -392,11 +392,17 @@ def flatten_subscans(subscans, tstart, nsamples, nbolos):
     return np.concatenate(starts), np.concatenate(ends)
 
 
-class FilterLO(lp.LinearOperator):
-    """Subscan offset filter (poly_order=0) -- interfaces/linearoperators.py:94-168, 263-282.
+FILTER_STAGED = True        # subscan staged in shared memory (cm2_filter_poly_apply) also for poly_order = 0
 
+
+class FilterLO(lp.LinearOperator):
+    """Subscan filter -- interfaces/linearoperators.py:94-322.
+
+    ``poly_order = 0``: offset removal (``mult`` :129-168).  ``poly_order > 0``: Legendre polynomials
+    up to that order (``polyfilter`` :170-204; the reference's ``multiprocessing.Pool`` of ``npool``
+    workers, :246-261, 286-322, is a CPU implementation detail -- ``npool`` is accepted and ignored).
     Same constructor; the (CES, detector, subscan) triple loop of the reference is flattened at
-    construction into one list of segments [start, end) and one kernel launch applies them all.
+    construction into one list of segments [start, end) and ONE kernel launch applies them all.
     """
 
     def __init__(self, size, subscan_nsample, samples_per_bolopair, bolos_per_ces, pix_samples,
@@ -413,25 +419,64 @@ class FilterLO(lp.LinearOperator):
             self.subscans = [self.subscans]
             self.tstart = [self.tstart]
         self.pixels = pix_samples
-        self.poly_order = poly_order
-        if poly_order != 0:
-            raise NotImplementedError("Legendre filtering (poly_order>0) is outside the accelerated hot path")
+        self.poly_order = int(poly_order)
+        if self.poly_order < 0:
+            raise ValueError("poly_order must be >= 0")
+        max_order = int(dv.call("cm2_filter_poly_max_order"))
+        if self.poly_order > max_order:
+            raise NotImplementedError("poly_order=%d: the device filter supports orders 0..%d"
+                                      % (self.poly_order, max_order))
         self._seg_start_host, self._seg_end_host = flatten_subscans(self.subscans, self.tstart, self.nsamples,
                                                                     self.nbolos)
-        if len(self._seg_end_host) and (self._seg_end_host.max() > size or self._seg_start_host.min() < 0):
+        ss, se = self._seg_start_host, self._seg_end_host
+        if len(se) and (se.max() > size or ss.min() < 0):
             raise lp.ShapeError("subscan table exceeds the TOD size")
-        self._seg_start = dv.to_dev(self._seg_start_host, torch.int64)
-        self._seg_end = dv.to_dev(self._seg_end_host, torch.int64)
-        self.nseg = len(self._seg_start_host)
+        self._seg_start = dv.to_dev(ss, torch.int64)
+        self._seg_end = dv.to_dev(se, torch.int64)
+        self.nseg = len(ss)
+        self._max_seg_len = int((se - ss).max()) if self.nseg else 0
+        # sorted, non-overlapping, non-negative lengths: the kernel then writes every output sample itself
+        self._sorted = bool(self.nseg == 0 or (np.all(se >= ss) and np.all(ss[1:] >= se[:-1])))
         self._pix_dev = dv.pix_to_dev(pix_samples)
-        super(FilterLO, self).__init__(nargin=size, nargout=size, matvec=self.mult, symmetric=False,
+        self._legendres = None
+        matvec = self.mult if self.poly_order == 0 else self.polyfilter
+        super(FilterLO, self).__init__(nargin=size, nargout=size, matvec=matvec, symmetric=False,
                                        device=True)
 
+    def _staged(self, d):
+        out = torch.empty_like(d)
+        dv.call("cm2_filter_poly_apply", dv.ptr(self._pix_dev), dv.ptr(self._seg_start), dv.ptr(self._seg_end),
+                self.nseg, self._max_seg_len, self.poly_order, int(self._sorted), dv.ptr(d), dv.ptr(out),
+                d.numel(), _stream())
+        return out
+
     def mult(self, d):                                    # :129-168
+        if FILTER_STAGED:
+            return self._staged(d)
         out = torch.empty_like(d)
         dv.call("cm2_filter_offset_apply", dv.ptr(self._pix_dev), dv.ptr(self._seg_start), dv.ptr(self._seg_end),
                 self.nseg, dv.ptr(d), dv.ptr(out), d.numel(), _stream())
         return out
+
+    def polyfilter(self, d):                              # :170-204
+        return self._staged(d)
+
+    polyfilter_multithreads = polyfilter                  # :246-261
+
+    def compute_legendres(self):                          # :206-213 (host tables; the kernel evaluates
+        from .utilities import get_legendre_polynomials   # the recurrence on the fly and never reads them)
+        sizes = []
+        for array in self.subscans:
+            for i in array:
+                if int(i) not in sizes:
+                    sizes.append(int(i))
+        self._legendres = {size: get_legendre_polynomials(self.poly_order, size) for size in sizes}
+
+    @property
+    def legendres(self):
+        if self._legendres is None:
+            self.compute_legendres()
+        return self._legendres
 
 
 # =============================================================================================
@@ -533,6 +578,29 @@ class _FusedFilterA(lp.LinearOperator):
         return y
 
 
+class _FusedPolyFilterA(lp.LinearOperator):
+    """P^T F_K P for the Legendre filter (poly_order 1..4) as one kernel: one CTA per subscan, the
+    subscan's P x kept in shared memory between the moment pass and the scatter pass."""
+
+    def __init__(self, P, F):
+        self.P, self.F = P, F
+        n = P.pol * P.ncols
+        super(_FusedPolyFilterA, self).__init__(n, n, matvec=self._run, symmetric=True, device=True)
+
+    @staticmethod
+    def supported(P, F):
+        return (1 <= F.poly_order <= int(dv.call("cm2_amatvec_filter_poly_max_order")) and F._sorted
+                and (F._max_seg_len // 256 + 2) * 256 * 12 <= 200 * 1024)
+
+    def _run(self, x):
+        P, F = self.P, self.F
+        y = dv.empty_f64(P.ncols * P.pol)
+        dv.call("cm2_amatvec_filter_poly", dv.ptr(P._pix_dev), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.nrows,
+                P.pol, dv.ptr(F._seg_start), dv.ptr(F._seg_end), F.nseg, F._max_seg_len, F.poly_order, dv.ptr(x),
+                dv.ptr(y), P.ncols, _stream())
+        return y
+
+
 def _is_pt(op):
     return getattr(op, "_adjoint_of", None) is not None and isinstance(op._adjoint_of, SparseLO)
 
@@ -558,7 +626,10 @@ def _fuse_pointing(factors):
                 return factors[:i] + [_FusedWhiteA(P, mid)] + factors[i + 3:]
             if (isinstance(mid, FilterLO) and mid.shape[0] == P.nrows
                     and mid._pix_dev.data_ptr() == P._pix_dev.data_ptr()):
-                return factors[:i] + [_FusedFilterA(P, mid)] + factors[i + 3:]
+                if mid.poly_order == 0:
+                    return factors[:i] + [_FusedFilterA(P, mid)] + factors[i + 3:]
+                if _FusedPolyFilterA.supported(P, mid):
+                    return factors[:i] + [_FusedPolyFilterA(P, mid)] + factors[i + 3:]
     return None
 
 
@@ -634,6 +705,46 @@ class BlockDiagonalPreconditionerLO(_PixelBlockLO):
         y = torch.empty_like(x)
         dv.call("cm2_bd_apply", dv.ptr(self._inv_dev), self._n, self.pol, dv.ptr(x), dv.ptr(y), _stream())
         return y
+
+
+class GroundFilterLO(lp.LinearOperator):
+    """Ground-template filter I - G (G^T G)^-1 G^T -- interfaces/linearoperators.py:24-61.
+
+    ``GroundFilterLO(ground)``: ``ground[t]`` = azimuth bin of sample t (-1 = flagged).  Attributes
+    ``nbins, n, Pg`` as in the reference; ``mult`` is two kernels (bin sums by the run-aggregating
+    pol-1 scatter, then the subtraction) instead of the three-operator chain ``G*invGtG*G.T``.
+    """
+
+    def counts_in_groundbins(self, g):                    # :26-46
+        gd = g if (isinstance(g, torch.Tensor) and g.is_cuda and g.dtype == torch.int32) else dv.pix_to_dev(g)
+        hits = torch.empty(max(self.nbins, 1), dtype=torch.int64, device=gd.device)
+        dv.call("cm2_hits_i64", dv.ptr(gd), gd.numel(), self.nbins, dv.ptr(hits), _stream())
+        self._hits_dev = hits
+        return dv.to_host(hits[:self.nbins]).astype(np.float64)
+
+    def mult(self, v):                                    # :48-49
+        out = torch.empty_like(v)
+        dv.call("cm2_ground_filter_apply", dv.ptr(self._g_dev), self.n, self.nbins, dv.ptr(self._hits_dev),
+                dv.ptr(v), dv.ptr(self._bins), dv.ptr(out), _stream())
+        return out
+
+    def __init__(self, ground):                           # :51-61
+        dv.require_cuda()
+        self.n = len(ground)
+        self._g_dev = dv.pix_to_dev(ground)
+        if isinstance(ground, torch.Tensor):
+            self.nbins = int(ground.max().item()) + 1 if self.n else 0
+        else:
+            self.nbins = int(np.max(ground)) + 1 if self.n else 0
+        self.nbins = max(self.nbins, 0)
+        counts = self.counts_in_groundbins(self._g_dev)
+        self._bins = dv.empty_f64(max(self.nbins, 1))
+        G = SparseLO(self.nbins, self.n, self._g_dev)
+        G.counts = counts
+        invGtG = BlockDiagonalPreconditionerLO(G, self.nbins)
+        self.Pg = (G * invGtG * G.T)
+        super(GroundFilterLO, self).__init__(nargin=self.n, nargout=self.n, matvec=self.mult,
+                                             symmetric=True, device=True)
 
 
 class InverseLO(lp.LinearOperator):

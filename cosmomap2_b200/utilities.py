@@ -147,3 +147,29 @@ def system_setup(nt, npix, nb, rng=None):
     phi = angles_gen(theta0, nt)
     t, diag = noise_val(nb, 2, rng)
     return d, pairs, phi, t, diag
+
+
+def reorganize_map(mapin, obspix, npix, nside, pol, fname=None):
+    """utilities/healpy_functions.py:50-105 -- from the interleaved solution over the observed pixels
+    to ``pol`` full-sky HEALPix arrays (12 nside^2 values each, zero where unobserved).  NumPy in ->
+    list of NumPy arrays (as the reference); CUDA tensor in -> list of CUDA tensors.  Writing FITS
+    files (``fname``) needs healpy, which is not part of this package."""
+    if pol not in (1, 2, 3):
+        raise RuntimeError("No valid polarization key set!\t=>\tpol=%d" % pol)
+    if fname is not None:
+        raise NotImplementedError("writing HEALPix FITS files needs healpy; pass fname=None")
+    dv.require_cuda()
+    hnpix = 12 * int(nside) * int(nside)
+    on_dev = isinstance(mapin, torch.Tensor)
+    m = dv.to_dev_f64(mapin)
+    npix = int(npix)
+    if m.numel() != pol * npix or len(obspix) != npix:
+        raise ValueError("mapin must hold pol*npix values and obspix npix pixels")
+    obs = dv.to_dev(obspix, torch.int64)
+    if npix and (int(obs.min().item()) < 0 or int(obs.max().item()) >= hnpix):
+        raise IndexError("obspix outside the nside=%d HEALPix range" % nside)
+    out = torch.empty(pol * hnpix, dtype=torch.float64, device=m.device)
+    dv.call("cm2_reorganize_map", dv.ptr(m), dv.ptr(obs), npix, pol, hnpix, dv.ptr(out),
+            torch.cuda.current_stream().cuda_stream)
+    parts = [out[k * hnpix:(k + 1) * hnpix] for k in range(pol)]
+    return parts if on_dev else [dv.to_host(p) for p in parts]

@@ -231,6 +231,43 @@ int cm2_pcg_bd_update(const double *bd_inv, int64_t npix, int pol, const double 
 int cm2_pcg_bd_iter(const double *bd_inv, int64_t npix, int pol, double *p, const double *q,
                     double *x, double *r, double *z, double *scal, cm2_stream_t stream);
 
+/* ---- (f) next rows: the other time-domain filters and the map output step ----------------------
+ * Subscan filter of polynomial order 0..cm2_filter_poly_max_order(), one CTA per subscan with the
+ * subscan staged in shared memory (d and pix read once, out written once; 20 B/sample).
+ *   poly_order = 0: FilterLO.mult (linearoperators.py:129-168), same result as
+ *                   cm2_filter_offset_apply: mean over samples with pix != -1, subtracted from every
+ *                   sample of the subscan; subscans without unflagged samples and the gaps stay 0.
+ *   poly_order > 0: FilterLO.polyfilter (:170-204): unflagged = pix >= 0; subscans with
+ *                   <= poly_order unflagged samples stay 0; without flags p = sum_k (b_k.d) b_k with
+ *                   b_k = L_k(x)/||L_k(x)||, x = linspace(-1,1,len) (get_legendre_polynomials,
+ *                   utilities/linear_algebra_funcs.py:47-59); with flags the least-squares
+ *                   polynomial over the unflagged samples (the reference's QR, :190-194);
+ *                   out = d - p on unflagged samples, 0 on flagged ones.
+ * max_seg_len = longest subscan (sizes the shared-memory window); sorted != 0 promises
+ * seg_start[k] >= seg_end[k-1] for all k (then no memset of `out` is issued). */
+int cm2_filter_poly_max_order(void);
+int cm2_filter_poly_apply(const int32_t *pix, const int64_t *seg_start, const int64_t *seg_end,
+                          int64_t nseg, int64_t max_seg_len, int poly_order, int sorted,
+                          const double *d, double *out, int64_t nt, cm2_stream_t stream);
+/* fused y = P^T F_K P x for the Legendre filter of order 1..cm2_amatvec_filter_poly_max_order()
+ * (the composition at src/test_M2_precond_onto_real_data.py:37-41), no TOD temporary; segments as
+ * above, flags taken from pix.  CM2_ERR_UNSUPPORTED if the longest subscan exceeds the
+ * shared-memory window (~16 000 samples) or the order is out of range. */
+int cm2_amatvec_filter_poly_max_order(void);
+int cm2_amatvec_filter_poly(const int32_t *pix, const double *cos2phi, const double *sin2phi,
+                            int64_t nt, int pol, const int64_t *seg_start, const int64_t *seg_end,
+                            int64_t nseg, int64_t max_seg_len, int poly_order, const double *x,
+                            double *y, int64_t npix, cm2_stream_t stream);
+/* GroundFilterLO.mult (linearoperators.py:24-61): out = v - G (G^T G)^-1 G^T v, G = pol-1 pointing
+ * onto ground bins (ground[t] in [0,nbins), -1 = flagged), (G^T G)^-1 = 1/hits where hits > 0
+ * (counts_in_groundbins :26-46 -> cm2_hits_i64).  bins[nbins] is scratch (receives G^T v). */
+int cm2_ground_filter_apply(const int32_t *ground, int64_t nt, int64_t nbins, const int64_t *hits,
+                            const double *v, double *bins, double *out, cm2_stream_t stream);
+/* reorganize_map (utilities/healpy_functions.py:50-105): out[k][obspix[p]] = map[pol*p + k] for
+ * k < pol, zero elsewhere; out is pol arrays of healpix_npix = 12 nside^2 values, back to back. */
+int cm2_reorganize_map(const double *map, const int64_t *obspix, int64_t npix, int pol,
+                       int64_t healpix_npix, double *out, cm2_stream_t stream);
+
 /* ---- (e) multi-GPU: map-domain all-reduce over NVLink peer memory ------------------------------
  * One process per GPU.  send/recv/signal tables are HOST arrays of `world` DEVICE pointers (entry g
  * = rank g's buffer mapped into this process through CUDA IPC; signal buffers are

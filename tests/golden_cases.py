@@ -224,4 +224,4 @@ def check_next_rows(impl, orders=(1, 2, 3)):
     nt = len(g["l_d"])
     for order in orders:
         F = impl.FilterLO(nt, [subs, tst], nsamples, nbolos, g["l_pix"].copy(), poly_order=order, npool=1)
-        close(F * g["l_d"], g["l_Fd_order%d" % order], rtol=1e-9, what="Legendre filter order %d" % order)
+        close(F * g["l_d"], g["l_Fd_order%d" % order], what="Legendre filter order %d" % order)

@@ -62,6 +62,29 @@ def main():
     t = timeit(lambda: P.T._apply(d)); out["Pt_ms"] = t; out["Pt_GBs"] = gb((bpp + 8) * nt + 8 * n, t)
     t = timeit(lambda: N._apply(d)); out["Nwhite_ms"] = t; out["Nwhite_GBs"] = gb(16 * nt, t)
     t = timeit(lambda: F._apply(d)); out["F_ms"] = t; out["F_GBs"] = gb(20 * nt, t)
+    # Legendre subscan filter (standalone and fused into the A-matvec), ground filter
+    from cosmomap2_b200 import linearoperators as lo
+    lo.FILTER_STAGED = False
+    t = timeit(lambda: F._apply(d)); out["F_first_kernel_ms"] = t; out["F_first_kernel_GBs"] = gb(20 * nt, t)
+    lo.FILTER_STAGED = True
+    pixf = np.array(sc.pix, copy=True)
+    pixf[np.random.default_rng(4).random(nt) < 0.01] = -1
+    for order in (1, 3):
+        Fk = cm.FilterLO(nt, [sc.sub_len, sc.sub_start], sc.ns, sc.ndet, sc.pix, poly_order=order)
+        t = timeit(lambda: Fk._apply(d)); out["F_leg%d_ms" % order] = t; out["F_leg%d_GBs" % order] = gb(20 * nt, t)
+        Ff = cm.FilterLO(nt, [sc.sub_len, sc.sub_start], sc.ns, sc.ndet, pixf, poly_order=order)
+        t = timeit(lambda: Ff._apply(d)); out["F_leg%d_flagged_ms" % order] = t
+        out["F_leg%d_flagged_GBs" % order] = gb(20 * nt, t)
+        AFk = P.T * Fk * P
+        t = timeit(lambda: AFk._apply(x)); out["amatvec_leg%d_ms" % order] = t
+        out["amatvec_leg%d_GBs" % order] = gb(bpp * nt + 16 * n, t)
+    del pixf, Ff
+    ground = ((np.arange(nt, dtype=np.int64) % sc.ns) // 50) % 400
+    ground[np.random.default_rng(5).random(nt) < 0.01] = -1
+    Gf = cm.GroundFilterLO(ground)
+    del ground
+    t = timeit(lambda: Gf._apply(d)); out["ground_ms"] = t; out["ground_GBs"] = gb(32 * nt, t)
+    del Gf
     t = timeit(lambda: Mbd._apply(x)); out["Mbd_ms"] = t; out["Mbd_GBs"] = gb(48 * npix + 16 * n, t)
     t = timeit(lambda: pts._moments(npix)); out["moments_ms"] = t
     bands = synthetic.toeplitz_bands(64, 64)
