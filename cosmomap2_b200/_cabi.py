@@ -53,6 +53,7 @@ SIGNATURES = {
     "cm2_filter_seg_mean": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
     "cm2_amatvec_filter_mu": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "cm2_filter_poly_max_order": (_int, []),
+    "cm2_filter_poly_set_tma": (_int, [_int]),
     "cm2_filter_poly_apply": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _int, _vp, _vp, _i64, _vp]),
     "cm2_amatvec_filter_poly_max_order": (_int, []),
     "cm2_amatvec_filter_poly": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _i64, _i64, _int, _vp, _vp, _i64, _vp]),
@@ -80,7 +81,7 @@ SIGNATURES = {
 # entry points that return a size/count rather than a status
 _NOT_STATUS = {"cm2_version", "cm2_last_error", "cm2_launch_count", "cm2_scan_scratch_bytes",
                "cm2_toeplitz_scratch_bytes", "cm2_defl_work_doubles", "cm2_allreduce_p2p_signal_bytes",
-               "cm2_toeplitz_fft_points", "cm2_toeplitz_fft_scratch_bytes", "cm2_filter_poly_max_order",
+               "cm2_toeplitz_fft_points", "cm2_toeplitz_fft_scratch_bytes", "cm2_filter_poly_max_order", "cm2_filter_poly_set_tma",
                "cm2_amatvec_filter_poly_max_order"}
 
 

@@ -17,9 +17,48 @@
 namespace cm2 {
 
 constexpr int FB = 256;          // threads per CTA
-constexpr int FW = FB / 32;      // warps per CTA
 constexpr int FP_MAXNK = 8;      // poly_order <= 7
 
+// ---- mbarrier + 1-D bulk copy (TMA engine, UBLKCP) ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    uint32_t spins = 0;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (!done && ++spins > (1u << 24)) __trap();      // a lost copy becomes an error, never a hang
+    } while (!done);
+}
+
+// Shared-memory scratch of one CTA for filter_segment
+template <int NK, bool OFFSET, int NT>
+struct FilterScratch {
+    static constexpr int NG = OFFSET ? 0 : NK * (NK + 1) / 2;
+    static constexpr int NR = NK + NG;
+    double red[(NT / 32) * NR > 32 ? (NT / 32) * NR : 32];
+    double tot[NR];
+    double coef[NK];
+    int cnt, jmin, jmax, skip, refine;
+};
+
+// One subscan [a, a+len) by the NT threads of a CTA.  getd(j) / getf(j) return sample j of the subscan
+// and whether it is unflagged (from shared memory, or global memory beyond the staged window).
 // NK = poly_order + 1.  OFFSET (NK == 1): the reference's poly_order = 0 path, where the mean over
 // the unflagged (pix != -1) samples is subtracted from EVERY sample of the subscan (:165).
 // Otherwise the Legendre path: unflagged = pix >= 0 (:174); a subscan with <= poly_order unflagged
@@ -28,176 +67,270 @@ constexpr int FP_MAXNK = 8;      // poly_order <= 7
 // basis is re-orthonormalised by QR on the unflagged rows (:190-194), i.e. p is the least-squares
 // polynomial of degree <= poly_order -- computed here from the Gram matrix in the Legendre basis of
 // the interval spanned by the unflagged samples (same span, well conditioned); flagged samples -> 0.
-// fill != 0: every output sample is written by this kernel (segments sorted, non-overlapping).
-// fill == 0: the caller zero-filled `out`; only what the reference assigns is written.
+// fill != 0: every sample of the subscan is written (zeros where the reference leaves the
+// zero-initialised output untouched); fill == 0: only what the reference assigns is written.
+// Ends with a CTA barrier (the staged window may be reused afterwards).
+template <int NK, bool OFFSET, int NT, class GetD, class GetF>
+__device__ __forceinline__ void filter_segment(GetD getd, GetF getf, int64_t a, int64_t len, double *__restrict__ out,
+                                               int fill, FilterScratch<NK, OFFSET, NT> &sh) {
+    constexpr int NR = FilterScratch<NK, OFFSET, NT>::NR;
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) { sh.cnt = 0; sh.jmin = INT_MAX; sh.jmax = -1; }
+    __syncthreads();
+    // ---- pass 1: count, first / last unflagged sample, (offset path) sum ------------------------
+    int cnt = 0, jmin = INT_MAX, jmax = -1;
+    double sum = 0.0;
+    for (int64_t j = tid; j < len; j += NT) {
+        if (getf(j)) {
+            ++cnt;
+            if (jmin == INT_MAX) jmin = (int)j;
+            jmax = (int)j;
+            if (OFFSET) sum += getd(j);
+        }
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    jmin = __reduce_min_sync(0xffffffffu, jmin);
+    jmax = __reduce_max_sync(0xffffffffu, jmax);
+    if (lane == 0 && cnt > 0) { atomicAdd(&sh.cnt, cnt); atomicMin(&sh.jmin, jmin); atomicMax(&sh.jmax, jmax); }
+    if constexpr (OFFSET) {
+        const double tsum = block_sum(sum, sh.red);      // two barriers inside: sh.cnt is complete after it
+        if (tid == 0) {
+            const double mean = tsum / (double)sh.cnt;    // 0/0 = NaN like the reference (:154, 163)
+            sh.skip = (sh.cnt == 0) || isinf(mean) || isnan(mean);
+            sh.coef[0] = mean;
+        }
+        __syncthreads();
+        const double mu = sh.coef[0];
+        if (!sh.skip) {
+            for (int64_t j = tid; j < len; j += NT) __stcs(out + a + j, getd(j) - mu);
+        } else if (fill) {
+            for (int64_t j = tid; j < len; j += NT) __stcs(out + a + j, 0.0);
+        }
+    } else {
+        __syncthreads();
+        const int n = sh.cnt;
+        if (n <= NK - 1) {                                // block-uniform: too few samples (:185-187)
+            if (fill)
+                for (int64_t j = tid; j < len; j += NT) __stcs(out + a + j, 0.0);
+        } else {
+            const bool full = (int64_t)n == len;
+            const int j0 = full ? 0 : sh.jmin;
+            const int j1 = full ? (int)(len - 1) : sh.jmax;
+            const double step = 2.0 / (double)(j1 - j0);
+            // ---- pass 2: S_k = sum L_k d, G_kl = sum L_k L_l over the unflagged samples ------------
+            double acc[NR];
+#pragma unroll
+            for (int i = 0; i < NR; ++i) acc[i] = 0.0;
+            for (int64_t j = tid; j < len; j += NT) {
+                if (!getf(j)) continue;
+                const double v = getd(j);
+                double L[NK];
+                legendre<NK>(fma((double)((int)j - j0), step, -1.0), L);
+                int q = NK;
+#pragma unroll
+                for (int r = 0; r < NK; ++r) {
+                    acc[r] = fma(L[r], v, acc[r]);
+#pragma unroll
+                    for (int c = r; c < NK; ++c) { acc[q] = fma(L[r], L[c], acc[q]); ++q; }
+                }
+            }
+            block_sum_n<NR, NW>(acc, sh.red, sh.tot);
+            if (tid == 0) {
+                sh.refine = 0;
+                if (full) {
+                    int q = NK;
+                    for (int r = 0; r < NK; ++r) {
+                        sh.coef[r] = sh.tot[q] > 0.0 ? sh.tot[r] / sh.tot[q] : 0.0;   // (b_k . d) / ||L_k||^2
+                        q += NK - r;
+                    }
+                } else {
+                    double c[NK];
+                    sh.refine = filter_refine_steps(gram_solve<NK>(sh.tot + NK, sh.tot, c));
+                    for (int r = 0; r < NK; ++r) sh.coef[r] = c[r];
+                }
+            }
+            __syncthreads();
+            const int nref = sh.refine;                   // block-uniform, 0 unless ill-conditioned
+            for (int it = 0; it < nref; ++it) {
+                double c[NK], racc[NK];
+#pragma unroll
+                for (int r = 0; r < NK; ++r) { c[r] = sh.coef[r]; racc[r] = 0.0; }
+                for (int64_t j = tid; j < len; j += NT) {
+                    if (!getf(j)) continue;
+                    double L[NK];
+                    legendre<NK>(fma((double)((int)j - j0), step, -1.0), L);
+                    double res = getd(j);
+#pragma unroll
+                    for (int r = 0; r < NK; ++r) res = fma(-c[r], L[r], res);
+#pragma unroll
+                    for (int r = 0; r < NK; ++r) racc[r] = fma(L[r], res, racc[r]);
+                }
+                block_sum_n<NK, NW>(racc, sh.red, sh.tot);    // tot[0..NK) = L^T (d - L c); the Gram matrix stays
+                if (tid == 0) {
+                    double dc[NK];
+                    gram_solve<NK>(sh.tot + NK, sh.tot, dc);
+                    for (int r = 0; r < NK; ++r) sh.coef[r] += dc[r];
+                }
+                __syncthreads();
+            }
+            // ---- pass 3: subtract and write ----------------------------------------------------------
+            double c[NK];
+#pragma unroll
+            for (int r = 0; r < NK; ++r) c[r] = sh.coef[r];
+            for (int64_t j = tid; j < len; j += NT) {
+                if (getf(j)) {
+                    double L[NK];
+                    legendre<NK>(fma((double)((int)j - j0), step, -1.0), L);
+                    double p = 0.0;
+#pragma unroll
+                    for (int r = 0; r < NK; ++r) p = fma(c[r], L[r], p);
+                    __stcs(out + a + j, getd(j) - p);
+                } else if (fill) {
+                    __stcs(out + a + j, 0.0);
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// zero-fill of the gap in front of subscan k (and behind the last one): sorted tables only
+template <int NT>
+__device__ __forceinline__ void fill_gap(const int64_t *__restrict__ seg_end, int64_t k, int64_t nseg, int64_t a, int64_t b,
+                                         int64_t nt, double *__restrict__ out) {
+    const int64_t g0 = k == 0 ? 0 : seg_end[k - 1];
+    for (int64_t t = g0 + threadIdx.x; t < a; t += NT) __stcs(out + t, 0.0);
+    if (k == nseg - 1)
+        for (int64_t t = b + threadIdx.x; t < nt; t += NT) __stcs(out + t, 0.0);
+}
+
+// ---- variant A: one CTA per subscan, staged by ordinary loads (any subscan length) --------------------
 template <int NK, bool OFFSET>
 __global__ void __launch_bounds__(FB) k_filter_poly(const int32_t *__restrict__ pix, const int64_t *__restrict__ seg_start,
                                                     const int64_t *__restrict__ seg_end, int64_t nseg,
                                                     const double *__restrict__ d, double *__restrict__ out, int64_t nt,
                                                     int cap, int fill) {
-    constexpr int NG = OFFSET ? 0 : NK * (NK + 1) / 2;
-    constexpr int NR = NK + NG;
     extern __shared__ double sm[];
     double *sd = sm;                                     // cap staged samples
     uint8_t *sf = reinterpret_cast<uint8_t *>(sm + cap);   // cap flags (1 = unflagged)
-    __shared__ double red[FW * NR];
-    __shared__ double tot[NR];
-    __shared__ double coef[NK];
-    __shared__ int s_cnt, s_jmin, s_jmax, s_skip, s_refine;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
+    __shared__ FilterScratch<NK, OFFSET, FB> sh;
     for (int64_t k = blockIdx.x; k < nseg; k += gridDim.x) {
         const int64_t a = seg_start[k], b = seg_end[k];
         const int64_t len = b - a;
-        if (fill) {          // gap in front of this subscan (and behind the last one)
-            const int64_t g0 = k == 0 ? 0 : seg_end[k - 1];
-            for (int64_t t = g0 + tid; t < a; t += FB) __stcs(out + t, 0.0);
-            if (k == nseg - 1)
-                for (int64_t t = b + tid; t < nt; t += FB) __stcs(out + t, 0.0);
-        }
-        if (tid == 0) { s_cnt = 0; s_jmin = INT_MAX; s_jmax = -1; }
-        __syncthreads();
-        // ---- pass 1: stage, count, (offset path) sum ------------------------------------------
-        int cnt = 0, jmin = INT_MAX, jmax = -1;
-        double sum = 0.0;
-        for (int64_t j = tid; j < len; j += FB) {
+        if (fill) fill_gap<FB>(seg_end, k, nseg, a, b, nt, out);
+        const int64_t nst = len < cap ? len : cap;
+        for (int64_t j = threadIdx.x; j < nst; j += FB) {
             const int p = __ldcs(pix + a + j);
-            const double v = __ldcs(d + a + j);
-            const bool f = OFFSET ? (p != -1) : (p >= 0);
-            if (j < cap) { sd[j] = v; sf[j] = f; }
-            if (f) {
-                ++cnt;
-                if (jmin == INT_MAX) jmin = (int)j;
-                jmax = (int)j;
-                if (OFFSET) sum += v;
-            }
-        }
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        jmin = __reduce_min_sync(0xffffffffu, jmin);
-        jmax = __reduce_max_sync(0xffffffffu, jmax);
-        if (lane == 0 && cnt > 0) { atomicAdd(&s_cnt, cnt); atomicMin(&s_jmin, jmin); atomicMax(&s_jmax, jmax); }
-        if constexpr (OFFSET) {
-            const double tsum = block_sum(sum, red);     // two barriers inside: s_cnt is complete after it
-            if (tid == 0) {
-                const double mean = tsum / (double)s_cnt;     // 0/0 = NaN like the reference (:154, 163)
-                s_skip = (s_cnt == 0) || isinf(mean) || isnan(mean);
-                coef[0] = mean;
-            }
-            __syncthreads();
-        } else {
-            __syncthreads();
-            const int n = s_cnt;
-            const bool skip = n <= NK - 1;
-            if (!skip) {
-                const bool full = (int64_t)n == len;
-                const int j0 = full ? 0 : s_jmin;
-                const int j1 = full ? (int)(len - 1) : s_jmax;
-                const double step = 2.0 / (double)(j1 - j0);
-                // ---- pass 2: S_k = sum L_k d, G_kl = sum L_k L_l over the unflagged samples -----
-                double acc[NR];
-#pragma unroll
-                for (int i = 0; i < NR; ++i) acc[i] = 0.0;
-                for (int64_t j = tid; j < len; j += FB) {
-                    const bool f = j < cap ? (sf[j] != 0) : (pix[a + j] >= 0);
-                    if (!f) continue;
-                    const double v = j < cap ? sd[j] : d[a + j];
-                    double L[NK];
-                    legendre<NK>(fma((double)((int)j - j0), step, -1.0), L);
-                    int q = NK;
-#pragma unroll
-                    for (int r = 0; r < NK; ++r) {
-                        acc[r] = fma(L[r], v, acc[r]);
-#pragma unroll
-                        for (int c = r; c < NK; ++c) { acc[q] = fma(L[r], L[c], acc[q]); ++q; }
-                    }
-                }
-                block_sum_n<NR, FW>(acc, red, tot);
-                if (tid == 0) {
-                    s_refine = 0;
-                    if (full) {
-                        int q = NK;
-                        for (int r = 0; r < NK; ++r) {
-                            coef[r] = tot[q] > 0.0 ? tot[r] / tot[q] : 0.0;   // (b_k . d) / ||L_k||^2
-                            q += NK - r;
-                        }
-                    } else {
-                        double c[NK];
-                        s_refine = filter_refine_steps(gram_solve<NK>(tot + NK, tot, c));
-                        for (int r = 0; r < NK; ++r) coef[r] = c[r];
-                    }
-                }
-                __syncthreads();
-                const int nref = s_refine;                   // block-uniform, 0 unless ill-conditioned
-                for (int it = 0; it < nref; ++it) {
-                    double c[NK], racc[NK];
-#pragma unroll
-                    for (int r = 0; r < NK; ++r) { c[r] = coef[r]; racc[r] = 0.0; }
-                    for (int64_t j = tid; j < len; j += FB) {
-                        const bool f = j < cap ? (sf[j] != 0) : (pix[a + j] >= 0);
-                        if (!f) continue;
-                        double L[NK];
-                        legendre<NK>(fma((double)((int)j - j0), step, -1.0), L);
-                        double res = j < cap ? sd[j] : d[a + j];
-#pragma unroll
-                        for (int r = 0; r < NK; ++r) res = fma(-c[r], L[r], res);
-#pragma unroll
-                        for (int r = 0; r < NK; ++r) racc[r] = fma(L[r], res, racc[r]);
-                    }
-                    block_sum_n<NK, FW>(racc, red, tot);      // tot[0..NK) = L^T (d - L c); the Gram matrix stays
-                    if (tid == 0) {
-                        double dc[NK];
-                        gram_solve<NK>(tot + NK, tot, dc);
-                        for (int r = 0; r < NK; ++r) coef[r] += dc[r];
-                    }
-                    __syncthreads();
-                }
-            }
-            if (tid == 0) s_skip = skip;
-            __syncthreads();
-        }
-        // ---- pass 3: subtract and write --------------------------------------------------------
-        const bool skip = s_skip != 0;
-        if (OFFSET) {
-            const double mu = coef[0];
-            if (!skip) {
-                for (int64_t j = tid; j < len; j += FB) __stcs(out + a + j, (j < cap ? sd[j] : d[a + j]) - mu);
-            } else if (fill) {
-                for (int64_t j = tid; j < len; j += FB) __stcs(out + a + j, 0.0);
-            }
-        } else {
-            if (!skip) {
-                const bool full = (int64_t)s_cnt == len;
-                const int j0 = full ? 0 : s_jmin;
-                const int j1 = full ? (int)(len - 1) : s_jmax;
-                const double step = 2.0 / (double)(j1 - j0);
-                double c[NK];
-#pragma unroll
-                for (int r = 0; r < NK; ++r) c[r] = coef[r];
-                for (int64_t j = tid; j < len; j += FB) {
-                    const bool f = j < cap ? (sf[j] != 0) : (pix[a + j] >= 0);
-                    if (f) {
-                        const double v = j < cap ? sd[j] : d[a + j];
-                        double L[NK];
-                        legendre<NK>(fma((double)((int)j - j0), step, -1.0), L);
-                        double p = 0.0;
-#pragma unroll
-                        for (int r = 0; r < NK; ++r) p = fma(c[r], L[r], p);
-                        __stcs(out + a + j, v - p);
-                    } else if (fill) {
-                        __stcs(out + a + j, 0.0);
-                    }
-                }
-            } else if (fill) {
-                for (int64_t j = tid; j < len; j += FB) __stcs(out + a + j, 0.0);
-            }
+            sd[j] = __ldcs(d + a + j);
+            sf[j] = OFFSET ? (p != -1) : (p >= 0);
         }
         __syncthreads();
+        auto getd = [&](int64_t j) { return j < cap ? sd[j] : d[a + j]; };
+        auto getf = [&](int64_t j) {
+            if (j < cap) return sf[j] != 0;
+            const int p = pix[a + j];
+            return OFFSET ? (p != -1) : (p >= 0);
+        };
+        filter_segment<NK, OFFSET, FB>(getd, getf, a, len, out, fill, sh);
+    }
+}
+
+// ---- variant B: persistent CTAs, subscans streamed through a ring of shared-memory stages by the TMA
+// engine (cp.async.bulk + mbarrier): while the CTA reduces and writes subscan i, the copies of
+// subscans i+1 .. i+nstage-1 are in flight, so DRAM latency is never exposed.  The copied window is
+// the 4-sample-aligned hull [a & ~3, min(roundup4(b), nt & ~3)) of d (8 B) and pix (4 B); the <= 3
+// samples of the last subscan beyond nt & ~3 are read directly.
+constexpr int TB = 512;
+constexpr int TMA_MAX_STAGES = 4;
+
+template <int NK, bool OFFSET>
+__global__ void __launch_bounds__(TB, 1) k_filter_poly_tma(const int32_t *__restrict__ pix, const int64_t *__restrict__ seg_start,
+                                                           const int64_t *__restrict__ seg_end, int64_t nseg,
+                                                           const double *__restrict__ d, double *__restrict__ out, int64_t nt,
+                                                           int capw, int nstage, int fill) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ FilterScratch<NK, OFFSET, TB> sh;
+    __shared__ __align__(8) uint64_t full[TMA_MAX_STAGES];
+    const size_t stage_bytes = (size_t)capw * 12;
+    const int64_t nt4 = nt & ~(int64_t)3;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nstage; ++s) mbar_init(&full[s], 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    if ((int64_t)blockIdx.x >= nseg) return;
+    const int64_t nmine = (nseg - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    auto issue = [&](int64_t i) {                          // thread 0: start the copies of my i-th subscan
+        const int64_t k = blockIdx.x + i * gridDim.x;
+        const int s = (int)(i % nstage);
+        const int64_t a = seg_start[k], b = seg_end[k];
+        const int64_t a4 = a & ~(int64_t)3;
+        int64_t e4 = (b + 3) & ~(int64_t)3;
+        if (e4 > nt4) e4 = nt4;
+        const int64_t n = e4 > a4 ? e4 - a4 : 0;           // multiple of 4
+        unsigned char *base = smraw + s * stage_bytes;
+        mbar_arrive_expect_tx(&full[s], (uint32_t)(n * 12));
+        if (n > 0) {
+            bulk_g2s(base, d + a4, (uint32_t)(n * 8), &full[s]);
+            bulk_g2s(base + (size_t)capw * 8, pix + a4, (uint32_t)(n * 4), &full[s]);
+        }
+    };
+    if (threadIdx.x == 0)
+        for (int64_t i = 0; i < nstage - 1 && i < nmine; ++i) issue(i);
+    for (int64_t i = 0; i < nmine; ++i) {
+        const int64_t k = blockIdx.x + i * gridDim.x;
+        const int s = (int)(i % nstage);
+        // the stage refilled here was read during iteration i-1, which ended with a CTA barrier
+        if (threadIdx.x == 0 && i + nstage - 1 < nmine) issue(i + nstage - 1);
+        const int64_t a = seg_start[k], b = seg_end[k];
+        const int64_t len = b - a;
+        if (fill) fill_gap<TB>(seg_end, k, nseg, a, b, nt, out);
+        const int64_t a4 = a & ~(int64_t)3;
+        int64_t e4 = (b + 3) & ~(int64_t)3;
+        if (e4 > nt4) e4 = nt4;
+        const double *sd = reinterpret_cast<const double *>(smraw + s * stage_bytes) + (a - a4);
+        const int *sp = reinterpret_cast<const int *>(smraw + s * stage_bytes + (size_t)capw * 8) + (a - a4);
+        const int64_t nsm = e4 - a;                        // samples of the subscan present in the stage
+        mbar_wait(&full[s], (uint32_t)((i / nstage) & 1));
+        auto getd = [&](int64_t j) { return j < nsm ? sd[j] : d[a + j]; };
+        auto getf = [&](int64_t j) {
+            const int p = j < nsm ? sp[j] : pix[a + j];
+            return OFFSET ? (p != -1) : (p >= 0);
+        };
+        filter_segment<NK, OFFSET, TB>(getd, getf, a, len, out, fill, sh);
     }
 }
 
 template <int NK, bool OFFSET>
 static int launch_filter_poly(const int32_t *pix, const int64_t *seg_start, const int64_t *seg_end, int64_t nseg,
-                              const double *d, double *out, int64_t nt, int cap, int fill, cudaStream_t st) {
+                              int64_t max_seg_len, const double *d, double *out, int64_t nt, int fill, int use_tma,
+                              cudaStream_t st) {
+    // variant B when at least two stages of the longest subscan fit into 200 kB of shared memory
+    const int64_t capw = (max_seg_len + 8 + 3) / 4 * 4;
+    const int64_t budget = 200 * 1024;
+    int nstage = (int)(budget / (capw * 12));
+    if (nstage > TMA_MAX_STAGES) nstage = TMA_MAX_STAGES;
+    if (use_tma && nstage >= 2 && aligned(d, 16) && aligned(pix, 16)) {
+        // no more stages than subscans per CTA make use of
+        const int64_t per_cta = (nseg + sm_count() - 1) / sm_count();
+        if (nstage > per_cta + 1) nstage = (int)(per_cta + 1);
+        if (nstage < 2) nstage = 2;
+        const size_t smem = (size_t)capw * 12 * nstage;
+        auto kern = k_filter_poly_tma<NK, OFFSET>;
+        CM2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = sm_count();
+        if (nseg < grid) grid = (int)nseg;
+        kern<<<grid, TB, smem, st>>>(pix, seg_start, seg_end, nseg, d, out, nt, (int)capw, nstage, fill);
+        CM2_LAUNCHED();
+        return CM2_OK;
+    }
+    // variant A: shared-memory window of the longest subscan, up to 24 000 samples (216 kB); longer
+    // subscans re-read their tail from global memory (L2)
+    int64_t cap64 = (max_seg_len + 15) / 16 * 16;
+    if (cap64 > 24000) cap64 = 24000;
+    if (cap64 < 16) cap64 = 16;
+    const int cap = (int)cap64;
     const size_t smem = (size_t)cap * 9;
     auto kern = k_filter_poly<NK, OFFSET>;
     CM2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -261,6 +394,8 @@ static int grid_fp(int64_t blocks, int per_sm = 8) {
 
 using namespace cm2;
 
+static int g_filter_tma = 1;
+
 extern "C" int cm2_filter_poly_max_order(void) { return FP_MAXNK - 1; }
 
 extern "C" int cm2_filter_poly_apply(const int32_t *pix, const int64_t *seg_start, const int64_t *seg_end, int64_t nseg,
@@ -275,22 +410,26 @@ extern "C" int cm2_filter_poly_apply(const int32_t *pix, const int64_t *seg_star
     const int fill = sorted && nseg > 0;
     if (nt > 0 && !fill) CM2_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)nt, st));
     if (nt == 0 || nseg == 0) return CM2_OK;
-    // shared-memory window: the longest subscan, up to 24 000 samples (216 kB); longer subscans
-    // re-read their tail from global memory (L2)
-    int64_t cap64 = (max_seg_len + 15) / 16 * 16;
-    if (cap64 > 24000) cap64 = 24000;
-    if (cap64 < 16) cap64 = 16;
-    const int cap = (int)cap64;
+    const int tma = g_filter_tma;
+#define CM2_FP(NKv, OFFv) launch_filter_poly<NKv, OFFv>(pix, seg_start, seg_end, nseg, max_seg_len, d, out, nt, fill, tma, st)
     switch (poly_order) {
-        case 0: return launch_filter_poly<1, true>(pix, seg_start, seg_end, nseg, d, out, nt, cap, fill, st);
-        case 1: return launch_filter_poly<2, false>(pix, seg_start, seg_end, nseg, d, out, nt, cap, fill, st);
-        case 2: return launch_filter_poly<3, false>(pix, seg_start, seg_end, nseg, d, out, nt, cap, fill, st);
-        case 3: return launch_filter_poly<4, false>(pix, seg_start, seg_end, nseg, d, out, nt, cap, fill, st);
-        case 4: return launch_filter_poly<5, false>(pix, seg_start, seg_end, nseg, d, out, nt, cap, fill, st);
-        case 5: return launch_filter_poly<6, false>(pix, seg_start, seg_end, nseg, d, out, nt, cap, fill, st);
-        case 6: return launch_filter_poly<7, false>(pix, seg_start, seg_end, nseg, d, out, nt, cap, fill, st);
-        default: return launch_filter_poly<8, false>(pix, seg_start, seg_end, nseg, d, out, nt, cap, fill, st);
+        case 0: return CM2_FP(1, true);
+        case 1: return CM2_FP(2, false);
+        case 2: return CM2_FP(3, false);
+        case 3: return CM2_FP(4, false);
+        case 4: return CM2_FP(5, false);
+        case 5: return CM2_FP(6, false);
+        case 6: return CM2_FP(7, false);
+        default: return CM2_FP(8, false);
     }
+#undef CM2_FP
+}
+
+/* development switch: 0 = always the ordinary-load variant (A), 1 = TMA-pipelined variant (B) when it fits */
+extern "C" int cm2_filter_poly_set_tma(int on) {
+    const int old = g_filter_tma;
+    g_filter_tma = on != 0;
+    return old;
 }
 
 extern "C" int cm2_ground_filter_apply(const int32_t *ground, int64_t nt, int64_t nbins, const int64_t *hits,

@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter(const int32_t *__restr
 //   pass 2: scatter-add of d - sum_k c_k L_k over the unflagged samples
 // cap = shared-memory window in samples (a multiple of TILE covering the longest subscan).
 template <int POL, int NK>
-__global__ void __launch_bounds__(BLOCK) k_amatvec_filter_poly(const int32_t *__restrict__ pix, const double *__restrict__ cs,
+__global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t *__restrict__ pix, const double *__restrict__ cs,
                                                                const double *__restrict__ sn, int64_t nt,
                                                                const int64_t *__restrict__ seg_start,
                                                                const int64_t *__restrict__ seg_end, int64_t nseg,

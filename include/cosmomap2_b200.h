@@ -246,6 +246,11 @@ int cm2_pcg_bd_iter(const double *bd_inv, int64_t npix, int pol, double *p, cons
  * max_seg_len = longest subscan (sizes the shared-memory window); sorted != 0 promises
  * seg_start[k] >= seg_end[k-1] for all k (then no memset of `out` is issued). */
 int cm2_filter_poly_max_order(void);
+/* Two variants exist: (A) one CTA per subscan staged by ordinary loads (any subscan length) and
+ * (B) persistent CTAs with the subscans streamed through a ring of shared-memory stages by the TMA
+ * engine (cp.async.bulk + mbarrier), used when two stages of the longest subscan fit (<= ~8 500
+ * samples).  cm2_filter_poly_set_tma(0) forces (A) (tests, measurements); returns the old setting. */
+int cm2_filter_poly_set_tma(int on);
 int cm2_filter_poly_apply(const int32_t *pix, const int64_t *seg_start, const int64_t *seg_end,
                           int64_t nseg, int64_t max_seg_len, int poly_order, int sorted,
                           const double *d, double *out, int64_t nt, cm2_stream_t stream);

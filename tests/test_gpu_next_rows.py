@@ -20,7 +20,17 @@ def cm():
     return cosmomap2_b200
 
 
-def test_golden_ground_and_legendre_filters(cm):
+@pytest.fixture(params=["tma", "ldg"])
+def variant(request, cm):
+    """Both variants of the subscan kernel: (B) subscans streamed through shared memory by the TMA
+    engine (the default when they fit) and (A) staged by ordinary loads."""
+    from cosmomap2_b200 import _cabi
+    old = _cabi.call("cm2_filter_poly_set_tma", 1 if request.param == "tma" else 0)
+    yield request.param
+    _cabi.call("cm2_filter_poly_set_tma", old)
+
+
+def test_golden_ground_and_legendre_filters(cm, variant):
     gc.check_next_rows(cm)
 
 
@@ -63,7 +73,7 @@ def _flag_patterns(rng, pix, starts, lens, order):
 
 
 @pytest.mark.parametrize("order", [0, 1, 2, 3, 4, 5, 6, 7])
-def test_subscan_filter_against_oracle(cm, order):
+def test_subscan_filter_against_oracle(cm, order, variant):
     import oracle
     rng = np.random.default_rng(100 + order)
     nsamples, nbolos = [6000, 4500], [3, 2]
@@ -95,7 +105,7 @@ def test_subscan_filter_against_oracle(cm, order):
         assert np.all(res[1][pix < 0] == 0.0)
 
 
-def test_offset_filter_staged_equals_first_kernel(cm):
+def test_offset_filter_staged_equals_first_kernel(cm, variant):
     """poly_order = 0 through the shared-memory-staged kernel == cm2_filter_offset_apply (bit for bit
     is not promised: the partial sums are grouped differently)."""
     from cosmomap2_b200 import linearoperators as lo
@@ -140,7 +150,7 @@ def test_filter_unsorted_table_and_long_subscans(cm):
         gc.close(Fr * d, ref, what="unsorted table, order %d" % order)
 
 
-def test_legendre_filter_properties(cm):
+def test_legendre_filter_properties(cm, variant):
     """Size-independent properties at a size the oracle would not finish quickly: with flags the
     filter is an exact projector on each subscan (idempotent; polynomials of degree <= order are
     annihilated); linear."""
