@@ -71,21 +71,24 @@ struct FilterScratch {
 // zero-initialised output untouched); fill == 0: only what the reference assigns is written.
 // Ends with a CTA barrier (the staged window may be reused afterwards).
 template <int NK, bool OFFSET, int NT, class GetD, class GetF>
-__device__ __forceinline__ void filter_segment(GetD getd, GetF getf, int64_t a, int64_t len, double *__restrict__ out,
+__device__ __forceinline__ void filter_segment(GetD getd, GetF getf, int64_t a, int64_t len64, double *__restrict__ out,
                                                int fill, FilterScratch<NK, OFFSET, NT> &sh) {
     constexpr int NR = FilterScratch<NK, OFFSET, NT>::NR;
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31;
+    const int len = len64 > 0 ? (int)len64 : 0;          // subscans are shorter than 2^31 samples (checked on the host)
+    double *__restrict__ oa = out + a;
     if (tid == 0) { sh.cnt = 0; sh.jmin = INT_MAX; sh.jmax = -1; }
     __syncthreads();
     // ---- pass 1: count, first / last unflagged sample, (offset path) sum ------------------------
     int cnt = 0, jmin = INT_MAX, jmax = -1;
     double sum = 0.0;
-    for (int64_t j = tid; j < len; j += NT) {
+#pragma unroll 4
+    for (int j = tid; j < len; j += NT) {
         if (getf(j)) {
             ++cnt;
-            if (jmin == INT_MAX) jmin = (int)j;
-            jmax = (int)j;
+            jmin = min(jmin, j);
+            jmax = j;
             if (OFFSET) sum += getd(j);
         }
     }
@@ -103,36 +106,61 @@ __device__ __forceinline__ void filter_segment(GetD getd, GetF getf, int64_t a, 
         __syncthreads();
         const double mu = sh.coef[0];
         if (!sh.skip) {
-            for (int64_t j = tid; j < len; j += NT) __stcs(out + a + j, getd(j) - mu);
+#pragma unroll 4
+            for (int j = tid; j < len; j += NT) __stcs(oa + j, getd(j) - mu);
         } else if (fill) {
-            for (int64_t j = tid; j < len; j += NT) __stcs(out + a + j, 0.0);
+            for (int j = tid; j < len; j += NT) __stcs(oa + j, 0.0);
         }
     } else {
         __syncthreads();
         const int n = sh.cnt;
         if (n <= NK - 1) {                                // block-uniform: too few samples (:185-187)
             if (fill)
-                for (int64_t j = tid; j < len; j += NT) __stcs(out + a + j, 0.0);
+                for (int j = tid; j < len; j += NT) __stcs(oa + j, 0.0);
         } else {
-            const bool full = (int64_t)n == len;
+            const bool full = n == len;
             const int j0 = full ? 0 : sh.jmin;
-            const int j1 = full ? (int)(len - 1) : sh.jmax;
+            const int j1 = full ? len - 1 : sh.jmax;
             const double step = 2.0 / (double)(j1 - j0);
-            // ---- pass 2: S_k = sum L_k d, G_kl = sum L_k L_l over the unflagged samples ------------
+            // x_j of this thread's m-th sample (j = tid + m NT): x0 + m dx, one fma instead of an int -> fp64
+            // conversion per sample
+            const double x0 = fma((double)(tid - j0), step, -1.0), dx = (double)NT * step;
+            // ---- pass 2: S_k = sum L_k d and the Gram matrix over the unflagged samples -------------
             double acc[NR];
 #pragma unroll
             for (int i = 0; i < NR; ++i) acc[i] = 0.0;
-            for (int64_t j = tid; j < len; j += NT) {
-                if (!getf(j)) continue;
-                const double v = getd(j);
-                double L[NK];
-                legendre<NK>(fma((double)((int)j - j0), step, -1.0), L);
-                int q = NK;
+            if (full) {                                  // no flag: only the diagonal ||L_k||^2 is needed
+                double m = 0.0;
+#pragma unroll 2
+                for (int j = tid; j < len; j += NT, m += 1.0) {
+                    const double v = getd(j);
+                    double L[NK];
+                    legendre<NK>(fma(m, dx, x0), L);
+                    int q = NK;
 #pragma unroll
-                for (int r = 0; r < NK; ++r) {
-                    acc[r] = fma(L[r], v, acc[r]);
+                    for (int r = 0; r < NK; ++r) {
+                        acc[r] = fma(L[r], v, acc[r]);
+                        acc[q] = fma(L[r], L[r], acc[q]);
+                        q += NK - r;
+                    }
+                }
+            } else {
+                double m = 0.0;
+#pragma unroll 2
+                for (int j = tid; j < len; j += NT, m += 1.0) {
+                    const bool f = getf(j);
+                    const double v = getd(j);
+                    double L[NK], Lw[NK];
+                    legendre<NK>(fma(m, dx, x0), L);
 #pragma unroll
-                    for (int c = r; c < NK; ++c) { acc[q] = fma(L[r], L[c], acc[q]); ++q; }
+                    for (int r = 0; r < NK; ++r) Lw[r] = f ? L[r] : 0.0;    // branch-free: flagged samples add 0
+                    int q = NK;
+#pragma unroll
+                    for (int r = 0; r < NK; ++r) {
+                        acc[r] = fma(Lw[r], v, acc[r]);
+#pragma unroll
+                        for (int c = r; c < NK; ++c) { acc[q] = fma(Lw[r], L[c], acc[q]); ++q; }
+                    }
                 }
             }
             block_sum_n<NR, NW>(acc, sh.red, sh.tot);
@@ -156,10 +184,11 @@ __device__ __forceinline__ void filter_segment(GetD getd, GetF getf, int64_t a, 
                 double c[NK], racc[NK];
 #pragma unroll
                 for (int r = 0; r < NK; ++r) { c[r] = sh.coef[r]; racc[r] = 0.0; }
-                for (int64_t j = tid; j < len; j += NT) {
+                double m = 0.0;
+                for (int j = tid; j < len; j += NT, m += 1.0) {
                     if (!getf(j)) continue;
                     double L[NK];
-                    legendre<NK>(fma((double)((int)j - j0), step, -1.0), L);
+                    legendre<NK>(fma(m, dx, x0), L);
                     double res = getd(j);
 #pragma unroll
                     for (int r = 0; r < NK; ++r) res = fma(-c[r], L[r], res);
@@ -178,17 +207,17 @@ __device__ __forceinline__ void filter_segment(GetD getd, GetF getf, int64_t a, 
             double c[NK];
 #pragma unroll
             for (int r = 0; r < NK; ++r) c[r] = sh.coef[r];
-            for (int64_t j = tid; j < len; j += NT) {
-                if (getf(j)) {
-                    double L[NK];
-                    legendre<NK>(fma((double)((int)j - j0), step, -1.0), L);
-                    double p = 0.0;
+            double m = 0.0;
+#pragma unroll 2
+            for (int j = tid; j < len; j += NT, m += 1.0) {
+                const bool f = full || getf(j);
+                double L[NK];
+                legendre<NK>(fma(m, dx, x0), L);
+                double p = 0.0;
 #pragma unroll
-                    for (int r = 0; r < NK; ++r) p = fma(c[r], L[r], p);
-                    __stcs(out + a + j, getd(j) - p);
-                } else if (fill) {
-                    __stcs(out + a + j, 0.0);
-                }
+                for (int r = 0; r < NK; ++r) p = fma(c[r], L[r], p);
+                if (f) __stcs(oa + j, getd(j) - p);
+                else if (fill) __stcs(oa + j, 0.0);
             }
         }
     }
@@ -226,13 +255,18 @@ __global__ void __launch_bounds__(FB) k_filter_poly(const int32_t *__restrict__ 
             sf[j] = OFFSET ? (p != -1) : (p >= 0);
         }
         __syncthreads();
-        auto getd = [&](int64_t j) { return j < cap ? sd[j] : d[a + j]; };
-        auto getf = [&](int64_t j) {
-            if (j < cap) return sf[j] != 0;
-            const int p = pix[a + j];
-            return OFFSET ? (p != -1) : (p >= 0);
-        };
-        filter_segment<NK, OFFSET, FB>(getd, getf, a, len, out, fill, sh);
+        if (len <= cap) {                                // block-uniform: the whole subscan is on chip
+            filter_segment<NK, OFFSET, FB>([&](int j) { return sd[j]; }, [&](int j) { return sf[j] != 0; }, a, len, out,
+                                           fill, sh);
+        } else {
+            auto getd = [&](int j) { return j < cap ? sd[j] : d[a + j]; };
+            auto getf = [&](int j) {
+                if (j < cap) return sf[j] != 0;
+                const int p = pix[a + j];
+                return OFFSET ? (p != -1) : (p >= 0);
+            };
+            filter_segment<NK, OFFSET, FB>(getd, getf, a, len, out, fill, sh);
+        }
     }
 }
 
@@ -293,12 +327,18 @@ __global__ void __launch_bounds__(TB, 1) k_filter_poly_tma(const int32_t *__rest
         const int *sp = reinterpret_cast<const int *>(smraw + s * stage_bytes + (size_t)capw * 8) + (a - a4);
         const int64_t nsm = e4 - a;                        // samples of the subscan present in the stage
         mbar_wait(&full[s], (uint32_t)((i / nstage) & 1));
-        auto getd = [&](int64_t j) { return j < nsm ? sd[j] : d[a + j]; };
-        auto getf = [&](int64_t j) {
-            const int p = j < nsm ? sp[j] : pix[a + j];
-            return OFFSET ? (p != -1) : (p >= 0);
-        };
-        filter_segment<NK, OFFSET, TB>(getd, getf, a, len, out, fill, sh);
+        if (nsm >= len) {                                // block-uniform: every sample came with the bulk copy
+            filter_segment<NK, OFFSET, TB>([&](int j) { return sd[j]; },
+                                           [&](int j) { return OFFSET ? (sp[j] != -1) : (sp[j] >= 0); }, a, len, out, fill,
+                                           sh);
+        } else {                                         // the <= 3 last samples of the TOD
+            auto getd = [&](int j) { return j < nsm ? sd[j] : d[a + j]; };
+            auto getf = [&](int j) {
+                const int p = j < nsm ? sp[j] : pix[a + j];
+                return OFFSET ? (p != -1) : (p >= 0);
+            };
+            filter_segment<NK, OFFSET, TB>(getd, getf, a, len, out, fill, sh);
+        }
     }
 }
 
@@ -311,7 +351,10 @@ static int launch_filter_poly(const int32_t *pix, const int64_t *seg_start, cons
     const int64_t budget = 200 * 1024;
     int nstage = (int)(budget / (capw * 12));
     if (nstage > TMA_MAX_STAGES) nstage = TMA_MAX_STAGES;
-    if (use_tma && nstage >= 2 && aligned(d, 16) && aligned(pix, 16)) {
+    // measured (1e8 samples, 8000-sample subscans): B wins up to order 2 (order 0: 0.31 vs 0.50 ms; order 1:
+    // 0.39 vs 0.46 ms); from order 3 on the kernel is bound by fp64 issue and A's larger number of
+    // resident warps wins (0.53 vs 0.57 ms)
+    if (use_tma && NK <= 3 && nstage >= 2 && aligned(d, 16) && aligned(pix, 16)) {
         // no more stages than subscans per CTA make use of
         const int64_t per_cta = (nseg + sm_count() - 1) / sm_count();
         if (nstage > per_cta + 1) nstage = (int)(per_cta + 1);

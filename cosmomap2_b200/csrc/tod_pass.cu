@@ -633,6 +633,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
             for (int i = 0; i < NR; ++i) acc[i] = 0.0;
             for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
                 const int64_t t0 = tile * TILE + (int64_t)lane * K;
+                const double jb = (double)((int)(t0 - a) - j0);      // x_j = -1 + (jb + j) step
                 int p[K];
                 double c[K], s[K], xv[K][POL];
 #pragma unroll
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
                     if (p[j] >= 0) {
                         dv = project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0);
                         double L[NK];
-                        legendre<NK>(fma((double)((int)(t0 + j - a) - j0), step, -1.0), L);
+                        legendre<NK>(fma(jb + (double)j, step, -1.0), L);
                         int q = NK;
 #pragma unroll
                         for (int r = 0; r < NK; ++r) {
@@ -682,11 +683,12 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
                 for (int r = 0; r < NK; ++r) { cc[r] = coef[r]; racc[r] = 0.0; }
                 for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
                     const int64_t t0 = tile * TILE + (int64_t)lane * K;
+                    const double jb = (double)((int)(t0 - a) - j0);
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
                         if (sp[t0 + j - base] < 0) continue;
                         double L[NK];
-                        legendre<NK>(fma((double)((int)(t0 + j - a) - j0), step, -1.0), L);
+                        legendre<NK>(fma(jb + (double)j, step, -1.0), L);
                         double res = sd[t0 + j - base];
 #pragma unroll
                         for (int r = 0; r < NK; ++r) res = fma(-cc[r], L[r], res);
@@ -708,6 +710,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
             for (int r = 0; r < NK; ++r) cf[r] = coef[r];
             for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
                 const int64_t t0 = tile * TILE + (int64_t)lane * K;
+                const double jb = (double)((int)(t0 - a) - j0);
                 int p[K];
                 double c[K], s[K], v[K];
 #pragma unroll
@@ -716,7 +719,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     double L[NK];
-                    legendre<NK>(fma((double)((int)(t0 + j - a) - j0), step, -1.0), L);
+                    legendre<NK>(fma(jb + (double)j, step, -1.0), L);
                     double pj = 0.0;
 #pragma unroll
                     for (int r = 0; r < NK; ++r) pj = fma(cf[r], L[r], pj);
