@@ -17,6 +17,8 @@
 //
 // Bound: shared-memory bandwidth (each fused pass moves 128 B per 4-point butterfly, 7 passes per
 // transform), ~60x fewer flops than the direct form at L = 4096.
+#include <cstdlib>
+
 #include "cm2_common.cuh"
 
 namespace cm2 {
@@ -24,7 +26,6 @@ namespace cm2 {
 constexpr int FFT_LOG2M = 13;
 constexpr int FFT_M = 1 << FFT_LOG2M;   // complex points per window
 constexpr int FFT_NF = 2 * FFT_M;       // real samples per window (16384)
-constexpr int FFT_THREADS = 512;
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
@@ -41,6 +42,7 @@ __global__ void k_fft_twiddles(double2 *__restrict__ tw) {
 }
 
 // one CTA per window.  win_first[b] = first window index of noise block b (prefix, nblocks+1).
+template <int FFT_THREADS>
 __global__ void __launch_bounds__(FFT_THREADS, 1)
     k_toeplitz_fft(const double2 *__restrict__ coef,   // [nblocks][2][M]: C1 then C2, indexed by PHYSICAL (bit-reversed) position
                    const double2 *__restrict__ tw, int L, int64_t nblocks, int64_t blocksize,
@@ -218,11 +220,22 @@ extern "C" int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64
     k_win_first<<<1, 1, 0, st>>>(nblocks, blocksize, blk_start, nt, S, win_first);
     CM2_LAUNCHED();
     const size_t smem = sizeof(double2) * (FFT_M + FFT_M / 8);
-    CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t nwin_ub = nt / S + nblocks + 1;
     int grid = (int)(nwin_ub < sm_count() ? nwin_ub : sm_count());
-    k_toeplitz_fft<<<grid, FFT_THREADS, smem, st>>>(reinterpret_cast<const double2 *>(coef), tw, nband, nblocks, blocksize,
-                                                   blk_start, win_first, d, out, nt);
+    // threads per CTA (one CTA per SM): 1024 by default, CM2_FFT_THREADS=512 selects the first version
+    static const int threads = [] {
+        const char *e = getenv("CM2_FFT_THREADS");
+        return (e && atoi(e) == 512) ? 512 : 1024;
+    }();
+    if (threads == 512) {
+        CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_toeplitz_fft<512><<<grid, 512, smem, st>>>(reinterpret_cast<const double2 *>(coef), tw, nband, nblocks, blocksize,
+                                                    blk_start, win_first, d, out, nt);
+    } else {
+        CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_toeplitz_fft<1024><<<grid, 1024, smem, st>>>(reinterpret_cast<const double2 *>(coef), tw, nband, nblocks, blocksize,
+                                                      blk_start, win_first, d, out, nt);
+    }
     CM2_LAUNCHED();
     return CM2_OK;
 }
