@@ -68,6 +68,9 @@ def main():
     ap.add_argument("--arnoldi", type=int, default=300)
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--maxiter", type=int, default=2000)
+    ap.add_argument("--poly-order", type=int, default=0,
+                    help="subscan filter: 0 = offsets (src/test_M2_precond_onto_real_data.py:79-80), "
+                         ">0 = Legendre polynomials up to that order (:37-38)")
     args = ap.parse_args()
 
     import torch.distributed as dist
@@ -89,7 +92,7 @@ def main():
     npix = pts.get_new_pixel[0]
     n = pol * npix
     P = cm.SparseLO(npix, nt, pts._pix_dev, pol=pol, angle_processed=pts)
-    F = cm.FilterLO(nt, [sub_len, sub_start], ns, args.ndet, pts._pix_dev)
+    F = cm.FilterLO(nt, [sub_len, sub_start], ns, args.ndet, pts._pix_dev, poly_order=args.poly_order)
     Mbd = cm.BlockDiagonalPreconditionerLO(pts, npix, pol=pol)
     A_local = P.T * F * P
     A = distributed.AllReduceLO(A_local) if world > 1 else A_local
@@ -116,7 +119,7 @@ def main():
                        true_relres=rel)
 
     out = {"world": world, "nt_total": nt * world, "nt_per_gpu": nt, "npix": int(npix), "nside": args.nside,
-           "nseg_per_gpu": F.nseg}
+           "nseg_per_gpu": F.nseg, "poly_order": args.poly_order}
     x_bd, out["M_BD"] = solve(Mbd, "M_BD")
 
     # ---- deflation space: preconditioned Arnoldi, Ritz vectors of the smallest Ritz values ----------
