@@ -31,11 +31,19 @@ struct BlockW {
     int64_t nblocks;
     int64_t blocksize;     // equal-size blocks when start == nullptr
     const int64_t *start;  // nblocks+1 block boundaries, or nullptr
+    uint64_t magic;        // ceil(2^64 / blocksize): t / blocksize == umul64hi(t, magic) for t < 2^32 (0: unused)
 };
+
+static BlockW make_blockw(const double *w, int64_t nblocks, int64_t blocksize, const int64_t *start) {
+    BlockW bw{w, nblocks, blocksize, start, 0};
+    if (start == nullptr && blocksize > 1) bw.magic = ~(uint64_t)0 / (uint64_t)blocksize + 1;
+    return bw;
+}
 
 __device__ __forceinline__ int64_t block_of(const BlockW &bw, int64_t t) {
     if (bw.start == nullptr) {
-        if (((uint64_t)t | (uint64_t)bw.blocksize) >> 32 == 0) return (uint32_t)t / (uint32_t)bw.blocksize;
+        // division by the invariant block size as one 64x64 -> high-64 multiply (exact for t < 2^32)
+        if (bw.magic != 0 && ((uint64_t)t >> 32) == 0) return (int64_t)__umul64hi((uint64_t)t, bw.magic);
         return t / bw.blocksize;
     }
     int64_t lo = 0, hi = bw.nblocks;
@@ -287,38 +295,34 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_white(const int32_t *__restri
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
     const int64_t ntiles = (nt + TILE - 1) / TILE;
-    int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
-    if (tile >= ntiles) return;
-    int p[K];
-    double c[K], s[K];
-    {
+    // The open runs of the previous tile (rs) are merged AFTER the loads of the current tile have been
+    // issued, so DRAM latency overlaps the shuffles and REDs of the merge.  One load site per loop trip
+    // (the loop-carried state is rs, 15 registers, not the 40 registers of p/c/s: the first version
+    // carried p/c/s across the back edge and spent 79 register moves per tile on it).
+    RunState<POL> rs;
+    rs.ph = rs.pt = -1;
+    rs.single = true;
+#pragma unroll
+    for (int k = 0; k < POL; ++k) rs.acc[k] = rs.head[k] = 0.0;
+    for (int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
         const int64_t t0 = tile * TILE + (int64_t)lane * K;
+        int p[K];
+        double c[K], s[K];
         load_pix(pix, t0, nt, p);
         if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
-    }
-    for (; tile < ntiles; tile += nwarps) {
-        const int64_t t0 = tile * TILE + (int64_t)lane * K;
-        RunState<POL> rs;
-        {
-            double w[K], xv[K][POL], v[K];
-            gather_x<POL>(x, p, xv);
-            chunk_weights(bw, t0 < nt ? t0 : nt - 1, nt, w);
+        run_merge<POL, POL>(y, rs);             // previous tile (the empty state on the first trip emits nothing)
+        double w[K], xv[K][POL], v[K];
+        gather_x<POL>(x, p, xv);
+        chunk_weights(bw, t0 < nt ? t0 : nt - 1, nt, w);
 #pragma unroll
-            for (int j = 0; j < K; ++j) v[j] = w[j] * project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0);
-            run_compress<POL, POL>(y, p, [&](int j, double (&o)[POL]) {
-                if constexpr (POL == 1) { o[0] = v[j]; }
-                else if constexpr (POL == 2) { o[0] = v[j] * c[j]; o[1] = v[j] * s[j]; }
-                else { o[0] = v[j]; o[1] = v[j] * c[j]; o[2] = v[j] * s[j]; }
-            }, rs);
-        }
-        const int64_t nxt = tile + nwarps;
-        if (nxt < ntiles) {   // warp-uniform
-            const int64_t t1 = nxt * TILE + (int64_t)lane * K;
-            load_pix(pix, t1, nt, p);
-            if (POL > 1) { load_f64(cs, t1, nt, c); load_f64(sn, t1, nt, s); }
-        }
-        run_merge<POL, POL>(y, rs);
+        for (int j = 0; j < K; ++j) v[j] = w[j] * project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0);
+        run_compress<POL, POL>(y, p, [&](int j, double (&o)[POL]) {
+            if constexpr (POL == 1) { o[0] = v[j]; }
+            else if constexpr (POL == 2) { o[0] = v[j] * c[j]; o[1] = v[j] * s[j]; }
+            else { o[0] = v[j]; o[1] = v[j] * c[j]; o[2] = v[j] * s[j]; }
+        }, rs);
     }
+    run_merge<POL, POL>(y, rs);
 }
 
 // Fused y = P^T (P x - mu_seg) over the unflagged samples inside subscans: the offset-filtered
@@ -829,7 +833,7 @@ extern "C" int cm2_amatvec_white(const int32_t *pix, const double *c, const doub
     cudaStream_t st = as_stream(stream);
     if (npix > 0) CM2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)npix * pol, st));
     if (nt == 0 || npix == 0) return CM2_OK;
-    BlockW bw{wblk, nblocks, blocksize, blk_start};
+    const BlockW bw = make_blockw(wblk, nblocks, blocksize, blk_start);
     if (pol == 1) k_amatvec_white<1><<<tod_grid(k_amatvec_white<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, x, y);
     else if (pol == 2) k_amatvec_white<2><<<tod_grid(k_amatvec_white<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, x, y);
     else k_amatvec_white<3><<<tod_grid(k_amatvec_white<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, x, y);
@@ -849,7 +853,7 @@ extern "C" int cm2_weights_moments(const int32_t *pix, const double *c, const do
     cudaStream_t st = as_stream(stream);
     if (npix > 0) CM2_CUDA(cudaMemsetAsync(mom, 0, sizeof(double) * 6 * (size_t)npix, st));
     if (nt == 0 || npix == 0) return CM2_OK;
-    BlockW bw{wblk, nblocks, blocksize, blk_start};
+    const BlockW bw = make_blockw(wblk, nblocks, blocksize, blk_start);
     if (pol == 1) k_moments<1><<<tod_grid(k_moments<1>, nt), BLOCK, 0, st>>>(pix, c, s, w, bw, nt, mom);
     else if (pol == 2) k_moments<2><<<tod_grid(k_moments<2>, nt), BLOCK, 0, st>>>(pix, c, s, w, bw, nt, mom);
     else k_moments<3><<<tod_grid(k_moments<3>, nt), BLOCK, 0, st>>>(pix, c, s, w, bw, nt, mom);

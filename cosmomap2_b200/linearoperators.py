@@ -395,6 +395,19 @@ def flatten_subscans(subscans, tstart, nsamples, nbolos):
 FILTER_STAGED = True        # subscan staged in shared memory (cm2_filter_poly_apply) also for poly_order = 0
 
 
+class _NoPool(object):
+    """Stand-in for the ``multiprocessing.Pool`` the reference keeps in ``FilterLO.procs`` when
+    ``poly_order > 0`` (linearoperators.py:280): scripts that close / terminate it keep working."""
+
+    def __init__(self, npool):
+        self._processes = npool
+
+    def close(self):
+        pass
+
+    terminate = join = close
+
+
 class FilterLO(lp.LinearOperator):
     """Subscan filter -- interfaces/linearoperators.py:94-322.
 
@@ -439,6 +452,8 @@ class FilterLO(lp.LinearOperator):
         self._sorted = bool(self.nseg == 0 or (np.all(se >= ss) and np.all(ss[1:] >= se[:-1])))
         self._pix_dev = dv.pix_to_dev(pix_samples)
         self._legendres = None
+        if self.poly_order > 0:
+            self.procs = _NoPool(npool)
         matvec = self.mult if self.poly_order == 0 else self.polyfilter
         super(FilterLO, self).__init__(nargin=size, nargout=size, matvec=matvec, symmetric=False,
                                        device=True)
