@@ -26,5 +26,12 @@ from .utilities import (dgemm, norm2, scalprod, get_legendre_polynomials, is_sor
                         bash_colors, filter_warnings, angles_gen, pairs_gen, checking_output,
                         noise_val, subscan_resize, system_setup, reorganize_map)
 from .pcg import cg  # noqa: F401
+from . import IOfiles  # noqa: F401
+from .IOfiles import (read_from_data, read_multiple_ces, read_from_data_with_subscan_resize,  # noqa: F401
+                      read_ces_shard, flagging_subscan, flagging_not_in_allCES,
+                      write_ritz_eigenvectors_to_hdf5, read_ritz_eigenvectors_from_hdf5,
+                      read_obspix_from_hdf5, write_obspix_to_hdf5, write_to_hdf5, read_from_hdf5,
+                      save_maplist, read_maplist, full2cutskymap, obspix2mask, find_common_obspix,
+                      write_ces_to_hdf5)
 
 __version__ = "0.1.0"

@@ -265,3 +265,40 @@ def test_reorganize_map(cm, pol):
     assert all(t.is_cuda for t in dev) and np.array_equal(dev[0].cpu().numpy(), ref[0])
     with pytest.raises(IndexError):
         cm.reorganize_map(m, obspix + 12 * nside * nside, npix, nside, pol)
+
+
+@pytest.mark.parametrize("name,pixscale,pol", [("testcase_block_diag_4.hdf5", 1, 1), ("testcase_block_diag_3.hdf5", 3, 3),
+                                               ("testcase_block_diag_3.hdf5", 3, 2)])
+def test_reference_hdf5_fixture_through_the_solve(cm, name, pixscale, pol):
+    """The reference's own test-case files (h5py, system_setup(nt=100, npix=15, nb=2)) read by
+    cosmomap2_b200.IOfiles and solved on the GPU and by the oracle: white and Toeplitz noise."""
+    import os
+    import scipy.sparse.linalg as spla
+    import oracle
+    det, pix_file, phi, weight = cm.read_from_hdf5(os.path.join(gc.GOLDEN, name))
+    nb, nt = 2, len(det)
+    res = {}
+    for label, impl, solver in (("oracle", oracle, spla.cg), ("gpu", cm, cm.cg)):
+        pix = (pix_file // pixscale).astype(np.int64)
+        t = np.asarray(weight, dtype=np.float64).reshape(nb, -1)
+        N = impl.BlockLO(nt // nb, t[:, 0].copy(), offdiag=False)
+        pts = impl.ProcessTimeSamples(pix, 15, pol=pol, phi=phi, w=N.diag)
+        npix = pts.get_new_pixel[0]
+        P = impl.SparseLO(npix, nt, pix, pol=pol, angle_processed=pts)
+        Mbd = impl.BlockDiagonalPreconditionerLO(pts, npix, pol=pol)
+        b = P.T * (N * det)
+        x, info = solver(P.T * N * P, b, M=Mbd, rtol=1e-12, maxiter=50)
+        out = dict(npix=npix, pix=pix, b=b, x=x, info=info)
+        if t.shape[1] > 1:                                 # the (nb, bandsize) noise values as Toeplitz bands
+            band = t.copy()
+            band[:, 0] += 1.0                              # diagonally dominant, as noise_val intends
+            NT = impl.BlockLO(nt // nb, [r for r in band], offdiag=True)
+            out["toep"] = P.T * (NT * (P * x))
+        res[label] = out
+    o, g = res["oracle"], res["gpu"]
+    assert o["npix"] == g["npix"] and o["info"] == 0 and g["info"] == 0
+    gc.exact(g["pix"], o["pix"], "relabelled pixels of the fixture")
+    gc.close(g["b"], o["b"], what="b")
+    gc.close(g["x"], o["x"], rtol=1e-9, what="x")
+    if "toep" in o:
+        gc.close(g["toep"], o["toep"], what="P^T N_toeplitz P x")
