@@ -13,6 +13,7 @@ Pinned by the reference's own fixtures data/testcase_block_diag_{3,4}.hdf5 (writ
 ``write_to_hdf5``, IOfiles.py:277-300; copies under tests/golden/), which the reader decodes and the
 writer reproduces structure for structure.
 """
+import mmap
 import struct
 import zlib
 
@@ -121,15 +122,23 @@ class File(_Group):
     def __init__(self, filename, mode="r"):
         if mode != "r":
             raise ValueError("hdf5lite.File reads; use hdf5lite.write(...) to create files")
-        with open(filename, "rb") as fh:
-            self._buf = fh.read()
+        self._fh = open(filename, "rb")
+        try:                                               # mapped, not read: CES files are GBs
+            self._buf = mmap.mmap(self._fh.fileno(), 0, access=mmap.ACCESS_READ)
+        except ValueError:                                 # empty file
+            self._buf = b""
         self.filename = filename
         self._cache = {}
         root = self._superblock()
         _Group.__init__(self, self, "/", self._object_links(root))
 
     def close(self):
+        if isinstance(self._buf, mmap.mmap):
+            self._buf.close()
         self._buf = b""
+        if self._fh is not None:
+            self._fh.close()
+            self._fh = None
 
     def __enter__(self):
         return self
@@ -183,7 +192,7 @@ class File(_Group):
         if b[heap_addr:heap_addr + 4] != b"HEAP":
             raise Hdf5Error("bad local heap at 0x%x" % heap_addr)
         data = self._u(heap_addr + 24, 8)
-        end = b.index(b"\0", data + off)
+        end = b.find(b"\0", data + off)
         return b[data + off:end].decode("utf-8")
 
     def _btree_group(self, addr, heap, links):
