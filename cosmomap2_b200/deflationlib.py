@@ -201,3 +201,158 @@ def find_ritz_eigenvalues(h, v, threshold=1.e-2, eigenvalues=False, filename=Non
         zsel = z[:, torch.as_tensor(idx, device=z.device)] if isinstance(z, torch.Tensor) else z[:, idx]
         return zsel, r, eig[sel]
     return z[:, :r], r
+
+
+def eigsh(A, k=6, M=None, Minv=None, which="SM", ncv=None, tol=0, maxiter=None, v0=None,
+          return_eigenvectors=True, device=False):
+    """Device-resident counterpart of ``scipy.sparse.linalg.eigsh(A, k, M=B, Minv=Mbd, which=...,
+    ncv=..., tol=..., v0=...)`` -- the route the reference's TESTS take to the deflation space
+    (tests/test_2level_preconditioner.py:33, tests/test_coarse_operator.py:16,
+    tests/test_deflation_operator.py:15): the ``k`` eigenpairs of ``A z = lambda B z`` selected by
+    ``which`` ('SM', 'LM', 'SA', 'LA'), ``Z^T B Z = I``.
+
+    ARPACK (implicitly restarted Lanczos, regular mode with ``OP = Minv A``) is replaced by the
+    mathematically equivalent thick-restart Lanczos, run on device vectors: basis ``V`` B-orthonormal
+    with its dual ``P = B V`` carried along (krypy's recurrence above, so ``B`` itself is never
+    applied, only ``A`` and ``Minv``); per step one A apply, one Minv apply and a two-pass block
+    Gram-Schmidt (two tall-skinny kernels per pass); per restart a dense ``eigh`` of the ncv x ncv
+    projected matrix on the host and one (l x ncv)(ncv x n) GEMM per basis.  Convergence test as in
+    ARPACK: ``|beta_m y_{m,i}| <= tol * max(eps^(2/3), |theta_i|)`` for the wanted Ritz pairs
+    (``tol = 0`` means machine precision).  ``M`` is accepted for signature compatibility and only
+    used when ``Minv`` is missing (then ``Minv = M^-1`` is required and an error is raised).
+
+    Returns ``w`` (ascending) and, unless ``return_eigenvectors=False``, ``Z`` (n x k): NumPy arrays,
+    or CUDA tensors with ``device=True``.  Raises ``scipy.sparse.linalg.ArpackNoConvergence`` (with the
+    converged pairs attached) when ``maxiter`` restarts do not suffice."""
+    from scipy.sparse.linalg import ArpackNoConvergence
+    dv.require_cuda()
+    A = _as_op(A)
+    n = A.shape[0]
+    if M is not None and Minv is None:
+        raise ValueError("eigsh: a generalized problem needs Minv (the reference passes Minv=Mbd)")
+    Minv = _as_op(Minv) if Minv is not None else None
+    if which not in ("SM", "LM", "SA", "LA"):
+        raise ValueError("which must be one of 'SM', 'LM', 'SA', 'LA'")
+    if k <= 0 or k >= n:
+        raise ValueError("k must be between 1 and n-1")
+    m = min(n, max(2 * k + 1, 20) if ncv is None else int(ncv))          # SciPy clamps ncv to n as well
+    if m <= k:
+        raise ValueError("ncv must be k<ncv<=n, ncv=%d" % m)
+    maxiter = 10 * n if maxiter is None else int(maxiter)
+    tol_eff = np.finfo(np.float64).eps if tol <= 0 else float(tol)
+    eps23 = np.finfo(np.float64).eps ** (2.0 / 3.0)
+    st = dv.stream
+    s = dv.zeros_f64(1)
+    p0 = dv.to_dev_f64(np.random.default_rng(0).uniform(-1, 1, n) if v0 is None else v0).reshape(-1).clone()
+    V = torch.zeros((m + 1, n), dtype=torch.float64, device=p0.device)
+    P = torch.zeros((m + 1, n), dtype=torch.float64, device=p0.device) if Minv is not None else V
+    H = np.zeros((m + 1, m))
+    work = dv.empty_f64(int(dv.call("cm2_defl_work_doubles", int(m + 1))))
+    hdev = dv.empty_f64(m + 1)
+    z0 = Minv._apply(p0) if Minv is not None else p0
+    nrm = np.sqrt(abs(_dot(p0, z0, s)))
+    if not np.isfinite(nrm) or nrm == 0.0:
+        raise ValueError("eigsh: the starting vector has zero norm in the B inner product")
+    V[0].copy_(z0)
+    V[0].mul_(1.0 / nrm)
+    if Minv is not None:
+        P[0].copy_(p0)
+        P[0].mul_(1.0 / nrm)
+
+    def wanted(theta):
+        if which == "SM":
+            return np.argsort(np.abs(theta), kind="stable")
+        if which == "LM":
+            return np.argsort(-np.abs(theta), kind="stable")
+        if which == "SA":
+            return np.argsort(theta, kind="stable")
+        return np.argsort(-theta, kind="stable")
+
+    ell = 0                       # number of basis vectors kept from the previous cycle (V[ell] is the residual direction)
+    theta = Y = res = sel = None
+    m_eff = m
+    for restart in range(maxiter + 1):
+        for j in range(ell, m):                            # Lanczos steps with full re-orthogonalisation
+            u = A._apply(V[j])
+            if u.data_ptr() == V[j].data_ptr():
+                u = u.clone()
+            H[:, j] = 0.0
+            for _ in range(2):
+                dv.call("cm2_defl_zt_apply", dv.ptr(V), n, j + 1, n, dv.ptr(u), 1, n, dv.ptr(hdev), dv.ptr(work), st())
+                dv.call("cm2_defl_z_apply", dv.ptr(P), n, j + 1, n, dv.ptr(hdev), -1.0, 1.0, dv.ptr(u), dv.ptr(u), st())
+                H[:j + 1, j] += dv.to_host(hdev[:j + 1])
+            z = Minv._apply(u) if Minv is not None else u
+            beta = np.sqrt(abs(_dot(u, z, s)))
+            H[j + 1, j] = beta
+            if beta <= 1e-12 * max(np.abs(H[:j + 2, :j + 1]).max(), 1e-300):
+                # invariant subspace (the whole space when ncv = n): every Ritz pair of this basis is exact
+                H[j + 1, j] = 0.0
+                made = False
+                if j + 1 < n:                              # continue with a fresh direction B-orthogonal to it
+                    fresh = dv.to_dev_f64(np.random.default_rng(1000 + restart * m + j).uniform(-1, 1, n))
+                    z = Minv._apply(fresh) if Minv is not None else fresh
+                    nrm0 = np.sqrt(abs(_dot(fresh, z, s)))
+                    for _ in range(2):
+                        dv.call("cm2_defl_zt_apply", dv.ptr(V), n, j + 1, n, dv.ptr(fresh), 1, n, dv.ptr(hdev), dv.ptr(work), st())
+                        dv.call("cm2_defl_z_apply", dv.ptr(P), n, j + 1, n, dv.ptr(hdev), -1.0, 1.0, dv.ptr(fresh),
+                                dv.ptr(fresh), st())
+                    z = Minv._apply(fresh) if Minv is not None else fresh
+                    beta_f = np.sqrt(abs(_dot(fresh, z, s)))
+                    if nrm0 > 0 and beta_f > 1e-8 * nrm0:
+                        V[j + 1].copy_(z)
+                        V[j + 1].mul_(1.0 / beta_f)
+                        if Minv is not None:
+                            P[j + 1].copy_(fresh)
+                            P[j + 1].mul_(1.0 / beta_f)
+                        made = True
+                if not made:                               # the basis spans everything Minv A can reach
+                    m_eff = j + 1
+                    break
+                continue
+            V[j + 1].copy_(z)
+            V[j + 1].mul_(1.0 / beta)
+            if Minv is not None:
+                P[j + 1].copy_(u)
+                P[j + 1].mul_(1.0 / beta)
+        T = np.triu(H[:m_eff, :m_eff])
+        T = T + np.triu(T, 1).T
+        theta, Y = eigh(T)
+        order = wanted(theta)
+        sel = order[:min(k, m_eff)]
+        res = np.abs(H[m_eff, m_eff - 1] * Y[m_eff - 1, :])
+        conv = res[sel] <= tol_eff * np.maximum(eps23, np.abs(theta[sel]))
+        if bool(conv.all()) or restart == maxiter or m_eff < m:
+            break
+        # thick restart: keep the wanted Ritz vectors plus part of the rest (as ARPACK's exact shifts do)
+        nconv = int(np.count_nonzero(conv))
+        ell = min(k + nconv + max((m - k) // 2 - nconv, 0), m - 1)
+        ell = max(ell, k)
+        keep = order[:ell]
+        Yk = dv.to_dev_f64(np.ascontiguousarray(Y[:, keep].T))             # ell x m
+        Vn = torch.matmul(Yk, V[:m])
+        V[:ell].copy_(Vn)
+        if Minv is not None:
+            Pn = torch.matmul(Yk, P[:m])
+            P[:ell].copy_(Pn)
+            P[ell].copy_(P[m])
+        V[ell].copy_(V[m])
+        coupling = H[m, m - 1] * Y[m - 1, keep]
+        H[:, :] = 0.0
+        H[np.arange(ell), np.arange(ell)] = theta[keep]
+        H[ell, :ell] = coupling
+        H[:ell, ell] = 0.0                                                  # refilled by the Gram-Schmidt of step ell
+    idx = sel[np.argsort(theta[sel], kind="stable")]
+    w = theta[idx]
+    converged = res[idx] <= tol_eff * np.maximum(eps23, np.abs(w))
+    Z = None
+    if return_eigenvectors or not converged.all():
+        Z = torch.matmul(dv.to_dev_f64(np.ascontiguousarray(Y[:, idx].T)), V[:m_eff]).t().contiguous()
+    if not converged.all():
+        good = np.nonzero(converged)[0]
+        raise ArpackNoConvergence("eigsh: %d of %d wanted eigenpairs converged in %d restarts"
+                                  % (len(good), k, maxiter), w[good],
+                                  dv.to_host(Z[:, torch.as_tensor(good, device=Z.device)]) if len(good) else
+                                  np.zeros((n, 0)))
+    if not return_eigenvectors:
+        return w
+    return (w, Z) if device else (w, dv.to_host(Z))

@@ -302,3 +302,47 @@ def test_reference_hdf5_fixture_through_the_solve(cm, name, pixscale, pol):
     gc.close(g["x"], o["x"], rtol=1e-9, what="x")
     if "toep" in o:
         gc.close(g["toep"], o["toep"], what="P^T N_toeplitz P x")
+
+
+@pytest.mark.parametrize("pol,nt,npix,nb,ncv,tol", [(1, 500, 40, 1, 15, 1e-10), (3, 4000, 20, 1, 15, 1e-5),
+                                                    (2, 1000, 20, 2, 50, 1e-4), (3, 60000, 400, 4, 40, 1e-8)])
+def test_device_eigsh_equals_arpack(cm, pol, nt, npix, nb, ncv, tol):
+    """cosmomap2_b200.eigsh (thick-restart Lanczos on device vectors) against SciPy's ARPACK on the
+    oracle's operators, for the calls the reference's tests make (tests/test_2level_preconditioner.py:33,
+    tests/test_coarse_operator.py:16, tests/test_deflation_operator.py:15; ncv > n is clamped like SciPy
+    does) and a larger system: eigenvalues, the eigenspace, B-orthonormality, and the two-level
+    identities M2 A z = z, R A z = 0 with the device-built Z."""
+    import scipy.sparse.linalg as spla
+    import oracle
+    import reference_suite as rs
+    no, Po, No, Mo, Bo, Ao, bo = rs._deflation_system(oracle, nt, npix, nb, pol, seed=70 + pol)
+    ng, Pg, Ng, Mg, Bg, Ag, bg = rs._deflation_system(cm, nt, npix, nb, pol, seed=70 + pol)
+    assert no == ng
+    n = pol * ng
+    w0, Z0 = spla.eigsh(Ao, M=Bo, Minv=Mo, k=5, v0=np.ones(n), which="SM", ncv=ncv, tol=tol)
+    w1, Z1 = cm.eigsh(Ag, M=Bg, Minv=Mg, k=5, v0=np.ones(n), which="SM", ncv=ncv, tol=tol)
+    order = np.argsort(w0)
+    w0, Z0 = w0[order], Z0[:, order]
+    assert np.allclose(w1, w0, rtol=max(100 * tol, 1e-9), atol=1e-12), (w0, w1)
+    BZ1 = np.column_stack([Bo * Z1[:, i] for i in range(5)])
+    assert np.abs(Z1.T.dot(BZ1) - np.eye(5)).max() < 1e-10             # Z^T B Z = I
+    for i in range(5):                                                 # A z = lambda B z
+        assert np.linalg.norm(Ao * Z1[:, i] - w1[i] * BZ1[:, i]) <= max(10 * tol, 1e-9) * np.linalg.norm(BZ1[:, i])
+    # same eigenspace as ARPACK's (eigenvalues may be clustered: compare the projector, not the vectors)
+    BZ0 = np.column_stack([Bo * Z0[:, i] for i in range(5)])
+    assert np.linalg.norm(Z0 - Z1.dot(Z1.T.dot(BZ0))) <= max(1e4 * tol, 1e-8) * np.linalg.norm(Z0)
+    # two-level preconditioner from the device-built Z (tests/test_2level_preconditioner.py:38-48)
+    Az = np.column_stack([Ag * Z1[:, i] for i in range(5)])
+    E = cm.CoarseLO(Z1, Az, 5)
+    Zd = cm.DeflationLO(Z1)
+    R = cm.lp.IdentityOperator(n) - Ag * Zd * E * Zd.T
+    M2 = Mg * R + Zd * E * Zd.T
+    for i in range(5):
+        assert np.allclose(M2 * (Ag * Z1[:, i]), Z1[:, i], atol=1e-8)
+        assert cm.norm2(R * (Ag * Z1[:, i])) <= 1e-9
+    # other selections, without eigenvectors
+    wl = cm.eigsh(Ag, M=Bg, Minv=Mg, k=3, which="LA", ncv=min(ncv, 20), tol=1e-10, v0=np.ones(n), return_eigenvectors=False)
+    wl0 = spla.eigsh(Ao, M=Bo, Minv=Mo, k=3, which="LA", ncv=min(ncv, 20), tol=1e-10, v0=np.ones(n), return_eigenvectors=False)
+    assert np.allclose(np.sort(wl), np.sort(wl0), rtol=1e-8)
+    with pytest.raises(ValueError):
+        cm.eigsh(Ag, M=Bg, k=3)
