@@ -35,6 +35,26 @@ METRIC = "tod_samples_per_s_per_pcg_iter"
 UNIT = "samples/s"
 
 
+_json_out = None
+
+
+def claim_stdout():
+    """Keep stdout to the ONE JSON line of the contract: the real stdout is set aside for it and file
+    descriptor 1 is pointed at stderr, so banners that libraries print to stdout (NCCL prints its
+    version there when NCCL_DEBUG is VERSION or WARN) cannot get in front of it."""
+    global _json_out
+    if _json_out is None:
+        sys.stdout.flush()
+        _json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    claim_stdout()
+    _json_out.write(json.dumps(line) + "\n")
+    _json_out.flush()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -99,7 +119,7 @@ def run_reference_arm(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -148,6 +168,7 @@ class ClockSampler(object):
 
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -162,8 +183,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+        claim_stdout()                                 # NCCL's version banner goes to stderr
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import cosmomap2_b200 as cm
@@ -370,7 +390,7 @@ def main():
                 "sample": "oracle port (C twin of the reference's weave loops, gcc -O3, + scipy cg) on %d samples of the "
                           "same workload generator, %d iterations, %.2f s/iteration" % (nt_cpu, args.cpu_iters, t_iter),
                 "host_cores_available": os.cpu_count()}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         A.check()
         A.close()
