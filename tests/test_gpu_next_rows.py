@@ -346,3 +346,25 @@ def test_device_eigsh_equals_arpack(cm, pol, nt, npix, nb, ncv, tol):
     assert np.allclose(np.sort(wl), np.sort(wl0), rtol=1e-8)
     with pytest.raises(ValueError):
         cm.eigsh(Ag, M=Bg, k=3)
+
+
+@pytest.mark.parametrize("nt", [1003, 1002, 1001, 1000, 7])
+def test_subscan_filter_last_samples_of_the_tod(cm, variant, nt):
+    """The last subscan ends at the very end of a TOD whose length is not a multiple of 4: the bulk
+    copies stop at nt & ~3 and the remaining <= 3 samples are read directly; also subscans of 1-3
+    samples and a single-subscan table."""
+    import oracle
+    rng = np.random.default_rng(nt)
+    if nt > 100:
+        L = np.array([3, 1, 200, 2, nt - 700], dtype=np.int64)
+        S = np.array([0, 5, 10, 400, 700], dtype=np.int64)
+    else:
+        L, S = np.array([nt], dtype=np.int64), np.array([0], dtype=np.int64)
+    pix = rng.integers(0, 9, size=nt).astype(np.int64)
+    pix[rng.random(nt) < 0.1] = -1
+    pix[-1] = 4
+    d = rng.standard_normal(nt) + 2.0
+    for order in (0, 1, 2):
+        ref = oracle.FilterLO(nt, [L, S], nt, 1, pix.copy(), poly_order=order) * d
+        out = cm.FilterLO(nt, [L, S], nt, 1, pix.copy(), poly_order=order) * d
+        gc.close(out, ref, what="order %d, nt = %d" % (order, nt))
