@@ -577,10 +577,12 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter(const int32_t *__restr
 
 // Fused y = P^T F_K P x with the Legendre subscan filter F_K (FilterLO.polyfilter,
 // linearoperators.py:170-204; NK = poly_order + 1 >= 2): one CTA per subscan, no TOD temporary.
-//   pass 0: the subscan's pixels -> shared memory; number / first / last unflagged sample
-//   pass 1: d = P x of the subscan -> shared memory; S_k = sum L_k d, G_kl = sum L_k L_l
+//   pass 1: the subscan's pixels and d = P x -> shared memory; number / first / last unflagged sample;
+//           S_k = sum L_k d, G_kl = sum L_k L_l in the Legendre basis of the whole subscan
 //   solve : c_k = S_k / G_kk without flags (the reference's literal sum over the sampled,
-//           not exactly orthogonal, basis), else G c = S (QR re-orthonormalised basis, :190-194)
+//           not exactly orthogonal, basis), else G c = S (QR re-orthonormalised basis, :190-194);
+//           if G is ill-conditioned (flags leave only part of the subscan) the moments are redone
+//           from shared memory in the basis of the interval the unflagged samples span
 //   pass 2: scatter-add of d - sum_k c_k L_k over the unflagged samples
 // cap = shared-memory window in samples (a multiple of TILE covering the longest subscan).
 template <int POL, int NK>
@@ -596,59 +598,100 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
     __shared__ double red[NW * NR];
     __shared__ double tot[NR];
     __shared__ double coef[NK];
-    __shared__ int s_cnt, s_jmin, s_jmax, s_refine;
+    __shared__ int s_cnt, s_jmin, s_jmax, s_refine, s_local;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t k = blockIdx.x; k < nseg; k += gridDim.x) {
         const int64_t a = seg_start[k], b = seg_end[k];
         const int64_t tile0 = a / TILE, tile1 = (b + TILE - 1) / TILE;   // [tile0, tile1)
         const int64_t base = tile0 * TILE;
+        const int len = (int)(b - a);
         if (threadIdx.x == 0) { s_cnt = 0; s_jmin = INT32_MAX; s_jmax = -1; }
         __syncthreads();
+        // ---- pass 1 (the only read of pix): pixels and d = P x -> shared memory; number / first / last
+        // unflagged sample; S and G in the Legendre basis of the WHOLE subscan (x = -1 + 2 j/(len-1)),
+        // which is the reference's basis without flags and close to orthogonal with a few flags
+        const double step_f = len > 1 ? 2.0 / (double)(len - 1) : 0.0;
         int cnt = 0, jmin = INT32_MAX, jmax = -1;
+        double acc[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) acc[i] = 0.0;
         for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
             const int64_t t0 = tile * TILE + (int64_t)lane * K;
+            const double jb = (double)(int)(t0 - a);
             int p[K];
+            double c[K], s[K], xv[K][POL];
             load_pix_keep(pix, t0, nt, p);
+            if (POL > 1) { load_f64_keep(cs, t0, nt, c); load_f64_keep(sn, t0, nt, s); }
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 if (t0 + j < a || t0 + j >= b || p[j] < 0) p[j] = -1;
                 sp[t0 + j - base] = p[j];
+            }
+            gather_x<POL>(x, p, xv);
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                double dv = 0.0;
                 if (p[j] >= 0) {
-                    const int jj = (int)(t0 + j - a);
+                    const int jj = (int)(t0 - a) + j;
                     ++cnt;
                     jmin = min(jmin, jj);
                     jmax = max(jmax, jj);
+                    dv = project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0);
+                    double L[NK];
+                    legendre<NK>(fma(jb + (double)j, step_f, -1.0), L);
+                    int q = NK;
+#pragma unroll
+                    for (int r = 0; r < NK; ++r) {
+                        acc[r] = fma(L[r], dv, acc[r]);
+#pragma unroll
+                        for (int l = r; l < NK; ++l) { acc[q] = fma(L[r], L[l], acc[q]); ++q; }
+                    }
                 }
+                sd[t0 + j - base] = dv;
             }
         }
         cnt = __reduce_add_sync(FULL, cnt);
         jmin = __reduce_min_sync(FULL, jmin);
         jmax = __reduce_max_sync(FULL, jmax);
         if (lane == 0 && cnt > 0) { atomicAdd(&s_cnt, cnt); atomicMin(&s_jmin, jmin); atomicMax(&s_jmax, jmax); }
-        __syncthreads();
+        block_sum_n<NR, NW>(acc, red, tot);                  // barriers inside: the counters are complete after it
         const int n = s_cnt;
-        if (n > NK - 1) {                                    // block-uniform
-            const bool full = (int64_t)n == b - a;
-            const int j0 = full ? 0 : s_jmin;
-            const int j1 = full ? (int)(b - a - 1) : s_jmax;
-            const double step = 2.0 / (double)(j1 - j0);
-            double acc[NR];
+        if (n > NK - 1) {                                    // block-uniform (else: too few samples, :185-187)
+            const bool full = n == len;
+            if (threadIdx.x == 0) {
+                s_refine = 0;
+                s_local = 0;
+                if (full) {                                  // the reference's literal sum_k (b_k . d) b_k
+                    int q = NK;
 #pragma unroll
-            for (int i = 0; i < NR; ++i) acc[i] = 0.0;
-            for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
-                const int64_t t0 = tile * TILE + (int64_t)lane * K;
-                const double jb = (double)((int)(t0 - a) - j0);      // x_j = -1 + (jb + j) step
-                int p[K];
-                double c[K], s[K], xv[K][POL];
+                    for (int r = 0; r < NK; ++r) {
+                        coef[r] = tot[q] > 0.0 ? tot[r] / tot[q] : 0.0;
+                        q += NK - r;
+                    }
+                } else {
+                    double cc[NK];
+                    // ill-conditioned in the whole-subscan basis (the unflagged samples cluster in part of
+                    // the subscan): redo the moments in the basis of the interval they span
+                    s_local = gram_solve<NK>(tot + NK, tot, cc) < 1e-3;
 #pragma unroll
-                for (int j = 0; j < K; ++j) p[j] = sp[t0 + j - base];
-                if (POL > 1) { load_f64_keep(cs, t0, nt, c); load_f64_keep(sn, t0, nt, s); }
-                gather_x<POL>(x, p, xv);
+                    for (int r = 0; r < NK; ++r) coef[r] = cc[r];
+                }
+            }
+            __syncthreads();
+            int j0 = 0;
+            double step = step_f;
+            if (s_local) {                                   // block-uniform, rare: shared memory only
+                j0 = s_jmin;
+                step = 2.0 / (double)(s_jmax - s_jmin);
 #pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    double dv = 0.0;
-                    if (p[j] >= 0) {
-                        dv = project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0);
+                for (int i = 0; i < NR; ++i) acc[i] = 0.0;
+                for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
+                    const int64_t t0 = tile * TILE + (int64_t)lane * K;
+                    const double jb = (double)((int)(t0 - a) - j0);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        if (sp[t0 + j - base] < 0) continue;
+                        const double dv = sd[t0 + j - base];
                         double L[NK];
                         legendre<NK>(fma(jb + (double)j, step, -1.0), L);
                         int q = NK;
@@ -659,56 +702,46 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
                             for (int l = r; l < NK; ++l) { acc[q] = fma(L[r], L[l], acc[q]); ++q; }
                         }
                     }
-                    sd[t0 + j - base] = dv;
                 }
-            }
-            block_sum_n<NR, NW>(acc, red, tot);
-            if (threadIdx.x == 0) {
-                s_refine = 0;
-                if (full) {
-                    int q = NK;
-#pragma unroll
-                    for (int r = 0; r < NK; ++r) {
-                        coef[r] = tot[q] > 0.0 ? tot[r] / tot[q] : 0.0;
-                        q += NK - r;
-                    }
-                } else {
+                block_sum_n<NR, NW>(acc, red, tot);
+                if (threadIdx.x == 0) {
                     double cc[NK];
                     s_refine = filter_refine_steps(gram_solve<NK>(tot + NK, tot, cc));
 #pragma unroll
                     for (int r = 0; r < NK; ++r) coef[r] = cc[r];
                 }
-            }
-            __syncthreads();
-            const int nref = s_refine;                       // block-uniform, 0 unless ill-conditioned
-            for (int it = 0; it < nref; ++it) {
-                double cc[NK], racc[NK];
-#pragma unroll
-                for (int r = 0; r < NK; ++r) { cc[r] = coef[r]; racc[r] = 0.0; }
-                for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
-                    const int64_t t0 = tile * TILE + (int64_t)lane * K;
-                    const double jb = (double)((int)(t0 - a) - j0);
-#pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        if (sp[t0 + j - base] < 0) continue;
-                        double L[NK];
-                        legendre<NK>(fma(jb + (double)j, step, -1.0), L);
-                        double res = sd[t0 + j - base];
-#pragma unroll
-                        for (int r = 0; r < NK; ++r) res = fma(-cc[r], L[r], res);
-#pragma unroll
-                        for (int r = 0; r < NK; ++r) racc[r] = fma(L[r], res, racc[r]);
-                    }
-                }
-                block_sum_n<NK, NW>(racc, red, tot);
-                if (threadIdx.x == 0) {
-                    double dc[NK];
-                    gram_solve<NK>(tot + NK, tot, dc);
-#pragma unroll
-                    for (int r = 0; r < NK; ++r) coef[r] += dc[r];
-                }
                 __syncthreads();
+                const int nref = s_refine;
+                for (int it = 0; it < nref; ++it) {
+                    double cc[NK], racc[NK];
+#pragma unroll
+                    for (int r = 0; r < NK; ++r) { cc[r] = coef[r]; racc[r] = 0.0; }
+                    for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
+                        const int64_t t0 = tile * TILE + (int64_t)lane * K;
+                        const double jb = (double)((int)(t0 - a) - j0);
+#pragma unroll
+                        for (int j = 0; j < K; ++j) {
+                            if (sp[t0 + j - base] < 0) continue;
+                            double L[NK];
+                            legendre<NK>(fma(jb + (double)j, step, -1.0), L);
+                            double res = sd[t0 + j - base];
+#pragma unroll
+                            for (int r = 0; r < NK; ++r) res = fma(-cc[r], L[r], res);
+#pragma unroll
+                            for (int r = 0; r < NK; ++r) racc[r] = fma(L[r], res, racc[r]);
+                        }
+                    }
+                    block_sum_n<NK, NW>(racc, red, tot);
+                    if (threadIdx.x == 0) {
+                        double dc[NK];
+                        gram_solve<NK>(tot + NK, tot, dc);
+#pragma unroll
+                        for (int r = 0; r < NK; ++r) coef[r] += dc[r];
+                    }
+                    __syncthreads();
+                }
             }
+            // ---- pass 2: scatter-add of d - sum_k c_k L_k over the unflagged samples
             double cf[NK];
 #pragma unroll
             for (int r = 0; r < NK; ++r) cf[r] = coef[r];
