@@ -58,6 +58,7 @@ SIGNATURES = {
     "cm2_amatvec_filter_poly_max_order": (_int, []),
     "cm2_amatvec_filter_poly": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _i64, _i64, _int, _vp, _vp, _i64, _vp]),
     "cm2_ground_filter_apply": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "cm2_ground_filter_sub": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "cm2_reorganize_map": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp]),
     "cm2_defl_work_doubles": (_i64, [_int]),
     "cm2_defl_zt_apply": (_int, [_vp, _i64, _int, _i64, _vp, _int, _i64, _vp, _vp, _vp]),

@@ -475,17 +475,23 @@ extern "C" int cm2_filter_poly_set_tma(int on) {
     return old;
 }
 
-extern "C" int cm2_ground_filter_apply(const int32_t *ground, int64_t nt, int64_t nbins, const int64_t *hits,
-                                       const double *v, double *bins, double *out, cm2_stream_t stream) {
+extern "C" int cm2_ground_filter_sub(const int32_t *ground, int64_t nt, int64_t nbins, const int64_t *hits,
+                                     const double *bins, const double *v, double *out, cm2_stream_t stream) {
     CM2_REQUIRE(nt >= 0 && nbins >= 0, "bad sizes");
     CM2_REQUIRE(aligned(ground, 32) && aligned(v, 32) && aligned(out, 32), "TOD vectors must be 32-byte aligned");
-    // bins = G^T v: the pol = 1 scatter-add with run aggregation (ground bins change slowly along a scan)
-    int rc = cm2_pointing_apply_t(ground, nullptr, nullptr, nt, 1, v, bins, nbins, stream);
-    if (rc) return rc;
     if (nt == 0) return CM2_OK;
     k_ground_sub<<<grid_fp(((nt + 3) / 4 + FB - 1) / FB), FB, 0, as_stream(stream)>>>(ground, bins, hits, v, out, nt);
     CM2_LAUNCHED();
     return CM2_OK;
+}
+
+extern "C" int cm2_ground_filter_apply(const int32_t *ground, int64_t nt, int64_t nbins, const int64_t *hits,
+                                       const double *v, double *bins, double *out, cm2_stream_t stream) {
+    CM2_REQUIRE(nt >= 0 && nbins >= 0, "bad sizes");
+    // bins = G^T v: the pol = 1 scatter-add with run aggregation (ground bins change slowly along a scan)
+    int rc = cm2_pointing_apply_t(ground, nullptr, nullptr, nt, 1, v, bins, nbins, stream);
+    if (rc) return rc;
+    return cm2_ground_filter_sub(ground, nt, nbins, hits, bins, v, out, stream);
 }
 
 extern "C" int cm2_reorganize_map(const double *map, const int64_t *obspix, int64_t npix, int pol, int64_t healpix_npix,

@@ -728,23 +728,42 @@ class GroundFilterLO(lp.LinearOperator):
     ``GroundFilterLO(ground)``: ``ground[t]`` = azimuth bin of sample t (-1 = flagged).  Attributes
     ``nbins, n, Pg`` as in the reference; ``mult`` is two kernels (bin sums by the run-aggregating
     pol-1 scatter, then the subtraction) instead of the three-operator chain ``G*invGtG*G.T``.
+
+    ``comm=True`` (or a process group): the TOD is sharded over GPUs by detector while the ground
+    template is common to all detectors, so the number of bins, the hits and -- at every application --
+    the bin sums are summed over the ranks (two tiny all-reduces; ``Pg`` then is the local part only).
     """
 
     def counts_in_groundbins(self, g):                    # :26-46
         gd = g if (isinstance(g, torch.Tensor) and g.is_cuda and g.dtype == torch.int32) else dv.pix_to_dev(g)
         hits = torch.empty(max(self.nbins, 1), dtype=torch.int64, device=gd.device)
         dv.call("cm2_hits_i64", dv.ptr(gd), gd.numel(), self.nbins, dv.ptr(hits), _stream())
+        if self._group is not None:
+            from . import distributed
+            distributed.all_reduce_sum_(hits, self._group_arg)
         self._hits_dev = hits
         return dv.to_host(hits[:self.nbins]).astype(np.float64)
 
     def mult(self, v):                                    # :48-49
         out = torch.empty_like(v)
-        dv.call("cm2_ground_filter_apply", dv.ptr(self._g_dev), self.n, self.nbins, dv.ptr(self._hits_dev),
-                dv.ptr(v), dv.ptr(self._bins), dv.ptr(out), _stream())
+        if self._group is None:
+            dv.call("cm2_ground_filter_apply", dv.ptr(self._g_dev), self.n, self.nbins, dv.ptr(self._hits_dev),
+                    dv.ptr(v), dv.ptr(self._bins), dv.ptr(out), _stream())
+            return out
+        from . import distributed
+        dv.call("cm2_pointing_apply_t", dv.ptr(self._g_dev), None, None, self.n, 1, dv.ptr(v), dv.ptr(self._bins),
+                self.nbins, _stream())
+        distributed.all_reduce_sum_(self._bins, self._group_arg)
+        dv.call("cm2_ground_filter_sub", dv.ptr(self._g_dev), self.n, self.nbins, dv.ptr(self._hits_dev),
+                dv.ptr(self._bins), dv.ptr(v), dv.ptr(out), _stream())
         return out
 
-    def __init__(self, ground):                           # :51-61
+    def __init__(self, ground, comm=None):                # :51-61
         dv.require_cuda()
+        from . import distributed
+        self._group_arg = None if comm is True else comm
+        self._group = comm if (comm is not None and comm is not False and distributed.is_distributed(self._group_arg)) \
+            else None
         self.n = len(ground)
         self._g_dev = dv.pix_to_dev(ground)
         if isinstance(ground, torch.Tensor):
@@ -752,6 +771,10 @@ class GroundFilterLO(lp.LinearOperator):
         else:
             self.nbins = int(np.max(ground)) + 1 if self.n else 0
         self.nbins = max(self.nbins, 0)
+        if self._group is not None:                       # every rank works on the same bins
+            nb = torch.tensor([self.nbins], dtype=torch.int64, device=self._g_dev.device)
+            torch.distributed.all_reduce(nb, op=torch.distributed.ReduceOp.MAX, group=self._group_arg)
+            self.nbins = int(nb.item())
         counts = self.counts_in_groundbins(self._g_dev)
         self._bins = dv.empty_f64(max(self.nbins, 1))
         G = SparseLO(self.nbins, self.n, self._g_dev)

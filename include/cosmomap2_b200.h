@@ -268,6 +268,10 @@ int cm2_amatvec_filter_poly(const int32_t *pix, const double *cos2phi, const dou
  * (counts_in_groundbins :26-46 -> cm2_hits_i64).  bins[nbins] is scratch (receives G^T v). */
 int cm2_ground_filter_apply(const int32_t *ground, int64_t nt, int64_t nbins, const int64_t *hits,
                             const double *v, double *bins, double *out, cm2_stream_t stream);
+/* second half alone, out = v - bins[g]/hits[g]: for a TOD sharded over GPUs the bin sums
+ * (cm2_pointing_apply_t with pol = 1) and the hits are summed over ranks in between */
+int cm2_ground_filter_sub(const int32_t *ground, int64_t nt, int64_t nbins, const int64_t *hits,
+                          const double *bins, const double *v, double *out, cm2_stream_t stream);
 /* reorganize_map (utilities/healpy_functions.py:50-105): out[k][obspix[p]] = map[pol*p + k] for
  * k < pol, zero elsewhere; out is pol arrays of healpix_npix = 12 nside^2 values, back to back. */
 int cm2_reorganize_map(const double *map, const int64_t *obspix, int64_t npix, int pol,
