@@ -64,24 +64,27 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
         const int64_t j0 = bs + (win - win_first[b]) * S;     // first output of this window
         const int64_t w0 = j0 - (L - 1);                      // first input sample of the window
         __syncthreads();
-        // ---- load the window, zero outside the noise block (non-circulant boundary)
-        for (int i = threadIdx.x; i < FFT_M; i += FFT_THREADS) {
+        // ---- forward FFT, decimation in frequency, natural in -> bit-reversed out.  Two radix-2
+        // stages (half-sizes 2q and q) are fused per pass: 4 points per thread stay in registers, so
+        // the shared-memory traffic and the number of barriers are halved.  The FIRST pass takes its
+        // inputs straight from global memory (zero outside the noise block: the non-circulant
+        // boundary), so the window never makes a separate trip through shared memory.
+        auto winload = [&](int i) {
             const int64_t t = w0 + 2 * (int64_t)i;
             double2 v;
             v.x = (t >= bs && t < be) ? d[t] : 0.0;
             v.y = (t + 1 >= bs && t + 1 < be) ? d[t + 1] : 0.0;
-            z(i) = v;
-        }
-        __syncthreads();
-        // ---- forward FFT, decimation in frequency, natural in -> bit-reversed out.  Two radix-2
-        // stages (half-sizes 2q and q) are fused per pass: 4 points per thread stay in registers, so
-        // the shared-memory traffic and the number of barriers are halved.
+            return v;
+        };
         for (int lq = FFT_LOG2M - 2; lq >= 0; lq -= 2) {
             const int q = 1 << lq;
+            const bool first = lq == FFT_LOG2M - 2;
             for (int j = threadIdx.x; j < FFT_M / 4; j += FFT_THREADS) {
                 const int pos = j & (q - 1);
                 const int i0 = ((j >> lq) << (lq + 2)) + pos;
-                const double2 z0 = z(i0), z1 = z(i0 + q), z2 = z(i0 + 2 * q), z3 = z(i0 + 3 * q);
+                double2 z0, z1, z2, z3;
+                if (first) { z0 = winload(i0); z1 = winload(i0 + q); z2 = winload(i0 + 2 * q); z3 = winload(i0 + 3 * q); }
+                else { z0 = z(i0); z1 = z(i0 + q); z2 = z(i0 + 2 * q); z3 = z(i0 + 3 * q); }
                 // stage with half-size 2q: pairs (0,2) and (1,3)
                 const double2 w1a = __ldg(tw + (pos << (FFT_LOG2M - 2 - lq)));
                 const double2 w1b = __ldg(tw + ((pos + q) << (FFT_LOG2M - 2 - lq)));
@@ -142,6 +145,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
         }
         for (int lq = lq0; lq < FFT_LOG2M; lq += 2) {
             const int q = 1 << lq;
+            const bool last = lq + 2 >= FFT_LOG2M;
             for (int j = threadIdx.x; j < FFT_M / 4; j += FFT_THREADS) {
                 const int pos = j & (q - 1);
                 const int i0 = ((j >> lq) << (lq + 2)) + pos;
@@ -155,19 +159,28 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                 wa.y = -wa.y;
                 wb.y = -wb.y;
                 const double2 b2 = cmul(a2, wa), b3 = cmul(a3, wb);
-                z(i0) = make_double2(a0.x + b2.x, a0.y + b2.y);
-                z(i0 + 2 * q) = make_double2(a0.x - b2.x, a0.y - b2.y);
-                z(i0 + q) = make_double2(a1.x + b3.x, a1.y + b3.y);
-                z(i0 + 3 * q) = make_double2(a1.x - b3.x, a1.y - b3.y);
+                const double2 o0 = make_double2(a0.x + b2.x, a0.y + b2.y), o2 = make_double2(a0.x - b2.x, a0.y - b2.y);
+                const double2 o1 = make_double2(a1.x + b3.x, a1.y + b3.y), o3 = make_double2(a1.x - b3.x, a1.y - b3.y);
+                if (!last) {
+                    z(i0) = o0;
+                    z(i0 + 2 * q) = o2;
+                    z(i0 + q) = o1;
+                    z(i0 + 3 * q) = o3;
+                } else {
+                    // the LAST pass produces the window in natural order: the alias-free samples, window
+                    // positions [L-1, L-1+S), go straight to global memory
+                    auto put = [&](int i, const double2 &v) {
+                        const int r0 = 2 * i - (L - 1);            // output index of v.x within the window's S outputs
+                        if (r0 >= 0 && r0 < S && j0 + r0 < be) out[j0 + r0] = v.x;
+                        if (r0 + 1 >= 0 && r0 + 1 < S && j0 + r0 + 1 < be) out[j0 + r0 + 1] = v.y;
+                    };
+                    put(i0, o0);
+                    put(i0 + q, o1);
+                    put(i0 + 2 * q, o2);
+                    put(i0 + 3 * q, o3);
+                }
             }
-            __syncthreads();
-        }
-        // ---- alias-free outputs: window positions [L-1, L-1+S)
-        for (int i = threadIdx.x; i < S; i += FFT_THREADS) {
-            const int64_t t = j0 + i;
-            const int r = L - 1 + i;
-            const double2 v = z(r >> 1);
-            if (t < be) out[t] = (r & 1) ? v.y : v.x;
+            if (!last) __syncthreads();
         }
     }
 }
