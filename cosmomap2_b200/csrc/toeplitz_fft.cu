@@ -31,13 +31,24 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
 }
 
-// tw[t] = exp(-2 pi i t / M), t in [0, M/2)
+// Twiddle tables, one compact table per fused pass so that consecutive butterflies read consecutive
+// 16-byte entries (indexing one table tw[t] = exp(-2 pi i t / M) with the stride of the pass cost up
+// to 32 L1 wavefronts per warp load and kept the LSU data pipe at 90 %; ncu, profiles/).  The pass
+// with quarter-size q = 2^lq (lq = LOG2M-2, LOG2M-4, ...) uses, for pos in [0, q):
+//   w1a = w^(pos << (LOG2M-2-lq)), w1b = w^((pos+q) << (LOG2M-2-lq)), w2 = w^(pos << (LOG2M-1-lq)),
+// stored as three arrays of q entries at offset M - 4q (the offsets telescope: 3 (q_top + ... ) ).
 __global__ void k_fft_twiddles(double2 *__restrict__ tw) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < FFT_M / 2) {
-        double s, c;
-        sincospi(-2.0 * (double)t / (double)FFT_M, &s, &c);
-        tw[t] = make_double2(c, s);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int lq = FFT_LOG2M - 2; lq >= 0; lq -= 2) {
+        const int q = 1 << lq;
+        if (i < 3 * q) {
+            const int which = i / q, pos = i - which * q;
+            const int t = which == 0 ? (pos << (FFT_LOG2M - 2 - lq))
+                        : which == 1 ? ((pos + q) << (FFT_LOG2M - 2 - lq)) : (pos << (FFT_LOG2M - 1 - lq));
+            double sn, cs;
+            sincospi(-2.0 * (double)t / (double)FFT_M, &sn, &cs);
+            tw[FFT_M - 4 * q + i] = make_double2(cs, sn);
+        }
     }
 }
 
@@ -86,14 +97,15 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                 if (first) { z0 = winload(i0); z1 = winload(i0 + q); z2 = winload(i0 + 2 * q); z3 = winload(i0 + 3 * q); }
                 else { z0 = z(i0); z1 = z(i0 + q); z2 = z(i0 + 2 * q); z3 = z(i0 + 3 * q); }
                 // stage with half-size 2q: pairs (0,2) and (1,3)
-                const double2 w1a = __ldg(tw + (pos << (FFT_LOG2M - 2 - lq)));
-                const double2 w1b = __ldg(tw + ((pos + q) << (FFT_LOG2M - 2 - lq)));
+                const double2 *pt = tw + (FFT_M - 4 * q) + pos;       // this pass's table: w1a | w1b | w2
+                const double2 w1a = __ldg(pt);
+                const double2 w1b = __ldg(pt + q);
                 const double2 a0 = make_double2(z0.x + z2.x, z0.y + z2.y);
                 const double2 a2 = cmul(make_double2(z0.x - z2.x, z0.y - z2.y), w1a);
                 const double2 a1 = make_double2(z1.x + z3.x, z1.y + z3.y);
                 const double2 a3 = cmul(make_double2(z1.x - z3.x, z1.y - z3.y), w1b);
                 // stage with half-size q: pairs (0,1) and (2,3)
-                const double2 w2 = __ldg(tw + (pos << (FFT_LOG2M - 1 - lq)));
+                const double2 w2 = __ldg(pt + 2 * q);
                 z(i0) = make_double2(a0.x + a1.x, a0.y + a1.y);
                 z(i0 + q) = cmul(make_double2(a0.x - a1.x, a0.y - a1.y), w2);
                 z(i0 + 2 * q) = make_double2(a2.x + a3.x, a2.y + a3.y);
@@ -149,13 +161,14 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             for (int j = threadIdx.x; j < FFT_M / 4; j += FFT_THREADS) {
                 const int pos = j & (q - 1);
                 const int i0 = ((j >> lq) << (lq + 2)) + pos;
-                double2 w = __ldg(tw + (pos << (FFT_LOG2M - 1 - lq)));       // half-size q
+                const double2 *pt = tw + (FFT_M - 4 * q) + pos;       // this pass's table: w1a | w1b | w2
+                double2 w = __ldg(pt + 2 * q);                               // half-size q
                 w.y = -w.y;
                 const double2 z0 = z(i0), z1 = cmul(z(i0 + q), w), z2 = z(i0 + 2 * q), z3 = cmul(z(i0 + 3 * q), w);
                 const double2 a0 = make_double2(z0.x + z1.x, z0.y + z1.y), a1 = make_double2(z0.x - z1.x, z0.y - z1.y);
                 const double2 a2 = make_double2(z2.x + z3.x, z2.y + z3.y), a3 = make_double2(z2.x - z3.x, z2.y - z3.y);
-                double2 wa = __ldg(tw + (pos << (FFT_LOG2M - 2 - lq)));       // half-size 2q, position pos
-                double2 wb = __ldg(tw + ((pos + q) << (FFT_LOG2M - 2 - lq))); // half-size 2q, position pos+q
+                double2 wa = __ldg(pt);                                      // half-size 2q, position pos
+                double2 wb = __ldg(pt + q);                                  // half-size 2q, position pos+q
                 wa.y = -wa.y;
                 wb.y = -wb.y;
                 const double2 b2 = cmul(a2, wa), b3 = cmul(a3, wb);
@@ -208,7 +221,7 @@ using namespace cm2;
 extern "C" int cm2_toeplitz_fft_points(void) { return FFT_M; }
 
 extern "C" int64_t cm2_toeplitz_fft_scratch_bytes(int64_t nblocks) {
-    return (nblocks + 1) * (int64_t)sizeof(int64_t) + (int64_t)(FFT_M / 2) * (int64_t)sizeof(double2) + 64;
+    return (nblocks + 1) * (int64_t)sizeof(int64_t) + (int64_t)FFT_M * (int64_t)sizeof(double2) + 64;
 }
 
 // coef: device, [nblocks][2][M] complex (C1, C2 stored at the bit-reversed position of their frequency, 1/M folded in);
@@ -224,9 +237,9 @@ extern "C" int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64
     if (nt == 0) return CM2_OK;
     cudaStream_t st = as_stream(stream);
     double2 *tw = reinterpret_cast<double2 *>(scratch);
-    int64_t *win_first = reinterpret_cast<int64_t *>(reinterpret_cast<char *>(scratch) + (FFT_M / 2) * sizeof(double2));
+    int64_t *win_first = reinterpret_cast<int64_t *>(reinterpret_cast<char *>(scratch) + FFT_M * sizeof(double2));
     if (init) {
-        k_fft_twiddles<<<(FFT_M / 2 + 255) / 256, 256, 0, st>>>(tw);
+        k_fft_twiddles<<<(3 * (FFT_M / 4) + 255) / 256, 256, 0, st>>>(tw);
         CM2_LAUNCHED();
     }
     const int S = FFT_NF - 2 * (nband - 1);
