@@ -121,27 +121,32 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             }
             __syncthreads();
         }
-        // ---- transfer function on the packed spectrum, pairs (k, M-k) in bit-reversed storage.
-        // Threads walk PHYSICAL positions (pk = t consecutive -> no bank conflicts; walking k made
-        // all 32 lanes hit one bank) and the coefficient tables are stored by physical position.
+        // ---- transfer function on the packed spectrum, in bit-reversed storage.  Every thread walks
+        // PHYSICAL positions pk (consecutive lanes -> consecutive elements and coefficients: the
+        // coefficient tables are stored by physical position) and computes W[k] alone, reading its
+        // partner Z[M-k] but not the partner's coefficients (the first version handled the pair
+        // (k, M-k) in one thread and paid two scattered 16-byte global loads per pair for them).
+        // All reads, a barrier, then all writes: the update is in place.
         const double2 *c1 = coef + (int64_t)b * 2 * FFT_M;
         const double2 *c2 = c1 + FFT_M;
-        for (int pk = threadIdx.x; pk < FFT_M; pk += FFT_THREADS) {
+        constexpr int NPOS = FFT_M / FFT_THREADS;
+        double2 res[NPOS];
+#pragma unroll
+        for (int i = 0; i < NPOS; ++i) {
+            const int pk = threadIdx.x + i * FFT_THREADS;
             const int k = __brev((unsigned)pk) >> (32 - FFT_LOG2M);
             const int km = (FFT_M - k) & (FFT_M - 1);
-            if (k > km) continue;                       // each pair once
             const int pm = __brev((unsigned)km) >> (32 - FFT_LOG2M);
             const double2 zk = z(pk), zm = z(pm);
             // E[k] = (Z[k] + conj Z[M-k])/2 ; O[k] = (Z[k] - conj Z[M-k])/(2i)
             const double2 Ek = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
             const double2 Ok = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
-            const double2 Em = make_double2(Ek.x, -Ek.y);   // E[M-k] = conj E[k]
-            const double2 Om = make_double2(Ok.x, -Ok.y);   // O[M-k] = conj O[k]
             const double2 a1 = cmul(__ldg(c1 + pk), Ek), a2 = cmul(__ldg(c2 + pk), Ok);
-            const double2 b1 = cmul(__ldg(c1 + pm), Em), b2 = cmul(__ldg(c2 + pm), Om);
-            z(pk) = make_double2(a1.x + a2.x, a1.y + a2.y);
-            if (km != k) z(pm) = make_double2(b1.x + b2.x, b1.y + b2.y);
+            res[i] = make_double2(a1.x + a2.x, a1.y + a2.y);
         }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < NPOS; ++i) z(threadIdx.x + i * FFT_THREADS) = res[i];
         __syncthreads();
         // ---- inverse FFT, decimation in time, bit-reversed in -> natural out (conjugate twiddles),
         // again two radix-2 stages (half-sizes q and 2q) per pass
