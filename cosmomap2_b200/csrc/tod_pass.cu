@@ -523,6 +523,7 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter(const int32_t *__restr
         double sum = 0.0, cnt = 0.0;
         for (int64_t tile = tile0 + warp; tile < tile1; tile += BLOCK / 32) {
             const int64_t t0 = tile * TILE + (int64_t)lane * K;
+                const int tb = (int)(tile * TILE - base);            // conflict-free layout: (lane, j) -> tb + 32 j + lane
             int p[K];
             double c[K], s[K], xv[K][POL];
             load_pix_keep(pix, t0, nt, p);
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter(const int32_t *__restr
             for (int j = 0; j < K; ++j) {
                 const double dv = p[j] >= 0 ? project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0) : 0.0;
                 if (p[j] >= 0) { sum += dv; cnt += 1.0; }
-                if (fits) sd[t0 + j - base] = dv;
+                if (fits) sd[tb + j * 32 + lane] = dv;
             }
         }
         const double tsum = block_sum(sum, red);
@@ -548,6 +549,7 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter(const int32_t *__restr
             const double mu = s_mean;
             for (int64_t tile = tile0 + warp; tile < tile1; tile += BLOCK / 32) {
                 const int64_t t0 = tile * TILE + (int64_t)lane * K;
+                const int tb = (int)(tile * TILE - base);            // conflict-free layout: (lane, j) -> tb + 32 j + lane
                 int p[K];
                 double c[K], s[K], v[K];
                 load_pix(pix, t0, nt, p);
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter(const int32_t *__restr
                 if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
                 if (fits) {
 #pragma unroll
-                    for (int j = 0; j < K; ++j) v[j] = sd[t0 + j - base] - mu;
+                    for (int j = 0; j < K; ++j) v[j] = sd[tb + j * 32 + lane] - mu;
                 } else {
                     double xv[K][POL];
                     gather_x<POL>(x, p, xv);
@@ -617,6 +619,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
         for (int i = 0; i < NR; ++i) acc[i] = 0.0;
         for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
             const int64_t t0 = tile * TILE + (int64_t)lane * K;
+                const int tb = (int)(tile * TILE - base);            // conflict-free layout: (lane, j) -> tb + 32 j + lane
             const double jb = (double)(int)(t0 - a);
             int p[K];
             double c[K], s[K], xv[K][POL];
@@ -625,7 +628,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 if (t0 + j < a || t0 + j >= b || p[j] < 0) p[j] = -1;
-                sp[t0 + j - base] = p[j];
+                sp[tb + j * 32 + lane] = p[j];
             }
             gather_x<POL>(x, p, xv);
 #pragma unroll
@@ -647,7 +650,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
                         for (int l = r; l < NK; ++l) { acc[q] = fma(L[r], L[l], acc[q]); ++q; }
                     }
                 }
-                sd[t0 + j - base] = dv;
+                sd[tb + j * 32 + lane] = dv;
             }
         }
         cnt = __reduce_add_sync(FULL, cnt);
@@ -687,11 +690,12 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
                 for (int i = 0; i < NR; ++i) acc[i] = 0.0;
                 for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
                     const int64_t t0 = tile * TILE + (int64_t)lane * K;
+                const int tb = (int)(tile * TILE - base);            // conflict-free layout: (lane, j) -> tb + 32 j + lane
                     const double jb = (double)((int)(t0 - a) - j0);
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
-                        if (sp[t0 + j - base] < 0) continue;
-                        const double dv = sd[t0 + j - base];
+                        if (sp[tb + j * 32 + lane] < 0) continue;
+                        const double dv = sd[tb + j * 32 + lane];
                         double L[NK];
                         legendre<NK>(fma(jb + (double)j, step, -1.0), L);
                         int q = NK;
@@ -718,13 +722,14 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
                     for (int r = 0; r < NK; ++r) { cc[r] = coef[r]; racc[r] = 0.0; }
                     for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
                         const int64_t t0 = tile * TILE + (int64_t)lane * K;
+                const int tb = (int)(tile * TILE - base);            // conflict-free layout: (lane, j) -> tb + 32 j + lane
                         const double jb = (double)((int)(t0 - a) - j0);
 #pragma unroll
                         for (int j = 0; j < K; ++j) {
-                            if (sp[t0 + j - base] < 0) continue;
+                            if (sp[tb + j * 32 + lane] < 0) continue;
                             double L[NK];
                             legendre<NK>(fma(jb + (double)j, step, -1.0), L);
-                            double res = sd[t0 + j - base];
+                            double res = sd[tb + j * 32 + lane];
 #pragma unroll
                             for (int r = 0; r < NK; ++r) res = fma(-cc[r], L[r], res);
 #pragma unroll
@@ -747,11 +752,12 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
             for (int r = 0; r < NK; ++r) cf[r] = coef[r];
             for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
                 const int64_t t0 = tile * TILE + (int64_t)lane * K;
+                const int tb = (int)(tile * TILE - base);            // conflict-free layout: (lane, j) -> tb + 32 j + lane
                 const double jb = (double)((int)(t0 - a) - j0);
                 int p[K];
                 double c[K], s[K], v[K];
 #pragma unroll
-                for (int j = 0; j < K; ++j) p[j] = sp[t0 + j - base];
+                for (int j = 0; j < K; ++j) p[j] = sp[tb + j * 32 + lane];
                 if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
@@ -760,7 +766,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
                     double pj = 0.0;
 #pragma unroll
                     for (int r = 0; r < NK; ++r) pj = fma(cf[r], L[r], pj);
-                    v[j] = sd[t0 + j - base] - pj;
+                    v[j] = sd[tb + j * 32 + lane] - pj;
                 }
                 run_scatter<POL, POL>(y, p, [&](int j, double (&o)[POL]) {
                     if constexpr (POL == 1) { o[0] = v[j]; }
