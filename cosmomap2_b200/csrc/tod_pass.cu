@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter(const int32_t *__restr
         double sum = 0.0, cnt = 0.0;
         for (int64_t tile = tile0 + warp; tile < tile1; tile += BLOCK / 32) {
             const int64_t t0 = tile * TILE + (int64_t)lane * K;
-                const int tb = (int)(tile * TILE - base);            // conflict-free layout: (lane, j) -> tb + 32 j + lane
+            const int tb = (int)(tile * TILE - base);   // bank-conflict-free tile layout: (lane, j) at tb + 32 j + lane
             int p[K];
             double c[K], s[K], xv[K][POL];
             load_pix_keep(pix, t0, nt, p);
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter(const int32_t *__restr
             const double mu = s_mean;
             for (int64_t tile = tile0 + warp; tile < tile1; tile += BLOCK / 32) {
                 const int64_t t0 = tile * TILE + (int64_t)lane * K;
-                const int tb = (int)(tile * TILE - base);            // conflict-free layout: (lane, j) -> tb + 32 j + lane
+                const int tb = (int)(tile * TILE - base);
                 int p[K];
                 double c[K], s[K], v[K];
                 load_pix(pix, t0, nt, p);
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
         for (int i = 0; i < NR; ++i) acc[i] = 0.0;
         for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
             const int64_t t0 = tile * TILE + (int64_t)lane * K;
-                const int tb = (int)(tile * TILE - base);            // conflict-free layout: (lane, j) -> tb + 32 j + lane
+            const int tb = (int)(tile * TILE - base);
             const double jb = (double)(int)(t0 - a);
             int p[K];
             double c[K], s[K], xv[K][POL];
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
                 for (int i = 0; i < NR; ++i) acc[i] = 0.0;
                 for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
                     const int64_t t0 = tile * TILE + (int64_t)lane * K;
-                const int tb = (int)(tile * TILE - base);            // conflict-free layout: (lane, j) -> tb + 32 j + lane
+                    const int tb = (int)(tile * TILE - base);
                     const double jb = (double)((int)(t0 - a) - j0);
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
@@ -722,7 +722,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
                     for (int r = 0; r < NK; ++r) { cc[r] = coef[r]; racc[r] = 0.0; }
                     for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
                         const int64_t t0 = tile * TILE + (int64_t)lane * K;
-                const int tb = (int)(tile * TILE - base);            // conflict-free layout: (lane, j) -> tb + 32 j + lane
+                        const int tb = (int)(tile * TILE - base);
                         const double jb = (double)((int)(t0 - a) - j0);
 #pragma unroll
                         for (int j = 0; j < K; ++j) {
@@ -752,7 +752,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_amatvec_filter_poly(const int32_t 
             for (int r = 0; r < NK; ++r) cf[r] = coef[r];
             for (int64_t tile = tile0 + warp; tile < tile1; tile += NW) {
                 const int64_t t0 = tile * TILE + (int64_t)lane * K;
-                const int tb = (int)(tile * TILE - base);            // conflict-free layout: (lane, j) -> tb + 32 j + lane
+                const int tb = (int)(tile * TILE - base);
                 const double jb = (double)((int)(t0 - a) - j0);
                 int p[K];
                 double c[K], s[K], v[K];
