@@ -97,15 +97,16 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                 if (first) { z0 = winload(i0); z1 = winload(i0 + q); z2 = winload(i0 + 2 * q); z3 = winload(i0 + 3 * q); }
                 else { z0 = z(i0); z1 = z(i0 + q); z2 = z(i0 + 2 * q); z3 = z(i0 + 3 * q); }
                 // stage with half-size 2q: pairs (0,2) and (1,3)
-                const double2 *pt = tw + (FFT_M - 4 * q) + pos;       // this pass's table: w1a | w1b | w2
-                const double2 w1a = __ldg(pt);
-                const double2 w1b = __ldg(pt + q);
+                // ONE twiddle load per butterfly: w1b = w^(t + M/4) = -i w1a and w2 = w1a^2 are derived (the
+                // LSU data pipe, not the fp64 pipe, bounds this kernel)
+                const double2 w1a = __ldg(tw + (FFT_M - 4 * q) + pos);
+                const double2 w1b = make_double2(w1a.y, -w1a.x);
                 const double2 a0 = make_double2(z0.x + z2.x, z0.y + z2.y);
                 const double2 a2 = cmul(make_double2(z0.x - z2.x, z0.y - z2.y), w1a);
                 const double2 a1 = make_double2(z1.x + z3.x, z1.y + z3.y);
                 const double2 a3 = cmul(make_double2(z1.x - z3.x, z1.y - z3.y), w1b);
                 // stage with half-size q: pairs (0,1) and (2,3)
-                const double2 w2 = __ldg(pt + 2 * q);
+                const double2 w2 = cmul(w1a, w1a);
                 z(i0) = make_double2(a0.x + a1.x, a0.y + a1.y);
                 z(i0 + q) = cmul(make_double2(a0.x - a1.x, a0.y - a1.y), w2);
                 z(i0 + 2 * q) = make_double2(a2.x + a3.x, a2.y + a3.y);
@@ -166,16 +167,13 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             for (int j = threadIdx.x; j < FFT_M / 4; j += FFT_THREADS) {
                 const int pos = j & (q - 1);
                 const int i0 = ((j >> lq) << (lq + 2)) + pos;
-                const double2 *pt = tw + (FFT_M - 4 * q) + pos;       // this pass's table: w1a | w1b | w2
-                double2 w = __ldg(pt + 2 * q);                               // half-size q
-                w.y = -w.y;
+                double2 wa = __ldg(tw + (FFT_M - 4 * q) + pos);              // half-size 2q, position pos
+                wa.y = -wa.y;                                                // inverse transform: conjugates
+                const double2 wb = make_double2(-wa.y, wa.x);                // conj(-i w1a) = i conj(w1a)
+                const double2 w = cmul(wa, wa);                              // half-size q
                 const double2 z0 = z(i0), z1 = cmul(z(i0 + q), w), z2 = z(i0 + 2 * q), z3 = cmul(z(i0 + 3 * q), w);
                 const double2 a0 = make_double2(z0.x + z1.x, z0.y + z1.y), a1 = make_double2(z0.x - z1.x, z0.y - z1.y);
                 const double2 a2 = make_double2(z2.x + z3.x, z2.y + z3.y), a3 = make_double2(z2.x - z3.x, z2.y - z3.y);
-                double2 wa = __ldg(pt);                                      // half-size 2q, position pos
-                double2 wb = __ldg(pt + q);                                  // half-size 2q, position pos+q
-                wa.y = -wa.y;
-                wb.y = -wb.y;
                 const double2 b2 = cmul(a2, wa), b3 = cmul(a3, wb);
                 const double2 o0 = make_double2(a0.x + b2.x, a0.y + b2.y), o2 = make_double2(a0.x - b2.x, a0.y - b2.y);
                 const double2 o1 = make_double2(a1.x + b3.x, a1.y + b3.y), o3 = make_double2(a1.x - b3.x, a1.y - b3.y);
