@@ -4,7 +4,7 @@
 // zero boundaries: 2(2L-1) flop/sample done directly, i.e. 16 382 flop/sample at the L = 4096 of
 // configs[2] -- 100x more time than the 16 B/sample of HBM traffic.  Here each CTA takes one window
 // of NF = 2M real samples (M complex points, 128 kB of shared memory), runs an in-place DIF FFT
-// (radix-2 stages fused in pairs, i.e. radix-4 passes; output bit-reversed), applies the real, even transfer function of the band in the
+// (radix-2 stages fused in threes, i.e. radix-8 passes; output bit-reversed), applies the real, even transfer function of the band in the
 // bit-reversed domain, runs the inverse in-place DIT FFT (input bit-reversed, output natural) and
 // writes the NF - 2(L-1) alias-free outputs.  No reordering pass, no global scratch.
 //
@@ -15,8 +15,8 @@
 // is the packed spectrum of the filtered window (derivation in DESIGN.md); C1 = Hs + i Hd w^-k and
 // C2 = Hd w^k + i Hs are precomputed per noise block on the host, 1/M folded in.
 //
-// Bound: shared-memory bandwidth (each fused pass moves 128 B per 4-point butterfly, 7 passes per
-// transform), ~60x fewer flops than the direct form at L = 4096.
+// Bound: the L1/shared-memory data pipe (each fused pass moves 256 B per 8-point butterfly, 4 passes + one
+// radix-2 stage per transform), ~60x fewer flops than the direct form at L = 4096.
 #include <cstdlib>
 
 #include "cm2_common.cuh"
@@ -31,25 +31,40 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
 }
 
-// Twiddle tables, one compact table per fused pass so that consecutive butterflies read consecutive
+// Twiddle tables: one compact table per pass so that consecutive butterflies read consecutive
 // 16-byte entries (indexing one table tw[t] = exp(-2 pi i t / M) with the stride of the pass cost up
-// to 32 L1 wavefronts per warp load and kept the LSU data pipe at 90 %; ncu, profiles/).  The pass
-// with quarter-size q = 2^lq (lq = LOG2M-2, LOG2M-4, ...) uses, for pos in [0, q):
-//   w1a = w^(pos << (LOG2M-2-lq)), w1b = w^((pos+q) << (LOG2M-2-lq)), w2 = w^(pos << (LOG2M-1-lq)),
-// stored as three arrays of q entries at offset M - 4q (the offsets telescope: 3 (q_top + ... ) ).
+// to 32 L1 wavefronts per warp load and kept the LSU data pipe at 90 %; ncu, profiles/).  A radix-8
+// pass with eighth-size q = 2^lq needs ONE entry per butterfly, w8 = exp(-2 pi i pos / (8 q)) for
+// pos in [0, q), stored at tw[q + pos]; every other twiddle of the pass follows from it:
+//   half-size 4q: w8 * exp(-2 pi i m/8), m = 0..3   half-size 2q: w8^2, -i w8^2   half-size q: w8^4
 __global__ void k_fft_twiddles(double2 *__restrict__ tw) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int lq = FFT_LOG2M - 2; lq >= 0; lq -= 2) {
-        const int q = 1 << lq;
-        if (i < 3 * q) {
-            const int which = i / q, pos = i - which * q;
-            const int t = which == 0 ? (pos << (FFT_LOG2M - 2 - lq))
-                        : which == 1 ? ((pos + q) << (FFT_LOG2M - 2 - lq)) : (pos << (FFT_LOG2M - 1 - lq));
-            double sn, cs;
-            sincospi(-2.0 * (double)t / (double)FFT_M, &sn, &cs);
-            tw[FFT_M - 4 * q + i] = make_double2(cs, sn);
-        }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // i = q + pos
+    if (i >= 1 && i < FFT_M / 4) {
+        const int lq = 31 - __clz(i);
+        const int q = 1 << lq, pos = i - q;
+        double sn, cs;
+        sincospi(-2.0 * (double)pos / (double)(8 * q), &sn, &cs);
+        tw[i] = make_double2(cs, sn);
     }
+}
+
+// x * (1 - i)/sqrt2, x * (-i), x * (-1 - i)/sqrt2 and their conjugate counterparts
+__device__ __forceinline__ double2 rot1(double2 x) { return make_double2(0.70710678118654752440 * (x.x + x.y), 0.70710678118654752440 * (x.y - x.x)); }
+__device__ __forceinline__ double2 rot2(double2 x) { return make_double2(x.y, -x.x); }
+__device__ __forceinline__ double2 rot3(double2 x) { return make_double2(0.70710678118654752440 * (x.y - x.x), -0.70710678118654752440 * (x.x + x.y)); }
+__device__ __forceinline__ double2 rot1c(double2 x) { return make_double2(0.70710678118654752440 * (x.x - x.y), 0.70710678118654752440 * (x.x + x.y)); }
+__device__ __forceinline__ double2 rot2c(double2 x) { return make_double2(-x.y, x.x); }
+__device__ __forceinline__ double2 rot3c(double2 x) { return make_double2(-0.70710678118654752440 * (x.x + x.y), 0.70710678118654752440 * (x.x - x.y)); }
+// decimation-in-frequency butterfly: (a, b) -> (a + b, (a - b) w); decimation in time: (a, b) -> (a + b w, a - b w)
+__device__ __forceinline__ void dif(double2 &a, double2 &b, double2 w) {
+    const double2 t = make_double2(a.x - b.x, a.y - b.y);
+    a = make_double2(a.x + b.x, a.y + b.y);
+    b = cmul(t, w);
+}
+__device__ __forceinline__ void dit(double2 &a, double2 &b, double2 w) {
+    const double2 t = cmul(b, w);
+    b = make_double2(a.x - t.x, a.y - t.y);
+    a = make_double2(a.x + t.x, a.y + t.y);
 }
 
 // one CTA per window.  win_first[b] = first window index of noise block b (prefix, nblocks+1).
@@ -75,11 +90,12 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
         const int64_t j0 = bs + (win - win_first[b]) * S;     // first output of this window
         const int64_t w0 = j0 - (L - 1);                      // first input sample of the window
         __syncthreads();
-        // ---- forward FFT, decimation in frequency, natural in -> bit-reversed out.  Two radix-2
-        // stages (half-sizes 2q and q) are fused per pass: 4 points per thread stay in registers, so
-        // the shared-memory traffic and the number of barriers are halved.  The FIRST pass takes its
-        // inputs straight from global memory (zero outside the noise block: the non-circulant
-        // boundary), so the window never makes a separate trip through shared memory.
+        // ---- forward FFT, decimation in frequency, natural in -> bit-reversed out.  Three radix-2
+        // stages (half-sizes 4q, 2q, q) are fused per pass: 8 points per butterfly stay in registers, so
+        // a transform makes 4 passes through shared memory (+ the last radix-2 stage) instead of 13.
+        // The FIRST pass takes its inputs straight from global memory (zero outside the noise block:
+        // the non-circulant boundary), so the window never makes a separate trip through shared memory.
+        static_assert(FFT_LOG2M % 3 == 1, "radix-8 passes + one radix-2 stage");
         auto winload = [&](int i) {
             const int64_t t = w0 + 2 * (int64_t)i;
             double2 v;
@@ -87,34 +103,36 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             v.y = (t + 1 >= bs && t + 1 < be) ? d[t + 1] : 0.0;
             return v;
         };
-        for (int lq = FFT_LOG2M - 2; lq >= 0; lq -= 2) {
+        for (int lq = FFT_LOG2M - 3; lq >= 0; lq -= 3) {
             const int q = 1 << lq;
-            const bool first = lq == FFT_LOG2M - 2;
-            for (int j = threadIdx.x; j < FFT_M / 4; j += FFT_THREADS) {
+            const bool first = lq == FFT_LOG2M - 3;
+            for (int j = threadIdx.x; j < FFT_M / 8; j += FFT_THREADS) {
                 const int pos = j & (q - 1);
-                const int i0 = ((j >> lq) << (lq + 2)) + pos;
-                double2 z0, z1, z2, z3;
-                if (first) { z0 = winload(i0); z1 = winload(i0 + q); z2 = winload(i0 + 2 * q); z3 = winload(i0 + 3 * q); }
-                else { z0 = z(i0); z1 = z(i0 + q); z2 = z(i0 + 2 * q); z3 = z(i0 + 3 * q); }
-                // stage with half-size 2q: pairs (0,2) and (1,3)
-                // ONE twiddle load per butterfly: w1b = w^(t + M/4) = -i w1a and w2 = w1a^2 are derived (the
-                // LSU data pipe, not the fp64 pipe, bounds this kernel)
-                const double2 w1a = __ldg(tw + (FFT_M - 4 * q) + pos);
-                const double2 w1b = make_double2(w1a.y, -w1a.x);
-                const double2 a0 = make_double2(z0.x + z2.x, z0.y + z2.y);
-                const double2 a2 = cmul(make_double2(z0.x - z2.x, z0.y - z2.y), w1a);
-                const double2 a1 = make_double2(z1.x + z3.x, z1.y + z3.y);
-                const double2 a3 = cmul(make_double2(z1.x - z3.x, z1.y - z3.y), w1b);
-                // stage with half-size q: pairs (0,1) and (2,3)
-                const double2 w2 = cmul(w1a, w1a);
-                z(i0) = make_double2(a0.x + a1.x, a0.y + a1.y);
-                z(i0 + q) = cmul(make_double2(a0.x - a1.x, a0.y - a1.y), w2);
-                z(i0 + 2 * q) = make_double2(a2.x + a3.x, a2.y + a3.y);
-                z(i0 + 3 * q) = cmul(make_double2(a2.x - a3.x, a2.y - a3.y), w2);
+                const int i0 = ((j >> lq) << (lq + 3)) + pos;
+                double2 v[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) v[m] = first ? winload(i0 + m * q) : z(i0 + m * q);
+                const double2 w8 = __ldg(tw + q + pos);
+                const double2 w4 = cmul(w8, w8), w2 = cmul(w4, w4);
+                dif(v[0], v[4], w8);                       // half-size 4q
+                dif(v[1], v[5], rot1(w8));
+                dif(v[2], v[6], rot2(w8));
+                dif(v[3], v[7], rot3(w8));
+                const double2 w4r = rot2(w4);
+                dif(v[0], v[2], w4);                       // half-size 2q
+                dif(v[1], v[3], w4r);
+                dif(v[4], v[6], w4);
+                dif(v[5], v[7], w4r);
+                dif(v[0], v[1], w2);                       // half-size q
+                dif(v[2], v[3], w2);
+                dif(v[4], v[5], w2);
+                dif(v[6], v[7], w2);
+#pragma unroll
+                for (int m = 0; m < 8; ++m) z(i0 + m * q) = v[m];
             }
             __syncthreads();
         }
-        if (FFT_LOG2M & 1) {   // odd number of stages: one last radix-2 stage with half-size 1
+        if (FFT_LOG2M % 3 == 1) {   // the remaining radix-2 stage with half-size 1
             for (int j = threadIdx.x; j < FFT_M / 2; j += FFT_THREADS) {
                 const double2 a = z(2 * j), bb = z(2 * j + 1);
                 z(2 * j) = make_double2(a.x + bb.x, a.y + bb.y);
@@ -150,9 +168,9 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
         for (int i = 0; i < NPOS; ++i) z(threadIdx.x + i * FFT_THREADS) = res[i];
         __syncthreads();
         // ---- inverse FFT, decimation in time, bit-reversed in -> natural out (conjugate twiddles),
-        // again two radix-2 stages (half-sizes q and 2q) per pass
+        // again three radix-2 stages (half-sizes q, 2q, 4q) per pass
         int lq0 = 0;
-        if (FFT_LOG2M & 1) {   // the stage with half-size 1 first
+        if (FFT_LOG2M % 3 == 1) {   // the stage with half-size 1 first
             for (int j = threadIdx.x; j < FFT_M / 2; j += FFT_THREADS) {
                 const double2 a = z(2 * j), bb = z(2 * j + 1);
                 z(2 * j) = make_double2(a.x + bb.x, a.y + bb.y);
@@ -161,39 +179,43 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             __syncthreads();
             lq0 = 1;
         }
-        for (int lq = lq0; lq < FFT_LOG2M; lq += 2) {
+        for (int lq = lq0; lq < FFT_LOG2M; lq += 3) {
             const int q = 1 << lq;
-            const bool last = lq + 2 >= FFT_LOG2M;
-            for (int j = threadIdx.x; j < FFT_M / 4; j += FFT_THREADS) {
+            const bool last = lq + 3 >= FFT_LOG2M;
+            for (int j = threadIdx.x; j < FFT_M / 8; j += FFT_THREADS) {
                 const int pos = j & (q - 1);
-                const int i0 = ((j >> lq) << (lq + 2)) + pos;
-                double2 wa = __ldg(tw + (FFT_M - 4 * q) + pos);              // half-size 2q, position pos
-                wa.y = -wa.y;                                                // inverse transform: conjugates
-                const double2 wb = make_double2(-wa.y, wa.x);                // conj(-i w1a) = i conj(w1a)
-                const double2 w = cmul(wa, wa);                              // half-size q
-                const double2 z0 = z(i0), z1 = cmul(z(i0 + q), w), z2 = z(i0 + 2 * q), z3 = cmul(z(i0 + 3 * q), w);
-                const double2 a0 = make_double2(z0.x + z1.x, z0.y + z1.y), a1 = make_double2(z0.x - z1.x, z0.y - z1.y);
-                const double2 a2 = make_double2(z2.x + z3.x, z2.y + z3.y), a3 = make_double2(z2.x - z3.x, z2.y - z3.y);
-                const double2 b2 = cmul(a2, wa), b3 = cmul(a3, wb);
-                const double2 o0 = make_double2(a0.x + b2.x, a0.y + b2.y), o2 = make_double2(a0.x - b2.x, a0.y - b2.y);
-                const double2 o1 = make_double2(a1.x + b3.x, a1.y + b3.y), o3 = make_double2(a1.x - b3.x, a1.y - b3.y);
+                const int i0 = ((j >> lq) << (lq + 3)) + pos;
+                double2 v[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) v[m] = z(i0 + m * q);
+                double2 w8 = __ldg(tw + q + pos);
+                w8.y = -w8.y;                                               // inverse transform: conjugates
+                const double2 w4 = cmul(w8, w8), w2 = cmul(w4, w4);
+                dit(v[0], v[1], w2);                       // half-size q
+                dit(v[2], v[3], w2);
+                dit(v[4], v[5], w2);
+                dit(v[6], v[7], w2);
+                const double2 w4r = rot2c(w4);
+                dit(v[0], v[2], w4);                       // half-size 2q
+                dit(v[1], v[3], w4r);
+                dit(v[4], v[6], w4);
+                dit(v[5], v[7], w4r);
+                dit(v[0], v[4], w8);                       // half-size 4q
+                dit(v[1], v[5], rot1c(w8));
+                dit(v[2], v[6], rot2c(w8));
+                dit(v[3], v[7], rot3c(w8));
                 if (!last) {
-                    z(i0) = o0;
-                    z(i0 + 2 * q) = o2;
-                    z(i0 + q) = o1;
-                    z(i0 + 3 * q) = o3;
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) z(i0 + m * q) = v[m];
                 } else {
                     // the LAST pass produces the window in natural order: the alias-free samples, window
                     // positions [L-1, L-1+S), go straight to global memory
-                    auto put = [&](int i, const double2 &v) {
-                        const int r0 = 2 * i - (L - 1);            // output index of v.x within the window's S outputs
-                        if (r0 >= 0 && r0 < S && j0 + r0 < be) out[j0 + r0] = v.x;
-                        if (r0 + 1 >= 0 && r0 + 1 < S && j0 + r0 + 1 < be) out[j0 + r0 + 1] = v.y;
-                    };
-                    put(i0, o0);
-                    put(i0 + q, o1);
-                    put(i0 + 2 * q, o2);
-                    put(i0 + 3 * q, o3);
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        const int r0 = 2 * (i0 + m * q) - (L - 1);    // output index of v.x within the window's S outputs
+                        if (r0 >= 0 && r0 < S && j0 + r0 < be) out[j0 + r0] = v[m].x;
+                        if (r0 + 1 >= 0 && r0 + 1 < S && j0 + r0 + 1 < be) out[j0 + r0 + 1] = v[m].y;
+                    }
                 }
             }
             if (!last) __syncthreads();
@@ -242,7 +264,7 @@ extern "C" int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64
     double2 *tw = reinterpret_cast<double2 *>(scratch);
     int64_t *win_first = reinterpret_cast<int64_t *>(reinterpret_cast<char *>(scratch) + FFT_M * sizeof(double2));
     if (init) {
-        k_fft_twiddles<<<(3 * (FFT_M / 4) + 255) / 256, 256, 0, st>>>(tw);
+        k_fft_twiddles<<<(FFT_M / 4 + 255) / 256, 256, 0, st>>>(tw);
         CM2_LAUNCHED();
     }
     const int S = FFT_NF - 2 * (nband - 1);
