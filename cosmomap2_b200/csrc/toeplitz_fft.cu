@@ -4,7 +4,7 @@
 // zero boundaries: 2(2L-1) flop/sample done directly, i.e. 16 382 flop/sample at the L = 4096 of
 // configs[2] -- 100x more time than the 16 B/sample of HBM traffic.  Here each CTA takes one window
 // of NF = 2M real samples (M complex points, 128 kB of shared memory), runs an in-place DIF FFT
-// (radix-2 stages fused in threes, i.e. radix-8 passes; output bit-reversed), applies the real, even transfer function of the band in the
+// (radix-2 stages fused into one radix-16 and three radix-8 passes; output bit-reversed), applies the real, even transfer function of the band in the
 // bit-reversed domain, runs the inverse in-place DIT FFT (input bit-reversed, output natural) and
 // writes the NF - 2(L-1) alias-free outputs.  No reordering pass, no global scratch.
 //
@@ -15,8 +15,9 @@
 // is the packed spectrum of the filtered window (derivation in DESIGN.md); C1 = Hs + i Hd w^-k and
 // C2 = Hd w^k + i Hs are precomputed per noise block on the host, 1/M folded in.
 //
-// Bound: the L1/shared-memory data pipe (each fused pass moves 256 B per 8-point butterfly, 4 passes + one
-// radix-2 stage per transform), ~60x fewer flops than the direct form at L = 4096.
+// Bound: the L1/shared-memory data pipe (each fused pass moves 32 B per point, 4 passes per transform, the
+// first and the last of the window fused with the global load / store), ~60x fewer flops than the direct
+// form at L = 4096.
 #include <cstdlib>
 
 #include "cm2_common.cuh"
@@ -46,6 +47,11 @@ __global__ void k_fft_twiddles(double2 *__restrict__ tw) {
         sincospi(-2.0 * (double)pos / (double)(8 * q), &sn, &cs);
         tw[i] = make_double2(cs, sn);
     }
+    if (i < FFT_M / 16) {     // radix-16 first / last pass: w16 = exp(-2 pi i pos / M) at tw[M/4 + pos]
+        double sn, cs;
+        sincospi(-2.0 * (double)i / (double)FFT_M, &sn, &cs);
+        tw[FFT_M / 4 + i] = make_double2(cs, sn);
+    }
 }
 
 // x * (1 - i)/sqrt2, x * (-i), x * (-1 - i)/sqrt2 and their conjugate counterparts
@@ -66,6 +72,52 @@ __device__ __forceinline__ void dit(double2 &a, double2 &b, double2 w) {
     b = make_double2(a.x - t.x, a.y - t.y);
     a = make_double2(a.x + t.x, a.y + t.y);
 }
+
+// x * (cr + i ci)
+__device__ __forceinline__ double2 rotc(double2 x, double cr, double ci) {
+    return make_double2(fma(x.x, cr, -x.y * ci), fma(x.x, ci, x.y * cr));
+}
+constexpr double C16 = 0.92387953251128675613, S16 = 0.38268343236508977173, R2H = 0.70710678118654752440;
+
+// The 16-point butterfly of the first forward pass (decimation in frequency, half-sizes 8q .. q) and of
+// the last inverse pass (decimation in time, q .. 8q; INV selects conjugate twiddles): one table entry
+// w16 = exp(-+2 pi i pos / 16q), every other twiddle derived from it.
+template <bool INV>
+__device__ __forceinline__ void butterfly16(double2 (&v)[16], double2 w16) {
+    constexpr double sg = INV ? 1.0 : -1.0;               // sign of the imaginary part of exp(-+ i ...)
+    const double2 w8 = cmul(w16, w16), w4 = cmul(w8, w8), w2 = cmul(w4, w4);
+    const double2 wa[8] = {w16, rotc(w16, C16, sg * S16), rotc(w16, R2H, sg * R2H), rotc(w16, S16, sg * C16),
+                           rotc(w16, 0.0, sg), rotc(w16, -S16, sg * C16), rotc(w16, -R2H, sg * R2H),
+                           rotc(w16, -C16, sg * S16)};
+    const double2 wb[4] = {w8, rotc(w8, R2H, sg * R2H), rotc(w8, 0.0, sg), rotc(w8, -R2H, sg * R2H)};
+    const double2 wc[2] = {w4, rotc(w4, 0.0, sg)};
+    if (!INV) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) dif(v[m], v[m + 8], wa[m]);
+#pragma unroll
+        for (int h = 0; h < 16; h += 8) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) dif(v[h + m], v[h + m + 4], wb[m]);
+        }
+#pragma unroll
+        for (int h = 0; h < 16; h += 4) { dif(v[h], v[h + 2], wc[0]); dif(v[h + 1], v[h + 3], wc[1]); }
+#pragma unroll
+        for (int p = 0; p < 16; p += 2) dif(v[p], v[p + 1], w2);
+    } else {
+#pragma unroll
+        for (int p = 0; p < 16; p += 2) dit(v[p], v[p + 1], w2);
+#pragma unroll
+        for (int h = 0; h < 16; h += 4) { dit(v[h], v[h + 2], wc[0]); dit(v[h + 1], v[h + 3], wc[1]); }
+#pragma unroll
+        for (int h = 0; h < 16; h += 8) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) dit(v[h + m], v[h + m + 4], wb[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) dit(v[m], v[m + 8], wa[m]);
+    }
+}
+
 
 // one CTA per window.  win_first[b] = first window index of noise block b (prefix, nblocks+1).
 template <int FFT_THREADS>
@@ -90,12 +142,12 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
         const int64_t j0 = bs + (win - win_first[b]) * S;     // first output of this window
         const int64_t w0 = j0 - (L - 1);                      // first input sample of the window
         __syncthreads();
-        // ---- forward FFT, decimation in frequency, natural in -> bit-reversed out.  Three radix-2
-        // stages (half-sizes 4q, 2q, q) are fused per pass: 8 points per butterfly stay in registers, so
-        // a transform makes 4 passes through shared memory (+ the last radix-2 stage) instead of 13.
+        // ---- forward FFT, decimation in frequency, natural in -> bit-reversed out.  Radix-2 stages are
+        // fused into passes whose points stay in registers: one radix-16 pass (4 stages) + radix-8 passes
+        // (3 stages each), so a transform makes 4 passes through shared memory instead of 13.
         // The FIRST pass takes its inputs straight from global memory (zero outside the noise block:
         // the non-circulant boundary), so the window never makes a separate trip through shared memory.
-        static_assert(FFT_LOG2M % 3 == 1, "radix-8 passes + one radix-2 stage");
+        static_assert(FFT_LOG2M % 3 == 1 && FFT_LOG2M >= 4, "one radix-16 pass + radix-8 passes");
         auto winload = [&](int i) {
             const int64_t t = w0 + 2 * (int64_t)i;
             double2 v;
@@ -103,15 +155,28 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             v.y = (t + 1 >= bs && t + 1 < be) ? d[t + 1] : 0.0;
             return v;
         };
-        for (int lq = FFT_LOG2M - 3; lq >= 0; lq -= 3) {
+        {   // first pass: radix-16 (half-sizes M/2 .. M/16), inputs from global memory
+            constexpr int lq = FFT_LOG2M - 4, q = 1 << lq;
+            for (int j = threadIdx.x; j < FFT_M / 16; j += FFT_THREADS) {
+                const int pos = j & (q - 1);
+                const int i0 = ((j >> lq) << (lq + 4)) + pos;
+                double2 v[16];
+#pragma unroll
+                for (int m = 0; m < 16; ++m) v[m] = winload(i0 + m * q);
+                butterfly16<false>(v, __ldg(tw + FFT_M / 4 + pos));
+#pragma unroll
+                for (int m = 0; m < 16; ++m) z(i0 + m * q) = v[m];
+            }
+            __syncthreads();
+        }
+        for (int lq = FFT_LOG2M - 7; lq >= 0; lq -= 3) {
             const int q = 1 << lq;
-            const bool first = lq == FFT_LOG2M - 3;
             for (int j = threadIdx.x; j < FFT_M / 8; j += FFT_THREADS) {
                 const int pos = j & (q - 1);
                 const int i0 = ((j >> lq) << (lq + 3)) + pos;
                 double2 v[8];
 #pragma unroll
-                for (int m = 0; m < 8; ++m) v[m] = first ? winload(i0 + m * q) : z(i0 + m * q);
+                for (int m = 0; m < 8; ++m) v[m] = z(i0 + m * q);
                 const double2 w8 = __ldg(tw + q + pos);
                 const double2 w4 = cmul(w8, w8), w2 = cmul(w4, w4);
                 dif(v[0], v[4], w8);                       // half-size 4q
@@ -129,14 +194,6 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                 dif(v[6], v[7], w2);
 #pragma unroll
                 for (int m = 0; m < 8; ++m) z(i0 + m * q) = v[m];
-            }
-            __syncthreads();
-        }
-        if (FFT_LOG2M % 3 == 1) {   // the remaining radix-2 stage with half-size 1
-            for (int j = threadIdx.x; j < FFT_M / 2; j += FFT_THREADS) {
-                const double2 a = z(2 * j), bb = z(2 * j + 1);
-                z(2 * j) = make_double2(a.x + bb.x, a.y + bb.y);
-                z(2 * j + 1) = make_double2(a.x - bb.x, a.y - bb.y);
             }
             __syncthreads();
         }
@@ -167,21 +224,11 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
 #pragma unroll
         for (int i = 0; i < NPOS; ++i) z(threadIdx.x + i * FFT_THREADS) = res[i];
         __syncthreads();
-        // ---- inverse FFT, decimation in time, bit-reversed in -> natural out (conjugate twiddles),
-        // again three radix-2 stages (half-sizes q, 2q, 4q) per pass
-        int lq0 = 0;
-        if (FFT_LOG2M % 3 == 1) {   // the stage with half-size 1 first
-            for (int j = threadIdx.x; j < FFT_M / 2; j += FFT_THREADS) {
-                const double2 a = z(2 * j), bb = z(2 * j + 1);
-                z(2 * j) = make_double2(a.x + bb.x, a.y + bb.y);
-                z(2 * j + 1) = make_double2(a.x - bb.x, a.y - bb.y);
-            }
-            __syncthreads();
-            lq0 = 1;
-        }
-        for (int lq = lq0; lq < FFT_LOG2M; lq += 3) {
+        // ---- inverse FFT, decimation in time, bit-reversed in -> natural out (conjugate twiddles):
+        // radix-8 passes (half-sizes q, 2q, 4q), then the radix-16 pass whose outputs -- the window in
+        // natural order -- go straight to global memory
+        for (int lq = 0; lq + 4 < FFT_LOG2M; lq += 3) {
             const int q = 1 << lq;
-            const bool last = lq + 3 >= FFT_LOG2M;
             for (int j = threadIdx.x; j < FFT_M / 8; j += FFT_THREADS) {
                 const int pos = j & (q - 1);
                 const int i0 = ((j >> lq) << (lq + 3)) + pos;
@@ -204,21 +251,30 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                 dit(v[1], v[5], rot1c(w8));
                 dit(v[2], v[6], rot2c(w8));
                 dit(v[3], v[7], rot3c(w8));
-                if (!last) {
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) z(i0 + m * q) = v[m];
-                } else {
-                    // the LAST pass produces the window in natural order: the alias-free samples, window
-                    // positions [L-1, L-1+S), go straight to global memory
+                for (int m = 0; m < 8; ++m) z(i0 + m * q) = v[m];
+            }
+            __syncthreads();
+        }
+        {
+            constexpr int lq = FFT_LOG2M - 4, q = 1 << lq;
+            for (int j = threadIdx.x; j < FFT_M / 16; j += FFT_THREADS) {
+                const int pos = j & (q - 1);
+                const int i0 = ((j >> lq) << (lq + 4)) + pos;
+                double2 v[16];
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) {
-                        const int r0 = 2 * (i0 + m * q) - (L - 1);    // output index of v.x within the window's S outputs
-                        if (r0 >= 0 && r0 < S && j0 + r0 < be) out[j0 + r0] = v[m].x;
-                        if (r0 + 1 >= 0 && r0 + 1 < S && j0 + r0 + 1 < be) out[j0 + r0 + 1] = v[m].y;
-                    }
+                for (int m = 0; m < 16; ++m) v[m] = z(i0 + m * q);
+                double2 w16 = __ldg(tw + FFT_M / 4 + pos);
+                w16.y = -w16.y;
+                butterfly16<true>(v, w16);
+                // the alias-free samples, window positions [L-1, L-1+S)
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int r0 = 2 * (i0 + m * q) - (L - 1);        // output index of v.x within the window's S outputs
+                    if (r0 >= 0 && r0 < S && j0 + r0 < be) out[j0 + r0] = v[m].x;
+                    if (r0 + 1 >= 0 && r0 + 1 < S && j0 + r0 + 1 < be) out[j0 + r0 + 1] = v[m].y;
                 }
             }
-            if (!last) __syncthreads();
         }
     }
 }
@@ -273,10 +329,12 @@ extern "C" int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64
     const size_t smem = sizeof(double2) * (FFT_M + FFT_M / 8);
     int64_t nwin_ub = nt / S + nblocks + 1;
     int grid = (int)(nwin_ub < sm_count() ? nwin_ub : sm_count());
-    // threads per CTA (one CTA per SM): 1024 by default, CM2_FFT_THREADS=512 selects the first version
+    // threads per CTA (one CTA per SM): 512 by default -- the 16-point butterflies of the first / last pass
+    // need the 128 registers per thread that 512 threads leave (measured at L = 4096: 1.81 ms vs 2.12 ms
+    // with 1024 threads, which spill); CM2_FFT_THREADS=1024 selects the other instantiation
     static const int threads = [] {
         const char *e = getenv("CM2_FFT_THREADS");
-        return (e && atoi(e) == 512) ? 512 : 1024;
+        return (e && atoi(e) == 1024) ? 1024 : 512;
     }();
     if (threads == 512) {
         CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
