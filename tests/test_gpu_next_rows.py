@@ -373,3 +373,17 @@ def test_subscan_filter_last_samples_of_the_tod(cm, variant, nt):
         ref = oracle.FilterLO(nt, [L, S], nt, 1, pix.copy(), poly_order=order) * d
         out = cm.FilterLO(nt, [L, S], nt, 1, pix.copy(), poly_order=order) * d
         gc.close(out, ref, what="order %d, nt = %d" % (order, nt))
+
+
+def test_ground_filter_edge_cases(cm):
+    """All samples flagged (no bin at all): the filter is the identity; a single bin: the mean of the
+    unflagged samples is removed from them."""
+    rng = np.random.default_rng(2)
+    v = rng.standard_normal(1001)
+    g = np.full(1001, -1, dtype=np.int64)
+    G = cm.GroundFilterLO(g.copy())
+    assert G.nbins == 0 and np.array_equal(G * v, v)
+    g[::3] = 0
+    out = cm.GroundFilterLO(g.copy()) * v
+    assert np.array_equal(out[g < 0], v[g < 0])
+    assert np.allclose(out[g == 0], v[g == 0] - v[g == 0].mean(), rtol=0, atol=1e-14)
