@@ -122,3 +122,80 @@ def test_sharded_solve_world_size_2():
         p.join(timeout=60)
     for rank, msg in res:
         assert msg == "ok", "rank %d: %s" % (rank, msg)
+
+
+def _worker_files(rank, world, port, out, workdir):
+    """File-driven sharding: every rank reads ITS detector pairs of two CES files (read_ces_shard) and
+    the summed operator equals the one built from read_multiple_ces of the whole files."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import scipy.sparse.linalg as spla
+        import oracle
+        from cosmomap2_b200 import distributed, synthetic
+        from cosmomap2_b200 import IOfiles as io
+        files = [os.path.join(workdir, "ces_%d.hdf5" % k) for k in range(2)]
+        if rank == 0:
+            scans = [synthetic.raster_scan(5 * 3000, nside=32, ndet=5, nx=40, ny=24, samples_per_pixel=5.0, seed=20 + k,
+                                           flag_turnarounds=True) for k in range(2)]
+            obspix = np.unique(np.concatenate([sc.pix[sc.pix >= 0] for sc in scans]))
+            for sc, path in zip(scans, files):
+                idx = np.where(sc.pix >= 0, np.searchsorted(obspix, sc.pix), -1)
+                cut = lambda a: [a[b * sc.ns:(b + 1) * sc.ns] for b in range(sc.ndet)]  # noqa: E731
+                io.write_ces_to_hdf5(path, obspix, cut(idx), cut(sc.phi), [np.zeros(sc.ns, dtype=np.int32)] * sc.ndet,
+                                     sc.ns, sc.sub_len, sc.sub_start, sum_=cut(sc.d), weight_sum=sc.weights)
+        dist.barrier()
+        pol = 1
+        # ---- whole files, one process ----
+        d, w, phi, pixs, hp, ground, subs, tst, ns_l, nb_l = io.read_multiple_ces(files, pol)
+        npix = len(hp)
+        P = oracle.SparseLO(npix, len(d), pixs, pol=pol)
+        F = oracle.FilterLO(len(d), [subs, tst], ns_l, nb_l, pixs)
+        A = P.T * F * P
+        b = P.T * (F * d)
+        # ---- this rank's pairs of every file ----
+        parts = [io.read_ces_shard(f, pol, rank, world) for f in files]
+        d_l = np.concatenate([p[0] for p in parts])
+        pix_l = np.concatenate([p[3] for p in parts])
+        Pl = oracle.SparseLO(npix, len(d_l), pix_l, pol=pol)
+        Fl = oracle.FilterLO(len(d_l), [[p[8][0] for p in parts], [p[8][1] for p in parts]], [p[6] for p in parts],
+                             [p[7] for p in parts], pix_l)
+        assert sum(p[7] for p in parts) in (4, 6) and len(d_l) < len(d)          # 2+2 or 3+3 of the 5+5 pairs
+        A_local = Pl.T * Fl * Pl
+        Ash = distributed.HostAllReduceLO(lambda v: A_local * v, npix)
+        bt = torch.from_numpy(np.ascontiguousarray(Pl.T * (Fl * d_l)))
+        distributed.all_reduce_sum_(bt)
+        assert np.allclose(bt.numpy(), b, rtol=1e-12, atol=1e-12 * np.abs(b).max())
+        v = np.random.default_rng(1).standard_normal(npix)
+        Av = A * v
+        assert np.allclose(Ash * v, Av, rtol=1e-12, atol=1e-12 * np.abs(Av).max())
+        hits = torch.from_numpy(np.bincount(pix_l[pix_l >= 0], minlength=npix).astype(np.float64))
+        distributed.all_reduce_sum_(hits)
+        assert np.array_equal(hits.numpy(), np.bincount(pixs[pixs >= 0], minlength=npix))
+        Minv = oracle.lp.DiagonalOperator(np.where(hits.numpy() > 0, 1.0 / np.maximum(hits.numpy(), 1), 0.0))
+        x1, _ = spla.cg(A, b, M=Minv, rtol=1e-12, maxiter=15)
+        x2, _ = spla.cg(Ash, bt.numpy(), M=Minv, rtol=1e-12, maxiter=15)
+        assert np.allclose(A * x2, A * x1, rtol=1e-8, atol=1e-9 * np.abs(b).max())
+        out.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        out.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_file_driven_sharded_operator_world_size_2(tmp_path):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_files, args=(r, 2, port, out, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == "ok", "rank %d: %s" % (rank, msg)
