@@ -24,7 +24,8 @@ from .deflationlib import (arnoldi, build_hess, build_Z, run_krypy_arnoldi,  # n
                            find_ritz_eigenvalues, krypy_arnoldi, krypy_ritz, eigsh)
 from .utilities import (dgemm, norm2, scalprod, get_legendre_polynomials, is_sorted,  # noqa: F401
                         bash_colors, filter_warnings, angles_gen, pairs_gen, checking_output,
-                        noise_val, subscan_resize, system_setup, reorganize_map)
+                        noise_val, subscan_resize, system_setup, reorganize_map, profile_run,
+                        output_profile, subtract_offset, rescalepixels)
 from .pcg import cg  # noqa: F401
 from . import IOfiles  # noqa: F401
 from .IOfiles import (read_from_data, read_multiple_ces, read_from_data_with_subscan_resize,  # noqa: F401

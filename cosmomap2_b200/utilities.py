@@ -173,3 +173,39 @@ def reorganize_map(mapin, obspix, npix, nside, pol, fname=None):
             torch.cuda.current_stream().cuda_stream)
     parts = [out[k * hnpix:(k + 1) * hnpix] for k in range(pol)]
     return parts if on_dev else [dv.to_host(p) for p in parts]
+
+
+def profile_run():
+    """utilities/utilities_functions.py:65-71 -- a ``cProfile.Profile`` for the host side of a run (the
+    device side is profiled with CUDA events / ncu, see tools/ and profiles/)."""
+    import cProfile
+    return cProfile.Profile()
+
+
+def output_profile(pr):
+    """utilities/utilities_functions.py:73-89 -- print the statistics collected by ``profile_run``,
+    sorted by cumulative time."""
+    import io
+    import pstats
+    s = io.StringIO()
+    pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats()
+    print(s.getvalue())
+
+
+def subtract_offset(mapp, obspix, pol):
+    """utilities/healpy_functions.py:146-158 -- remove, in place, the average over the observed pixels
+    (what the reference does before comparing maps solved with the offset filter, whose A has the
+    monopole in its null space)."""
+    if pol == 1:
+        mapp[obspix] -= np.mean(mapp[obspix])
+    else:
+        for i in range(len(mapp)):
+            mapp[i][obspix] -= np.mean(mapp[i][obspix])
+    return mapp
+
+
+def rescalepixels(pixs):
+    """utilities/utilities_functions.py:91-96 -- ``(minpix, pixs - minpix, maxpix)``."""
+    pixs = np.asarray(pixs)
+    minpix, maxpix = pixs.min(), pixs.max()
+    return minpix, pixs - minpix, maxpix

@@ -136,3 +136,23 @@ def test_synthetic_scan_properties():
     bands = synthetic.toeplitz_bands(3, 16)
     for a in bands:                                            # diagonally dominant -> SPD Toeplitz
         assert a[0] > 2 * np.abs(a[1:]).sum()
+
+
+def test_small_utilities_of_the_reference_surface():
+    """profile_run / output_profile (utilities_functions.py:65-89), rescalepixels (:91-96),
+    subtract_offset (healpy_functions.py:146-158)."""
+    import cosmomap2_b200 as cm
+    pr = cm.profile_run()
+    pr.enable()
+    sum(range(100))
+    pr.disable()
+    cm.output_profile(pr)
+    lo, shifted, hi = cm.rescalepixels(np.array([7, 9, 12]))
+    assert (lo, hi) == (7, 12) and shifted.tolist() == [0, 2, 5]
+    obs = np.array([1, 2, 3])
+    m = [np.arange(10.0), np.ones(10)]
+    cm.subtract_offset(m, obs, 3)
+    assert abs(m[0][obs].mean()) < 1e-15 and m[0][0] == 0.0 and np.all(m[1][obs] == 0.0) and m[1][0] == 1.0
+    one = np.arange(10.0)
+    cm.subtract_offset(one, np.array([0, 9]), 1)
+    assert one[0] == -4.5 and one[9] == 4.5 and one[5] == 5.0
