@@ -151,3 +151,45 @@ def test_config3_two_level_from_arnoldi(cm):
     gc.close(g["xm"], o["xm"], rtol=1e-7, what="M_2lvl solution")
     assert abs(g["nbd"] - o["nbd"]) <= 1 and abs(g["nm2"] - o["nm2"]) <= 1
     assert g["nm2"] <= g["nbd"] + 3     # Ritz vectors after 30 steps are only roughly converged
+
+
+def test_config0_from_a_ces_file(cm, tmp_path):
+    """configs[0] as the reference script runs it (src/test_BD_precond_onto_real_data.py:8-61): a CES
+    file in the AnalysisBackend HDF5 schema -> read_from_data(file, pol, npairs=4) -> ProcessTimeSamples
+    with the file's obspix -> A = P^T P -> cg(tol=1e-3, maxiter=10) -> reorganize_map -- on the GPU and
+    through the oracle, from the same file."""
+    import oracle
+    from cosmomap2_b200 import synthetic
+    sc = synthetic.raster_scan(5 * 60000, nside=128, ndet=5, nx=160, ny=120, samples_per_pixel=12.0, seed=4,
+                               flag_turnarounds=True)
+    obspix = np.unique(sc.pix[sc.pix >= 0])
+    idx = np.where(sc.pix >= 0, np.searchsorted(obspix, sc.pix), -1)
+    cut = lambda a: [a[b * sc.ns:(b + 1) * sc.ns] for b in range(sc.ndet)]  # noqa: E731
+    path = str(tmp_path / "ces.hdf5")
+    cm.write_ces_to_hdf5(path, obspix, cut(idx), cut(sc.phi), [np.zeros(sc.ns, dtype=np.int32)] * sc.ndet, sc.ns,
+                         sc.sub_len, sc.sub_start, sum_=cut(sc.d), weight_sum=sc.weights, dif=cut(sc.d),
+                         weight_dif=sc.weights)
+    nside = 128
+    for pol in (1, 3):
+        res = []
+        for impl, solver in ((oracle, spla.cg), (cm, cm.cg)):
+            d, weight, phi, pixs, hp_pixs, ground, ces_size = cm.read_from_data(path, pol, npairs=4)
+            assert len(d) == 4 * sc.ns and int(ces_size) == sc.ns
+            npix = len(hp_pixs)
+            pts = impl.ProcessTimeSamples(pixs, npix, obspix=hp_pixs, pol=pol, phi=phi)
+            npix, obs = pts.get_new_pixel
+            P = impl.SparseLO(npix, len(d), pixs, pol=pol, angle_processed=pts)
+            Mbd = impl.BlockDiagonalPreconditionerLO(pts, npix, pol=pol)
+            A = P.T * P
+            b = P.T * d
+            x, info = solver(A, b, M=Mbd, rtol=1e-3, maxiter=10)
+            hp = (cm if impl is cm else oracle).reorganize_map(x, obs, npix, nside, pol)
+            res.append((npix, np.asarray(obs), b, x, info, hp))
+        (n0, o0, b0, x0, i0, h0), (n1, o1, b1, x1, i1, h1) = res
+        assert n0 == n1 and i0 == 0 and i1 == 0
+        gc.exact(o1, o0, "observed HEALPix pixels")
+        gc.close(b1, b0, what="rhs from file")
+        gc.close(x1, x0, rtol=1e-9, what="map from file, pol=%d" % pol)
+        for a, bb in zip(h1, h0):
+            gc.close(a, bb, rtol=1e-9, what="HEALPix map")
+            assert np.count_nonzero(a) <= n1
