@@ -199,3 +199,67 @@ class HostAllReduceLO(object):
 
     def __mul__(self, x):
         return self.matvec(x)
+
+
+class ShardedTwoLevelPreconditionerLO(lp.LinearOperator):
+    """``M_2lvl = M_BD (I - AZ E^-1 Z^T) + Z E^-1 Z^T`` with ``Z``, ``AZ`` and the ``M_BD`` blocks sharded
+    by PIXEL over the ranks (each rank keeps 1/G of their rows: at configs[3] Z and AZ are the largest
+    objects after the TOD), for PCG vectors that are replicated:
+
+        t = Z_loc^T v_loc          tall-skinny kernel on the local rows
+        t <- sum over ranks        r doubles (NCCL; bit-identical on every rank)
+        c = E^-1 t                 replicated r x r apply
+        y_loc = M_BD,loc (v_loc - AZ_loc c) + Z_loc c
+        y <- all-gather(y_loc)     one n-vector, the same volume as the map exchange of an A apply
+
+    Per apply every rank streams 3 r n / G doubles instead of 3 r n.  Built from the replicated
+    operators (``Mbd``, ``DeflationLO(Z)``, ``DeflationLO(AZ)``, ``CoarseLO``): the local rows are copied,
+    the caller may then drop the full ``Z`` / ``AZ``.
+    """
+
+    def __init__(self, Mbd, Zd, AZd, E, group=None):
+        from . import _device as dv
+        self.group = group
+        dist_on = is_distributed(group)
+        self.world = dist.get_world_size(group) if dist_on else 1
+        self.rank = dist.get_rank(group) if dist_on else 0
+        self.pol, npix, n = Mbd.pol, Mbd._n, Zd.nrows
+        assert n == self.pol * npix and AZd.nrows == n and AZd.ncols == Zd.ncols
+        self.r = int(Zd.ncols)
+        spans = [shard_detectors(npix, self.world, g) for g in range(self.world)]
+        plo, phi = spans[self.rank]
+        self._lo, self._hi, self._npix_loc = self.pol * plo, self.pol * phi, phi - plo
+        self._sizes = [self.pol * (b - a) for a, b in spans]
+        self._nmax = max(self._sizes)
+        self._z = Zd._zt[:, self._lo:self._hi].contiguous()
+        self._az = AZd._zt[:, self._lo:self._hi].contiguous()
+        self._inv = Mbd._inv_dev[6 * plo:6 * phi].clone()          # own, aligned copy of the local blocks
+        self._einv = E._einv_dev
+        nl = max(self._hi - self._lo, 1)
+        self._v, self._u = dv.empty_f64(nl), dv.empty_f64(nl)
+        self._y = dv.zeros_f64(self._nmax)
+        self._t, self._c = dv.empty_f64(self.r), dv.empty_f64(self.r)
+        self._gather = dv.empty_f64(self._nmax * self.world)
+        self._work = dv.empty_f64(int(dv.call("cm2_defl_work_doubles", self.r)))
+        super(ShardedTwoLevelPreconditionerLO, self).__init__(n, n, matvec=self.mult, symmetric=True, device=True)
+
+    def mult(self, v):
+        from . import _device as dv
+        st = dv.stream
+        nl, r = self._hi - self._lo, self.r
+        self._v[:nl].copy_(v[self._lo:self._hi])
+        dv.call("cm2_defl_zt_apply", dv.ptr(self._z), nl, r, nl, dv.ptr(self._v), 1, nl, dv.ptr(self._t),
+                dv.ptr(self._work), st())
+        all_reduce_sum_(self._t, self.group)
+        dv.call("cm2_coarse_apply", dv.ptr(self._einv), r, dv.ptr(self._t), dv.ptr(self._c), st())
+        dv.call("cm2_defl_z_apply", dv.ptr(self._az), nl, r, nl, dv.ptr(self._c), -1.0, 1.0, dv.ptr(self._v),
+                dv.ptr(self._u), st())
+        dv.call("cm2_bd_apply", dv.ptr(self._inv), self._npix_loc, self.pol, dv.ptr(self._u), dv.ptr(self._y), st())
+        dv.call("cm2_defl_z_apply", dv.ptr(self._z), nl, r, nl, dv.ptr(self._c), 1.0, 1.0, dv.ptr(self._y),
+                dv.ptr(self._y), st())
+        if self.world == 1:
+            return self._y[:nl].clone()
+        dist.all_gather_into_tensor(self._gather, self._y, group=self.group)
+        if all(s == self._nmax for s in self._sizes):
+            return self._gather.clone()
+        return torch.cat([self._gather[g * self._nmax:g * self._nmax + s] for g, s in enumerate(self._sizes)])

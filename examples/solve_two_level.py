@@ -68,6 +68,9 @@ def main():
     ap.add_argument("--arnoldi", type=int, default=300)
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--maxiter", type=int, default=2000)
+    ap.add_argument("--shard-m2", action="store_true",
+                    help="N > 1: Z, AZ and the M_BD blocks sharded by pixel over the ranks "
+                         "(distributed.ShardedTwoLevelPreconditionerLO)")
     ap.add_argument("--poly-order", type=int, default=0,
                     help="subscan filter: 0 = offsets (src/test_M2_precond_onto_real_data.py:79-80), "
                          ">0 = Legendre polynomials up to that order (:37-38)")
@@ -119,7 +122,7 @@ def main():
                        true_relres=rel)
 
     out = {"world": world, "nt_total": nt * world, "nt_per_gpu": nt, "npix": int(npix), "nside": args.nside,
-           "nseg_per_gpu": F.nseg, "poly_order": args.poly_order}
+           "nseg_per_gpu": F.nseg, "poly_order": args.poly_order, "shard_m2": bool(args.shard_m2 and world > 1)}
     x_bd, out["M_BD"] = solve(Mbd, "M_BD")
 
     # ---- deflation space: preconditioned Arnoldi, Ritz vectors of the smallest Ritz values ----------
@@ -134,7 +137,10 @@ def main():
     AZ = torch.stack([A._apply(dv.to_dev_f64(Zc[:, i].contiguous())) for i in range(r)]).t()
     E = cm.CoarseLO(Zc, AZ, r, apply="eig")
     Zd, AZd = cm.DeflationLO(Zc), cm.DeflationLO(AZ)
-    M2 = Mbd * (cm.lp.IdentityOperator(n) - AZd * E * Zd.T) + Zd * E * Zd.T      # fused at first use
+    if args.shard_m2 and world > 1:
+        M2 = distributed.ShardedTwoLevelPreconditionerLO(Mbd, Zd, AZd, E)
+    else:
+        M2 = Mbd * (cm.lp.IdentityOperator(n) - AZd * E * Zd.T) + Zd * E * Zd.T  # fused at first use
     torch.cuda.synchronize()
     out["deflation"] = dict(arnoldi_steps=int(m), r=int(r), ritz_min=float(theta[0]), ritz_cut=float(thr),
                             ritz_max=float(theta[-1]), discarded_E_modes=int(getattr(E, "ndiscarded", 0)),
