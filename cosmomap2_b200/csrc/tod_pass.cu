@@ -325,6 +325,128 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_white(const int32_t *__restri
     run_merge<POL, POL>(y, rs);
 }
 
+// Fused y = P^T T P x for a short symmetric band (T = the banded Toeplitz blocks of
+// BlockLO(offdiag=True), linearoperators.py:582-595, 672-674; the composition P.T*N*P of
+// tests/test_2level_preconditioner.py:16-29), NLAG = nband-1 <= 8 lags: one pass over the TOD, no
+// time-domain temporary (20 B/sample instead of the 28 + 16 + 28 of the chain P, T, P^T).
+// Warp tiles OVERLAP: a warp loads 256 consecutive samples, the first and last HL lanes are halo
+// (their P x is only input to the neighbours' band sums), the 256 - 16 HL samples in between are the
+// tile's outputs.  P x of the tile goes through 2 kB of shared memory per warp, stored transposed
+// (element (lane, j) at 32 j + lane: conflict-free for the store and for the neighbour reads, which
+// have a fixed offset to 8 lane + j); every lane then reads its 2 NLAG neighbours once and slides
+// the band over a register window.  Contributions never cross a noise block (the zero boundary of
+// ToeplitzLO): masked by the block's [begin, end) on the rare lanes near a boundary; a lane whose
+// own 8 samples straddle a boundary takes a per-sample path.
+struct ToepW {
+    const double *band;    // [nblocks][nband]: a_0 .. a_{nband-1} per block
+    int nband;
+    BlockW blk;            // block geometry (w unused)
+};
+
+template <int POL, int NLAG>
+__global__ void __launch_bounds__(BLOCK) k_amatvec_toeplitz(const int32_t *__restrict__ pix, const double *__restrict__ cs,
+                                                            const double *__restrict__ sn, int64_t nt, ToepW tw,
+                                                            const double *__restrict__ x, double *__restrict__ y) {
+    constexpr int HL = (NLAG + K - 1) / K;     // halo lanes on either side
+    constexpr int VAL = TILE - 2 * HL * K;     // output samples per tile
+    __shared__ double sv_all[BLOCK / 32][TILE];
+    double *sv = sv_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
+    const int64_t ntiles = (nt + VAL - 1) / VAL;
+    RunState<POL> rs;
+    rs.ph = rs.pt = -1;
+    rs.single = true;
+#pragma unroll
+    for (int k = 0; k < POL; ++k) rs.acc[k] = rs.head[k] = 0.0;
+    for (int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
+        const int64_t t0 = tile * VAL - HL * K + (int64_t)lane * K;   // multiple of 8: the 256-bit loads stay aligned
+        int p[K];
+        double c[K], s[K];
+        if (t0 >= 0) {
+            load_pix(pix, t0, nt, p);
+            if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j) { p[j] = -1; c[j] = 0.0; s[j] = 0.0; }
+        }
+        run_merge<POL, POL>(y, rs);            // previous tile, after this tile's loads have been issued
+        double v[K];
+        {
+            double xv[K][POL];
+            gather_x<POL>(x, p, xv);
+#pragma unroll
+            for (int j = 0; j < K; ++j) v[j] = p[j] >= 0 ? project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) sv[32 * j + lane] = v[j];
+        __syncwarp();
+        double out[K];
+        const bool active = lane >= HL && lane < 32 - HL && t0 < nt;
+        if (active) {
+            int64_t b0 = block_of(tw.blk, t0);
+            if (b0 >= tw.blk.nblocks) b0 = tw.blk.nblocks - 1;
+            const int64_t bs = tw.blk.start ? __ldg(tw.blk.start + b0) : b0 * tw.blk.blocksize;
+            int64_t be = tw.blk.start ? __ldg(tw.blk.start + b0 + 1) : (b0 + 1) * tw.blk.blocksize;
+            if (be > nt) be = nt;
+            if (t0 + K <= be) {                // the lane's 8 samples lie in one noise block (the common case)
+                const double *a = tw.band + b0 * tw.nband;
+                double ak[NLAG + 1];
+#pragma unroll
+                for (int k = 0; k <= NLAG; ++k) ak[k] = k < tw.nband ? __ldg(a + k) : 0.0;
+                double w[K + 2 * NLAG];        // P x at t0 - NLAG .. t0 + K + NLAG - 1
+#pragma unroll
+                for (int m = 0; m < NLAG; ++m) {
+                    const int il = K * lane - NLAG + m, ir = K * lane + K + m;
+                    w[m] = (t0 - NLAG + m >= bs) ? sv[32 * (il & 7) + (il >> 3)] : 0.0;
+                    w[NLAG + K + m] = (t0 + K + m < be) ? sv[32 * (ir & 7) + (ir >> 3)] : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < K; ++j) w[NLAG + j] = v[j];
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    double acc = ak[0] * w[NLAG + j];
+#pragma unroll
+                    for (int k = 1; k <= NLAG; ++k) acc = fma(ak[k], w[NLAG + j - k] + w[NLAG + j + k], acc);
+                    out[j] = acc;
+                }
+            } else {                           // a block boundary inside the lane's samples: per sample
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int64_t t = t0 + j;
+                    out[j] = 0.0;
+                    if (t >= nt) continue;
+                    int64_t b = block_of(tw.blk, t);
+                    if (b >= tw.blk.nblocks) b = tw.blk.nblocks - 1;
+                    const int64_t s0 = tw.blk.start ? __ldg(tw.blk.start + b) : b * tw.blk.blocksize;
+                    int64_t s1 = tw.blk.start ? __ldg(tw.blk.start + b + 1) : (b + 1) * tw.blk.blocksize;
+                    if (s1 > nt) s1 = nt;
+                    const double *a = tw.band + b * tw.nband;
+                    double acc = __ldg(a) * v[j];
+                    for (int k = 1; k <= NLAG && k < tw.nband; ++k) {
+                        const int il = K * lane + j - k, ir = K * lane + j + k;
+                        double nb = 0.0;
+                        if (t - k >= s0) nb += sv[32 * (il & 7) + (il >> 3)];
+                        if (t + k < s1) nb += sv[32 * (ir & 7) + (ir >> 3)];
+                        acc = fma(__ldg(a + k), nb, acc);
+                    }
+                    out[j] = acc;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j) { out[j] = 0.0; p[j] = -1; }
+        }
+        __syncwarp();                          // all reads of sv done before the next tile overwrites it
+        run_compress<POL, POL>(y, p, [&](int j, double (&o)[POL]) {
+            if constexpr (POL == 1) { o[0] = out[j]; }
+            else if constexpr (POL == 2) { o[0] = out[j] * c[j]; o[1] = out[j] * s[j]; }
+            else { o[0] = out[j]; o[1] = out[j] * c[j]; o[2] = out[j] * s[j]; }
+        }, rs);
+    }
+    run_merge<POL, POL>(y, rs);
+}
+
 // Fused y = P^T (P x - mu_seg) over the unflagged samples inside subscans: the offset-filtered
 // A-matvec in ONE pass over the TOD, given the subscan means mu (k_seg_mean, filter_runs.cu).
 // tile_seg[tile] = index of the first segment whose end lies beyond the tile's first sample.
@@ -414,6 +536,71 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter_mu(const int32_t *__re
             m0 = flag == 1 ? __ldg(sg.mu + k0) : 0.0;
         }
         run_merge<POL, POL>(y, rs);
+    }
+}
+
+// d = F P x for the offset filter in one pass (no P x temporary, no second pass for F): the subscan
+// means of P x come from the run table (k_seg_mean), so d_t = (P x)_t - mu_seg(t) inside subscans --
+// also on flagged samples, where (P x)_t = 0, exactly as FilterLO.mult subtracts the mean from them
+// (linearoperators.py:165) -- and 0 in the gaps.  28 B/sample instead of 28 + 20.
+template <int POL>
+__global__ void __launch_bounds__(BLOCK) k_pointing_filter_mu(const int32_t *__restrict__ pix, const double *__restrict__ cs,
+                                                              const double *__restrict__ sn, int64_t nt, SegInfo sg,
+                                                              const double *__restrict__ x, double *__restrict__ d) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
+    const int64_t ntiles = (nt + TILE - 1) / TILE;
+    for (int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
+        const int64_t t0 = tile * TILE + (int64_t)lane * K;
+        if (t0 >= nt) continue;
+        int p[K];
+        double c[K], s[K], mu[K], xv[K][POL], out[K];
+        bool in[K];
+        load_pix(pix, t0, nt, p);
+        if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
+        const int flag = __ldg(sg.tile_flag + tile);
+        const int k0 = __ldg(sg.tile_seg + tile);
+        if (flag == 1) {
+            const double m0 = __ldg(sg.mu + k0);
+#pragma unroll
+            for (int j = 0; j < K; ++j) { mu[j] = m0; in[j] = true; }
+        } else if (flag == 0) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) { mu[j] = 0.0; in[j] = false; }
+        } else {
+            int64_t k = k0;
+            while (k < sg.nseg && __ldg(sg.end + k) <= t0) ++k;
+            int64_t a = k < sg.nseg ? __ldg(sg.start + k) : INT64_MAX, b = k < sg.nseg ? __ldg(sg.end + k) : INT64_MAX;
+            double m = k < sg.nseg ? __ldg(sg.mu + k) : 0.0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int64_t t = t0 + j;
+                while (k < sg.nseg && t >= b) {
+                    ++k;
+                    a = k < sg.nseg ? __ldg(sg.start + k) : INT64_MAX;
+                    b = k < sg.nseg ? __ldg(sg.end + k) : INT64_MAX;
+                    m = k < sg.nseg ? __ldg(sg.mu + k) : 0.0;
+                }
+                in[j] = k < sg.nseg && t >= a;
+                mu[j] = m;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) if (!in[j]) p[j] = -1;
+        gather_x<POL>(x, p, xv);
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            out[j] = in[j] ? (p[j] >= 0 ? project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0) : 0.0) - mu[j] : 0.0;
+        if (t0 + K <= nt) {
+            D4 a, b;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { a.v[j] = out[j]; b.v[j] = out[4 + j]; }
+            st_stream_d4(d + t0, a);
+            st_stream_d4(d + t0 + 4, b);
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j) if (t0 + j < nt) d[t0 + j] = out[j];
+        }
     }
 }
 
@@ -880,6 +1067,51 @@ extern "C" int cm2_amatvec_white(const int32_t *pix, const double *c, const doub
     return CM2_OK;
 }
 
+template <int POL, int NLAG>
+static int launch_amatvec_toeplitz(const int32_t *pix, const double *c, const double *s, int64_t nt, const ToepW &tw,
+                                   const double *x, double *y, cudaStream_t st) {
+    constexpr int VAL = TILE - 2 * ((NLAG + K - 1) / K) * K;
+    const int64_t ntiles = (nt + VAL - 1) / VAL;
+    const int64_t blocks = (ntiles + (BLOCK / 32) - 1) / (BLOCK / 32);
+    auto kern = k_amatvec_toeplitz<POL, NLAG>;
+    kern<<<persistent_grid(kern, BLOCK, 0, blocks), BLOCK, 0, st>>>(pix, c, s, nt, tw, x, y);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+template <int POL>
+static int dispatch_amatvec_toeplitz(const int32_t *pix, const double *c, const double *s, int64_t nt, const ToepW &tw,
+                                     const double *x, double *y, cudaStream_t st) {
+    const int nlag = tw.nband - 1;
+    if (nlag <= 2) return launch_amatvec_toeplitz<POL, 2>(pix, c, s, nt, tw, x, y, st);
+    if (nlag <= 4) return launch_amatvec_toeplitz<POL, 4>(pix, c, s, nt, tw, x, y, st);
+    return launch_amatvec_toeplitz<POL, 8>(pix, c, s, nt, tw, x, y, st);
+}
+
+extern "C" int cm2_amatvec_toeplitz_max_band(void) { return 9; }
+
+extern "C" int cm2_amatvec_toeplitz(const int32_t *pix, const double *c, const double *s, int64_t nt, int pol,
+                                    const double *band, int nband, int64_t nblocks, int64_t blocksize,
+                                    const int64_t *blk_start, const double *x, double *y, int64_t npix,
+                                    cm2_stream_t stream) {
+    int rc = check_tod(pix, c, s, nt, pol);
+    if (rc) return rc;
+    CM2_REQUIRE(band != nullptr && nband >= 1, "band required");
+    rc = check_blocks(band, nblocks, blocksize, blk_start);
+    if (rc) return rc;
+    if (nband > cm2_amatvec_toeplitz_max_band())
+        return set_error(CM2_ERR_UNSUPPORTED, "fused Toeplitz A-matvec: nband=%d, bands of up to %d coefficients are supported",
+                         nband, cm2_amatvec_toeplitz_max_band());
+    CM2_REQUIRE(npix >= 0, "npix < 0");
+    cudaStream_t st = as_stream(stream);
+    if (npix > 0) CM2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)npix * pol, st));
+    if (nt == 0 || npix == 0) return CM2_OK;
+    const ToepW tw{band, nband, make_blockw(nullptr, nblocks, blocksize, blk_start)};
+    if (pol == 1) return dispatch_amatvec_toeplitz<1>(pix, c, s, nt, tw, x, y, st);
+    if (pol == 2) return dispatch_amatvec_toeplitz<2>(pix, c, s, nt, tw, x, y, st);
+    return dispatch_amatvec_toeplitz<3>(pix, c, s, nt, tw, x, y, st);
+}
+
 extern "C" int cm2_weights_moments(const int32_t *pix, const double *c, const double *s, const double *w,
                                    const double *wblk, int64_t nblocks, int64_t blocksize, const int64_t *blk_start,
                                    int64_t nt, int pol, double *mom, int64_t npix, cm2_stream_t stream) {
@@ -949,6 +1181,28 @@ extern "C" int cm2_amatvec_filter_mu(const int32_t *pix, const double *c, const 
     if (pol == 1) k_amatvec_filter_mu<1><<<tod_grid(k_amatvec_filter_mu<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, y);
     else if (pol == 2) k_amatvec_filter_mu<2><<<tod_grid(k_amatvec_filter_mu<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, y);
     else k_amatvec_filter_mu<3><<<tod_grid(k_amatvec_filter_mu<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, y);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+extern "C" int cm2_pointing_filter_mu(const int32_t *pix, const double *c, const double *s, int64_t nt, int pol,
+                                      const int64_t *seg_start, const int64_t *seg_end, const double *seg_mu,
+                                      const int32_t *tile_seg, const uint8_t *tile_flag, int64_t nseg, const double *x,
+                                      double *d, cm2_stream_t stream) {
+    int rc = check_tod(pix, c, s, nt, pol);
+    if (rc) return rc;
+    CM2_REQUIRE(nseg >= 0, "negative size");
+    CM2_REQUIRE(aligned(d, 32), "d must be 32-byte aligned");
+    if (nt == 0) return CM2_OK;
+    cudaStream_t st = as_stream(stream);
+    if (nseg == 0) {
+        CM2_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * (size_t)nt, st));
+        return CM2_OK;
+    }
+    SegInfo sg{seg_start, seg_end, seg_mu, tile_seg, tile_flag, nseg};
+    if (pol == 1) k_pointing_filter_mu<1><<<tod_grid(k_pointing_filter_mu<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, d);
+    else if (pol == 2) k_pointing_filter_mu<2><<<tod_grid(k_pointing_filter_mu<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, d);
+    else k_pointing_filter_mu<3><<<tod_grid(k_pointing_filter_mu<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, d);
     CM2_LAUNCHED();
     return CM2_OK;
 }

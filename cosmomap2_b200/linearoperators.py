@@ -521,6 +521,62 @@ class _FusedWhiteA(lp.LinearOperator):
 FILTER_RUN_TABLE = True     # single-TOD-pass P^T F P through the run-compressed u_k table
 
 
+def _build_filter_runs(P, F):
+    """Run-compressed table of u_k = P^T 1_k per subscan + the per-tile subscan lookup (csrc/filter_runs.cu),
+    built on the device; False when the subscans are unsorted or the pointing has no runs."""
+    nt, st = P.nrows, _stream()
+    dev = P._pix_dev.device
+    ss, se = F._seg_start_host, F._seg_end_host
+    if F.nseg == 0 or np.any(ss[1:] < se[:-1]):
+        return False                                    # unsorted / overlapping subscans
+    flags = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
+    pixm = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
+    dv.call("cm2_filter_runs_mark", dv.ptr(P._pix_dev), dv.ptr(F._seg_start), dv.ptr(F._seg_end), F.nseg, nt,
+            dv.ptr(flags), dv.ptr(pixm), st)
+    runidx = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    scratch = torch.empty(int(dv.call("cm2_scan_scratch_bytes", nt)) // 8 + 1, dtype=torch.int64, device=dev)
+    dv.call("cm2_weights_old2new", dv.ptr(flags), nt, dv.ptr(runidx), dv.ptr(count), dv.ptr(scratch), st)
+    nruns = int(count.item())
+    del flags, scratch
+    if nruns == 0 or 2 * nruns > nt:
+        return False
+    run_pix = torch.empty(nruns, dtype=torch.int32, device=dev)
+    run_mom = torch.empty(3 * nruns, dtype=torch.float64, device=dev)
+    seg_first = torch.empty(max(F.nseg, 1), dtype=torch.int64, device=dev)
+    seg_nruns = torch.empty(max(F.nseg, 1), dtype=torch.int32, device=dev)
+    dv.call("cm2_filter_runs_fill", dv.ptr(pixm), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.pol,
+            dv.ptr(F._seg_start), dv.ptr(F._seg_end), F.nseg, dv.ptr(runidx), dv.ptr(run_pix), dv.ptr(run_mom),
+            dv.ptr(seg_first), dv.ptr(seg_nruns), st)
+    del pixm, runidx
+    # first segment whose end lies beyond the first sample of every 256-sample tile
+    ntiles = (nt + 255) // 256
+    tile_t0 = torch.arange(ntiles, dtype=torch.int64, device=dev) * 256
+    tile_seg = torch.searchsorted(F._seg_end, tile_t0, right=True)
+    kk = torch.clamp(tile_seg, max=F.nseg - 1)
+    a, b = F._seg_start[kk], F._seg_end[kk]
+    t1 = torch.clamp(tile_t0 + 256, max=nt)
+    inside = (tile_seg < F.nseg) & (a <= tile_t0) & (t1 <= b)
+    outside = (tile_seg >= F.nseg) | (a >= t1)
+    tile_flag = torch.full((ntiles,), 2, dtype=torch.uint8, device=dev)
+    tile_flag[inside] = 1
+    tile_flag[outside] = 0
+    mu = torch.empty(max(F.nseg, 1), dtype=torch.float64, device=dev)
+    return dict(run_pix=run_pix, run_mom=run_mom, seg_first=seg_first, seg_nruns=seg_nruns, nruns=nruns,
+                tile_seg=tile_seg.to(torch.int32), tile_flag=tile_flag, mu=mu)
+
+
+def _filter_runs(P, F):
+    """The table of _build_filter_runs, built once per (P, F) pair and shared by the fused operators."""
+    if not FILTER_RUN_TABLE:
+        return False
+    cache = F.__dict__.setdefault("_run_tables", {})
+    key = (id(P), P._pix_dev.data_ptr())
+    if key not in cache:
+        cache[key] = _build_filter_runs(P, F)
+    return cache[key]
+
+
 class _FusedFilterA(lp.LinearOperator):
     """P^T F P as one operator.  Default: the subscan means from the run-compressed table of
     u_k = P^T 1_k (csrc/filter_runs.cu), then ONE fused gather/scatter pass over the TOD; the table
@@ -533,54 +589,11 @@ class _FusedFilterA(lp.LinearOperator):
         n = P.pol * P.ncols
         super(_FusedFilterA, self).__init__(n, n, matvec=self._run, symmetric=True, device=True)
 
-    def _build_runs(self):
-        P, F = self.P, self.F
-        nt, st = P.nrows, _stream()
-        dev = P._pix_dev.device
-        ss, se = F._seg_start_host, F._seg_end_host
-        if F.nseg == 0 or np.any(ss[1:] < se[:-1]):
-            return False                                    # unsorted / overlapping subscans
-        flags = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
-        pixm = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
-        dv.call("cm2_filter_runs_mark", dv.ptr(P._pix_dev), dv.ptr(F._seg_start), dv.ptr(F._seg_end), F.nseg, nt,
-                dv.ptr(flags), dv.ptr(pixm), st)
-        runidx = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
-        count = torch.zeros(1, dtype=torch.int64, device=dev)
-        scratch = torch.empty(int(dv.call("cm2_scan_scratch_bytes", nt)) // 8 + 1, dtype=torch.int64, device=dev)
-        dv.call("cm2_weights_old2new", dv.ptr(flags), nt, dv.ptr(runidx), dv.ptr(count), dv.ptr(scratch), st)
-        nruns = int(count.item())
-        del flags, scratch
-        if nruns == 0 or 2 * nruns > nt:
-            return False
-        run_pix = torch.empty(nruns, dtype=torch.int32, device=dev)
-        run_mom = torch.empty(3 * nruns, dtype=torch.float64, device=dev)
-        seg_first = torch.empty(max(F.nseg, 1), dtype=torch.int64, device=dev)
-        seg_nruns = torch.empty(max(F.nseg, 1), dtype=torch.int32, device=dev)
-        dv.call("cm2_filter_runs_fill", dv.ptr(pixm), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.pol,
-                dv.ptr(F._seg_start), dv.ptr(F._seg_end), F.nseg, dv.ptr(runidx), dv.ptr(run_pix), dv.ptr(run_mom),
-                dv.ptr(seg_first), dv.ptr(seg_nruns), st)
-        del pixm, runidx
-        # first segment whose end lies beyond the first sample of every 256-sample tile
-        ntiles = (nt + 255) // 256
-        tile_t0 = torch.arange(ntiles, dtype=torch.int64, device=dev) * 256
-        tile_seg = torch.searchsorted(F._seg_end, tile_t0, right=True)
-        kk = torch.clamp(tile_seg, max=F.nseg - 1)
-        a, b = F._seg_start[kk], F._seg_end[kk]
-        t1 = torch.clamp(tile_t0 + 256, max=nt)
-        inside = (tile_seg < F.nseg) & (a <= tile_t0) & (t1 <= b)
-        outside = (tile_seg >= F.nseg) | (a >= t1)
-        tile_flag = torch.full((ntiles,), 2, dtype=torch.uint8, device=dev)
-        tile_flag[inside] = 1
-        tile_flag[outside] = 0
-        mu = torch.empty(max(F.nseg, 1), dtype=torch.float64, device=dev)
-        return dict(run_pix=run_pix, run_mom=run_mom, seg_first=seg_first, seg_nruns=seg_nruns, nruns=nruns,
-                    tile_seg=tile_seg.to(torch.int32), tile_flag=tile_flag, mu=mu)
-
     def _run(self, x):
         P, F = self.P, self.F
         y = dv.empty_f64(P.ncols * P.pol)
         if self._runs is None:
-            self._runs = self._build_runs() if FILTER_RUN_TABLE else False
+            self._runs = _filter_runs(P, F)
         rt = self._runs
         if rt:
             dv.call("cm2_filter_seg_mean", dv.ptr(rt["run_pix"]), dv.ptr(rt["run_mom"]), dv.ptr(rt["seg_first"]),
@@ -617,11 +630,65 @@ class _FusedPolyFilterA(lp.LinearOperator):
         return y
 
 
+class _FusedFilterP(lp.LinearOperator):
+    """F P (offset filter) as one TOD pass: the subscan means of P x come from the run table, so
+    d = P x - mu_seg is written directly (the head of chains such as P.T*F*N*F*P).  Falls back to the
+    two operators when the run table cannot be used (unsorted subscans, run-free pointing)."""
+
+    def __init__(self, P, F):
+        self.P, self.F = P, F
+        self._runs = None
+        super(_FusedFilterP, self).__init__(P.pol * P.ncols, P.nrows, matvec=self._run, symmetric=False, device=True)
+
+    def _run(self, x):
+        P, F = self.P, self.F
+        if self._runs is None:
+            self._runs = _filter_runs(P, F)
+        rt = self._runs
+        if not rt:
+            return F._apply(P._apply(x))
+        d = dv.empty_f64(P.nrows)
+        dv.call("cm2_filter_seg_mean", dv.ptr(rt["run_pix"]), dv.ptr(rt["run_mom"]), dv.ptr(rt["seg_first"]),
+                dv.ptr(rt["seg_nruns"]), F.nseg, P.pol, dv.ptr(x), dv.ptr(rt["mu"]), _stream())
+        dv.call("cm2_pointing_filter_mu", dv.ptr(P._pix_dev), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.nrows, P.pol,
+                dv.ptr(F._seg_start), dv.ptr(F._seg_end), dv.ptr(rt["mu"]), dv.ptr(rt["tile_seg"]),
+                dv.ptr(rt["tile_flag"]), F.nseg, dv.ptr(x), dv.ptr(d), _stream())
+        return d
+
+
+class _FusedToeplitzA(lp.LinearOperator):
+    """P^T N P for a short-band Toeplitz N = BlockLO(offdiag=True) (the reference tests' composition,
+    tests/test_2level_preconditioner.py:16-29) as ONE kernel without a TOD temporary."""
+
+    def __init__(self, P, N):
+        self.P, self.N = P, N
+        n = P.pol * P.ncols
+        super(_FusedToeplitzA, self).__init__(n, n, matvec=self._run, symmetric=True, device=True)
+
+    @staticmethod
+    def supported(P, N):
+        return (N.isoffdiag and N.shape[0] == P.nrows
+                and N._nband <= int(dv.call("cm2_amatvec_toeplitz_max_band")))
+
+    def _run(self, x):
+        P, N = self.P, self.N
+        y = dv.empty_f64(P.ncols * P.pol)
+        if N._band_dev is None:
+            N._band_dev = dv.to_dev_f64(N._band_host.reshape(-1))
+            N._fft = None
+        nb, bs, startp = N._blk.args()
+        dv.call("cm2_amatvec_toeplitz", dv.ptr(P._pix_dev), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.nrows, P.pol,
+                dv.ptr(N._band_dev), int(N._nband), nb, bs, startp, dv.ptr(x), dv.ptr(y), P.ncols, _stream())
+        return y
+
+
 def _is_pt(op):
     return getattr(op, "_adjoint_of", None) is not None and isinstance(op._adjoint_of, SparseLO)
 
 
 fusion_enabled = True
+FUSE_TOEPLITZ_A = False     # [P.T, N_toeplitz (<= 9 coefficients), P] -> cm2_amatvec_toeplitz   (off until validated on a B200)
+FUSE_FILTER_P = False       # [F_offset, P] -> cm2_pointing_filter_mu                           (off until validated on a B200)
 
 
 @lp.register_fuser
@@ -640,12 +707,28 @@ def _fuse_pointing(factors):
             mid = factors[i + 1]
             if isinstance(mid, BlockLO) and not mid.isoffdiag and mid.shape[0] == P.nrows:
                 return factors[:i] + [_FusedWhiteA(P, mid)] + factors[i + 3:]
+            if FUSE_TOEPLITZ_A and isinstance(mid, BlockLO) and _FusedToeplitzA.supported(P, mid):
+                return factors[:i] + [_FusedToeplitzA(P, mid)] + factors[i + 3:]
             if (isinstance(mid, FilterLO) and mid.shape[0] == P.nrows
                     and mid._pix_dev.data_ptr() == P._pix_dev.data_ptr()):
                 if mid.poly_order == 0:
                     return factors[:i] + [_FusedFilterA(P, mid)] + factors[i + 3:]
                 if _FusedPolyFilterA.supported(P, mid):
                     return factors[:i] + [_FusedPolyFilterA(P, mid)] + factors[i + 3:]
+    return None
+
+
+@lp.register_fuser
+def _fuse_filter_pointing(factors):
+    """[..., F, P] with the offset filter and no P.T in front of it (that case is one kernel, above):
+    F P becomes one TOD pass."""
+    if not (fusion_enabled and FUSE_FILTER_P):
+        return None
+    for i in range(len(factors) - 1):
+        F, P = factors[i], factors[i + 1]
+        if (isinstance(F, FilterLO) and isinstance(P, SparseLO) and F.poly_order == 0 and F._sorted and F.nseg > 0
+                and F.shape[0] == P.nrows and F._pix_dev.data_ptr() == P._pix_dev.data_ptr()):
+            return factors[:i] + [_FusedFilterP(P, F)] + factors[i + 2:]
     return None
 
 

@@ -172,6 +172,26 @@ int cm2_amatvec_filter_mu(const int32_t *pix, const double *cos2phi, const doubl
                           int64_t nseg, const double *x, double *y, int64_t npix,
                           cm2_stream_t stream);
 
+/* d = F P x for the offset filter in one TOD pass (the first two factors of a chain such as
+ * P.T*F*N*F*P): d_t = (P x)_t - mu_seg(t) inside subscans -- flagged samples included, as
+ * FilterLO.mult does (interfaces/linearoperators.py:165) -- and 0 in the gaps; seg_mu from
+ * cm2_filter_seg_mean, tile tables as for cm2_amatvec_filter_mu. */
+int cm2_pointing_filter_mu(const int32_t *pix, const double *cos2phi, const double *sin2phi,
+                           int64_t nt, int pol, const int64_t *seg_start, const int64_t *seg_end,
+                           const double *seg_mu, const int32_t *tile_seg, const uint8_t *tile_flag,
+                           int64_t nseg, const double *x, double *d, cm2_stream_t stream);
+
+/* y = P^T T P x with T = the banded symmetric Toeplitz blocks of BlockLO(offdiag=True)
+ * (ToeplitzLO.mult interfaces/linearoperators.py:582-595 applied per block, :672-674; the composition
+ * A = P.T*N*P of tests/test_2level_preconditioner.py:16-29, tests/test_coarse_operator.py:15-26):
+ * one TOD pass, no time-domain temporary.  band[nblocks][nband] = a_0 .. a_{nband-1} per block,
+ * nband <= cm2_amatvec_toeplitz_max_band(); block geometry as for cm2_amatvec_white. */
+int cm2_amatvec_toeplitz_max_band(void);
+int cm2_amatvec_toeplitz(const int32_t *pix, const double *cos2phi, const double *sin2phi,
+                         int64_t nt, int pol, const double *band, int nband, int64_t nblocks,
+                         int64_t blocksize, const int64_t *blk_start, const double *x, double *y,
+                         int64_t npix, cm2_stream_t stream);
+
 /* ---- a10/a11/a13: deflation, coarse operator, two-level preconditioner ---------------------- */
 /* Z is n x r, column-major (column i at Z + i*ldz), as DeflationLO stores columns (:1058-1062).
  * `work`: cm2_defl_work_doubles(r) doubles of device scratch. */
