@@ -687,8 +687,8 @@ def _is_pt(op):
 
 
 fusion_enabled = True
-FUSE_TOEPLITZ_A = False     # [P.T, N_toeplitz (<= 9 coefficients), P] -> cm2_amatvec_toeplitz   (off until validated on a B200)
-FUSE_FILTER_P = False       # [F_offset, P] -> cm2_pointing_filter_mu                           (off until validated on a B200)
+FUSE_TOEPLITZ_A = True      # [P.T, N_toeplitz (<= 9 coefficients), P] -> cm2_amatvec_toeplitz
+FUSE_FILTER_P = True        # [F_offset, P] -> cm2_pointing_filter_mu
 
 
 @lp.register_fuser

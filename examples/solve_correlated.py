@@ -120,7 +120,7 @@ def main():
                       residual_first_last=[float(res[0]), float(res[-1])] if len(res) else None),
            "samples_per_s_per_pcg_iter": nt * world / (dt / max(its, 1)),
            "A_apply_ms": a_ms, "A_apply_samples_per_s": nt * world / (a_ms * 1e-3),
-           "symmetry_rel": abs(uav - vau) / max(abs(uav), 1e-300),
+           "symmetry": {"u_Av": uav, "v_Au": vau, "rel": abs(uav - vau) / max(abs(uav), 1e-300)},
            "hbm_GB": torch.cuda.max_memory_allocated() / 1e9}
     if rank == 0:
         print(json.dumps(out))
