@@ -92,7 +92,9 @@ def main():
     # symmetry of the composed operator (F and N symmetric): <u, A v> = <v, A u>
     u = torch.randn(n, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7))
     v = torch.randn(n, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(8))
-    uav, vau = float(torch.dot(u, A._apply(v))), float(torch.dot(v, A._apply(u)))
+    Av, Au = A._apply(v), A._apply(u)
+    uav, vau = float(torch.dot(u, Av)), float(torch.dot(v, Au))
+    sym_scale = float(torch.linalg.norm(u) * torch.linalg.norm(Av))
 
     # device time of the A apply alone (CUDA events; the TOD streams are far larger than L2)
     for _ in range(3):
@@ -120,7 +122,9 @@ def main():
                       residual_first_last=[float(res[0]), float(res[-1])] if len(res) else None),
            "samples_per_s_per_pcg_iter": nt * world / (dt / max(its, 1)),
            "A_apply_ms": a_ms, "A_apply_samples_per_s": nt * world / (a_ms * 1e-3),
-           "symmetry": {"u_Av": uav, "v_Au": vau, "rel": abs(uav - vau) / max(abs(uav), 1e-300)},
+           "symmetry": {"u_Av": uav, "v_Au": vau, "rel": abs(uav - vau) / max(abs(uav), 1e-300),
+                        "rel_to_norms": abs(uav - vau) / max(sym_scale, 1e-300),
+                        "u_minus_v_norm": float(torch.linalg.norm(u - v))},
            "hbm_GB": torch.cuda.max_memory_allocated() / 1e9}
     if rank == 0:
         print(json.dumps(out))

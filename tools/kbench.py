@@ -102,6 +102,12 @@ def main():
     NT = cm.BlockLO(sc.ns, bands, offdiag=True)
     t = timeit(lambda: NT._apply(d), reps=5, warm=1); out["toeplitz64_ms"] = t
     out["toeplitz64_GFLOPs"] = 2.0 * (2 * 64 - 1) * nt / (t * 1e-3) / 1e9
+    for L in (3, 9):                            # the reference tests' composition: P^T T P in one TOD pass
+        ATs = P.T * cm.BlockLO(sc.ns, synthetic.toeplitz_bands(64, L), offdiag=True) * P
+        t = timeit(lambda: ATs._apply(x)); out["amatvec_toeplitz%d_ms" % L] = t
+        out["amatvec_toeplitz%d_GBs" % L] = gb(bpp * nt + 16 * n, t)
+    FP = F * P                                  # offset filter fused into the gather
+    t = timeit(lambda: FP._apply(x)); out["FP_fused_ms"] = t; out["FP_fused_GBs"] = gb((bpp + 8) * nt + 8 * n, t)
     for L in (256, 4096):
         NTf = cm.BlockLO(sc.ns, synthetic.toeplitz_bands(64, L), offdiag=True)
         t = timeit(lambda: NTf._apply(d), reps=3, warm=1)
