@@ -130,3 +130,55 @@ def test_fullsize_subscan_filters(cm, c2, order):
     mono[0::pol] = 3.0
     if order <= 1:      # from order 2 on the unflagged branch is the reference's non-orthogonal sum, not a projector
         assert (A * mono).abs().max().item() <= 1e-9 * 3.0 * (sc.nt / npix)
+
+
+@pytest.mark.parametrize("nband", [1, 3, 9])
+def test_fullsize_fused_toeplitz_amatvec(cm, c2, nband):
+    """P^T T P in one TOD pass over 1e8 samples (64 noise blocks): equal to the chain P, T, P^T with its
+    two TOD temporaries, symmetric, and -- with a one-coefficient band -- equal to the white-noise kernel."""
+    import torch
+    from cosmomap2_b200 import linearoperators as lo, synthetic
+    sc, P, N, npix, pol = c2["sc"], c2["P"], c2["N"], c2["npix"], c2["pol"]
+    rng = np.random.default_rng(3)
+    x = _dev(rng.standard_normal(pol * npix))
+    if nband == 1:
+        bands = [[w] for w in sc.weights]
+    else:
+        bands = synthetic.toeplitz_bands(sc.ndet, nband, seed=nband)
+    Nt = cm.BlockLO(sc.ns, bands, offdiag=True)
+    A = P.T * Nt * P
+    Ax = A * x
+    assert [type(f) for f in A.planned()] == [lo._FusedToeplitzA]
+    lo.fusion_enabled = False
+    try:
+        chain = (P.T * Nt * P) * x
+    finally:
+        lo.fusion_enabled = True
+    assert (chain - Ax).abs().max().item() <= 1e-11 * Ax.abs().max().item()
+    z = _dev(rng.standard_normal(pol * npix))
+    sym = abs(torch.dot(z, Ax).item() - torch.dot(x, A * z).item()) / (Ax.norm().item() * z.norm().item())
+    assert sym < 1e-12, sym
+    if nband == 1:
+        white = (P.T * N * P) * x
+        assert (white - Ax).abs().max().item() <= 1e-12 * Ax.abs().max().item()
+
+
+def test_fullsize_fused_filter_pointing(cm, c2):
+    """F P in one pass over 1e8 samples == the chain; a map constant in I is removed inside every subscan."""
+    import torch
+    from cosmomap2_b200 import linearoperators as lo
+    sc, P, npix, pol = c2["sc"], c2["P"], c2["npix"], c2["pol"]
+    F = cm.FilterLO(sc.nt, [sc.sub_len, sc.sub_start], sc.ns, sc.ndet, sc.pix)
+    x = _dev(np.random.default_rng(4).standard_normal(pol * npix))
+    FP = F * P
+    d = FP * x
+    assert [type(f) for f in FP.planned()] == [lo._FusedFilterP] and FP.planned()[0]._runs
+    chain = F * (P * x)
+    assert (chain - d).abs().max().item() <= 1e-11 * chain.abs().max().item()
+    mono = torch.zeros(pol * npix, dtype=torch.float64, device=x.device)
+    mono[0::pol] = 3.0
+    dm = FP * mono
+    # unflagged samples: exactly filtered; flagged samples inside a subscan carry -mean = -3 (FilterLO.mult :165)
+    pix = torch.as_tensor(sc.pix, device=x.device)
+    assert dm[pix >= 0].abs().max().item() <= 1e-9
+    assert dm.abs().max().item() <= 3.0 + 1e-9
