@@ -299,6 +299,61 @@ def case_next_rows():
     save("next_rows", **out)
 
 
+def case_fused_chains():
+    """The compositions the product collapses into single TOD passes, through the reference's own
+    operators: A = P.T*N*P with N = BlockLO(bs, t, offdiag=True) and bands of 2..9 coefficients
+    (tests/test_2level_preconditioner.py:16-29) on a scan with runs of equal pixels, flags and noise
+    blocks that are not multiples of the kernel's 8-sample chunks; F*P and P.T*F*N*F*P with the
+    offset filter (flagged samples inside subscans, one fully flagged subscan)."""
+    rng = np.random.default_rng(31)
+    out = {}
+    nb, bs = 5, 403
+    nt = nb * bs
+    npix = 40
+    # a scan: the pixel index drifts slowly, so consecutive samples share pixels (runs of 1..9 samples)
+    steps = rng.random(nt) < 0.25
+    pix = (np.cumsum(steps) % npix).astype(np.int64)
+    pix[rng.random(nt) < 0.05] = -1
+    phi = R.angles_gen(0.3, nt)
+    out.update(pix=pix, phi=phi, npix=npix, nb=nb, bs=bs)
+    # subscans: per block (detector) 4 subscans with gaps
+    L, S = make_subscans(rng, bs, 4)
+    out.update(sub_len=L, sub_start=S)
+    for pol in (1, 2, 3):
+        pp = pix.copy()
+        pts = R.ProcessTimeSamples(pp, npix, pol=pol, phi=phi)
+        npn = pts.get_new_pixel[0]
+        P = R.SparseLO(npn, nt, pp, pol=pol, angle_processed=pts)
+        x = rng.standard_normal(pol * npn)
+        out["pix_pol%d" % pol] = pp
+        out["npix_pol%d" % pol] = npn
+        out["x_pol%d" % pol] = x
+        for nband in (2, 3, 5, 9):
+            t = [rng.standard_normal(nband) * 0.5 ** np.arange(nband) + np.eye(1, nband)[0] * 2.0 for _ in range(nb)]
+            N = R.BlockLO(bs, t, offdiag=True)
+            out["t_pol%d_nband%d" % (pol, nband)] = np.array(t)
+            out["PtNPx_pol%d_nband%d" % (pol, nband)] = P.T * (N * (P * x))
+        # offset filter: the same scan with one subscan of block 1 fully flagged, processed on its own
+        pf = pix.copy()
+        s0 = bs * 1 + S[2]
+        pf[s0:s0 + L[2]] = -1
+        ptsf = R.ProcessTimeSamples(pf, npix, pol=pol, phi=phi)
+        npf = ptsf.get_new_pixel[0]
+        Pf = R.SparseLO(npf, nt, pf, pol=pol, angle_processed=ptsf)
+        F = R.FilterLO(nt, [L, S], bs, nb, Pf.pairs)
+        t = [rng.standard_normal(4) * 0.5 ** np.arange(4) + np.eye(1, 4)[0] * 2.0 for _ in range(nb)]
+        N = R.BlockLO(bs, t, offdiag=True)
+        xf = rng.standard_normal(pol * npf)
+        dF = F * (Pf * xf)
+        out["pixf_pol%d" % pol] = pf
+        out["npixf_pol%d" % pol] = npf
+        out["xf_pol%d" % pol] = xf
+        out["tF_pol%d" % pol] = np.array(t)
+        out["FPx_pol%d" % pol] = dF
+        out["PtFNFPx_pol%d" % pol] = Pf.T * (F * (N * dF))
+    save("fused_chains", **out)
+
+
 if __name__ == "__main__":
     print("scipy", scipy.__version__, "numpy", np.__version__)
     case_process_and_pointing()
@@ -307,3 +362,4 @@ if __name__ == "__main__":
     case_filter()
     case_pcg_and_deflation()
     case_next_rows()
+    case_fused_chains()

@@ -128,6 +128,50 @@ def check_filter_ops(impl):
         close((P.T * Fp * P) * x, g["A_y_pol%d" % pol], what="P^T F P x composed pol%d" % pol)
 
 
+def check_fused_chains(impl, expect_fused=None):
+    """P.T*N*P with short Toeplitz bands, F*P and P.T*F*N*F*P against the reference's own operators
+    (fixture fused_chains.npz).  ``expect_fused``: the product's linearoperators module, to assert
+    that the compositions really ran as the fused kernels."""
+    g = load("fused_chains")
+    nb, bs, npix = int(g["nb"]), int(g["bs"]), int(g["npix"])
+    nt = nb * bs
+    for pol in (1, 2, 3):
+        pix = g["pix"].copy()
+        pts = impl.ProcessTimeSamples(pix, npix, pol=pol, phi=g["phi"])
+        npn = pts.get_new_pixel[0]
+        assert npn == int(g["npix_pol%d" % pol])
+        exact(pix, g["pix_pol%d" % pol], "pix")
+        P = impl.SparseLO(npn, nt, pix, pol=pol, angle_processed=pts)
+        x = g["x_pol%d" % pol]
+        for nband in (2, 3, 5, 9):
+            t = g["t_pol%d_nband%d" % (pol, nband)]
+            N = impl.BlockLO(bs, [t[i] for i in range(nb)], offdiag=True)
+            A = P.T * N * P
+            close(A * x, g["PtNPx_pol%d_nband%d" % (pol, nband)], what="P^T N P x pol%d nband%d" % (pol, nband))
+            if expect_fused is not None:
+                assert [type(f) for f in A.planned()] == [expect_fused._FusedToeplitzA]
+        pf = g["pix"].copy()
+        L, S = g["sub_len"], g["sub_start"]
+        s0 = bs * 1 + int(S[2])
+        pf[s0:s0 + int(L[2])] = -1
+        ptsf = impl.ProcessTimeSamples(pf, npix, pol=pol, phi=g["phi"])
+        npf = ptsf.get_new_pixel[0]
+        assert npf == int(g["npixf_pol%d" % pol])
+        exact(pf, g["pixf_pol%d" % pol], "pix (filter case)")
+        Pf = impl.SparseLO(npf, nt, pf, pol=pol, angle_processed=ptsf)
+        F = impl.FilterLO(nt, [L, S], bs, nb, Pf.pairs)
+        tF = g["tF_pol%d" % pol]
+        N = impl.BlockLO(bs, [tF[i] for i in range(nb)], offdiag=True)
+        xf = g["xf_pol%d" % pol]
+        FP = F * Pf
+        close(FP * xf, g["FPx_pol%d" % pol], what="F P x pol%d" % pol)
+        A = Pf.T * F * N * F * Pf
+        close(A * xf, g["PtFNFPx_pol%d" % pol], what="P^T F N F P x pol%d" % pol)
+        if expect_fused is not None:
+            assert [type(f) for f in FP.planned()] == [expect_fused._FusedFilterP]
+            assert isinstance(A.planned()[-1], expect_fused._FusedFilterP)
+
+
 def build_solve_system(impl, g):
     pol = int(g["pol"])
     pix = g["pix_in"].copy()

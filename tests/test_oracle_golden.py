@@ -34,6 +34,11 @@ def test_oracle_next_rows_ground_and_legendre_filters():
     gc.check_next_rows(oracle)
 
 
+def test_oracle_fused_chains():
+    """P.T*N*P with short Toeplitz bands, F*P and P.T*F*N*F*P: the oracle against the reference's own run."""
+    gc.check_fused_chains(oracle)
+
+
 def test_oracle_reorganize_map():
     rng = np.random.default_rng(0)
     nside, npix = 8, 40
