@@ -539,6 +539,101 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter_mu(const int32_t *__re
     }
 }
 
+// Fused y = P^T (P x - sum_k c_k L_k(x_t)) over the unflagged samples inside subscans: the Legendre-
+// filtered A-matvec in ONE pass over the TOD, given the per-subscan coefficients (k_poly_seg_coef,
+// filter_runs.cu).  Same tile / subscan lookup as k_amatvec_filter_mu; x_t = -1 + 2 (t - a)/(len - 1).
+struct SegPoly {
+    const int64_t *start, *end;   // nseg, sorted, non-overlapping (the subscans this path handles)
+    const double *coef;           // nseg x NK
+    const int32_t *tile_seg;
+    const uint8_t *tile_flag;
+    int64_t nseg;
+};
+
+template <int NK>
+__device__ __forceinline__ double poly_eval(const double (&cf)[NK], double xt) {
+    double L[NK];
+    legendre<NK>(xt, L);
+    double p = cf[0];
+#pragma unroll
+    for (int k = 1; k < NK; ++k) p = fma(cf[k], L[k], p);
+    return p;
+}
+
+template <int POL, int NK>
+__global__ void __launch_bounds__(BLOCK) k_amatvec_filter_poly_mu(const int32_t *__restrict__ pix, const double *__restrict__ cs,
+                                                                  const double *__restrict__ sn, int64_t nt, SegPoly sg,
+                                                                  const double *__restrict__ x, double *__restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
+    const int64_t ntiles = (nt + TILE - 1) / TILE;
+    RunState<POL> rs;
+    rs.ph = rs.pt = -1;
+    rs.single = true;
+#pragma unroll
+    for (int k = 0; k < POL; ++k) rs.acc[k] = rs.head[k] = 0.0;
+    for (int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
+        const int64_t t0 = tile * TILE + (int64_t)lane * K;
+        int p[K];
+        double c[K], s[K];
+        load_pix(pix, t0, nt, p);
+        if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
+        const int flag = __ldg(sg.tile_flag + tile);
+        const int k0 = __ldg(sg.tile_seg + tile);
+        run_merge<POL, POL>(y, rs);            // previous tile, after this tile's loads have been issued
+        double pv[K];                          // the polynomial at the lane's samples
+        if (flag == 0) {                       // the whole tile lies in a gap
+#pragma unroll
+            for (int j = 0; j < K; ++j) { pv[j] = 0.0; p[j] = -1; }
+        } else {
+            int64_t k = k0;
+            if (flag != 1) {
+                while (k < sg.nseg && __ldg(sg.end + k) <= t0) ++k;
+            }
+            int64_t a = k < sg.nseg ? __ldg(sg.start + k) : INT64_MAX, b = k < sg.nseg ? __ldg(sg.end + k) : INT64_MAX;
+            if (flag == 1 || (t0 >= a && t0 + K <= b)) {   // the lane's chunk lies inside one subscan
+                double cf[NK];
+#pragma unroll
+                for (int i = 0; i < NK; ++i) cf[i] = __ldg(sg.coef + k * NK + i);
+                const double step = b - a > 1 ? 2.0 / (double)(b - a - 1) : 0.0;
+                const double x0 = fma((double)(t0 - a), step, -1.0);
+#pragma unroll
+                for (int j = 0; j < K; ++j) pv[j] = poly_eval<NK>(cf, fma((double)j, step, x0));
+            } else if (t0 + K <= a) {                      // ... or entirely in a gap
+#pragma unroll
+                for (int j = 0; j < K; ++j) { pv[j] = 0.0; p[j] = -1; }
+            } else {                                       // a subscan boundary inside the lane's 8 samples
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int64_t t = t0 + j;
+                    while (k < sg.nseg && t >= b) {
+                        ++k;
+                        a = k < sg.nseg ? __ldg(sg.start + k) : INT64_MAX;
+                        b = k < sg.nseg ? __ldg(sg.end + k) : INT64_MAX;
+                    }
+                    pv[j] = 0.0;
+                    if (k >= sg.nseg || t < a) { p[j] = -1; continue; }
+                    double cf[NK];
+#pragma unroll
+                    for (int i = 0; i < NK; ++i) cf[i] = __ldg(sg.coef + k * NK + i);
+                    const double step = b - a > 1 ? 2.0 / (double)(b - a - 1) : 0.0;
+                    pv[j] = poly_eval<NK>(cf, fma((double)(t - a), step, -1.0));
+                }
+            }
+        }
+        double xv[K][POL], v[K];
+        gather_x<POL>(x, p, xv);
+#pragma unroll
+        for (int j = 0; j < K; ++j) v[j] = project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0) - pv[j];
+        run_compress<POL, POL>(y, p, [&](int j, double (&o)[POL]) {
+            if constexpr (POL == 1) { o[0] = v[j]; }
+            else if constexpr (POL == 2) { o[0] = v[j] * c[j]; o[1] = v[j] * s[j]; }
+            else { o[0] = v[j]; o[1] = v[j] * c[j]; o[2] = v[j] * s[j]; }
+        }, rs);
+    }
+    run_merge<POL, POL>(y, rs);
+}
+
 // d = F P x for the offset filter in one pass (no P x temporary, no second pass for F): the subscan
 // means of P x come from the run table (k_seg_mean), so d_t = (P x)_t - mu_seg(t) inside subscans --
 // also on flagged samples, where (P x)_t = 0, exactly as FilterLO.mult subtracts the mean from them
@@ -1205,6 +1300,42 @@ extern "C" int cm2_pointing_filter_mu(const int32_t *pix, const double *c, const
     else k_pointing_filter_mu<3><<<tod_grid(k_pointing_filter_mu<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, d);
     CM2_LAUNCHED();
     return CM2_OK;
+}
+
+template <int POL>
+static int dispatch_amatvec_filter_poly_mu(int nk, const int32_t *pix, const double *c, const double *s, int64_t nt,
+                                           const SegPoly &sg, const double *x, double *y, cudaStream_t st) {
+#define CM2_POLY_MU(NK) k_amatvec_filter_poly_mu<POL, NK><<<tod_grid(k_amatvec_filter_poly_mu<POL, NK>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, y)
+    switch (nk) {
+        case 2: CM2_POLY_MU(2); break;
+        case 3: CM2_POLY_MU(3); break;
+        case 4: CM2_POLY_MU(4); break;
+        default: CM2_POLY_MU(5); break;
+    }
+#undef CM2_POLY_MU
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+/* single-TOD-pass P^T F_K P given the per-subscan Legendre coefficients (cm2_filter_poly_seg_coef);
+ * accumulate != 0 adds to y instead of overwriting it */
+extern "C" int cm2_amatvec_filter_poly_mu(const int32_t *pix, const double *c, const double *s, int64_t nt, int pol,
+                                          const int64_t *seg_start, const int64_t *seg_end, const double *seg_coef,
+                                          const int32_t *tile_seg, const uint8_t *tile_flag, int64_t nseg, int poly_order,
+                                          const double *x, double *y, int64_t npix, int accumulate, cm2_stream_t stream) {
+    int rc = check_tod(pix, c, s, nt, pol);
+    if (rc) return rc;
+    CM2_REQUIRE(npix >= 0 && nseg >= 0, "negative size");
+    if (poly_order < 1 || poly_order > 4)
+        return set_error(CM2_ERR_UNSUPPORTED, "run-table Legendre A-matvec: poly_order=%d, orders 1..4 are supported", poly_order);
+    cudaStream_t st = as_stream(stream);
+    if (npix > 0 && !accumulate) CM2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)npix * pol, st));
+    if (nt == 0 || npix == 0 || nseg == 0) return CM2_OK;
+    SegPoly sg{seg_start, seg_end, seg_coef, tile_seg, tile_flag, nseg};
+    const int nk = poly_order + 1;
+    if (pol == 1) return dispatch_amatvec_filter_poly_mu<1>(nk, pix, c, s, nt, sg, x, y, st);
+    if (pol == 2) return dispatch_amatvec_filter_poly_mu<2>(nk, pix, c, s, nt, sg, x, y, st);
+    return dispatch_amatvec_filter_poly_mu<3>(nk, pix, c, s, nt, sg, x, y, st);
 }
 
 /* fused P^T F_K P, Legendre subscan filter of order 1..4 */

@@ -521,6 +521,24 @@ class _FusedWhiteA(lp.LinearOperator):
 FILTER_RUN_TABLE = True     # single-TOD-pass P^T F P through the run-compressed u_k table
 
 
+def _tile_tables(seg_start, seg_end, nseg, nt):
+    """Per 256-sample tile of the TOD: the first segment whose end lies beyond the tile's first sample
+    (int32) and a flag -- 0 = the tile lies in a gap, 1 = inside that segment, 2 = a boundary falls inside."""
+    dev = seg_start.device
+    ntiles = (nt + 255) // 256
+    tile_t0 = torch.arange(ntiles, dtype=torch.int64, device=dev) * 256
+    tile_seg = torch.searchsorted(seg_end, tile_t0, right=True)
+    kk = torch.clamp(tile_seg, max=nseg - 1)
+    a, b = seg_start[kk], seg_end[kk]
+    t1 = torch.clamp(tile_t0 + 256, max=nt)
+    inside = (tile_seg < nseg) & (a <= tile_t0) & (t1 <= b)
+    outside = (tile_seg >= nseg) | (a >= t1)
+    tile_flag = torch.full((ntiles,), 2, dtype=torch.uint8, device=dev)
+    tile_flag[inside] = 1
+    tile_flag[outside] = 0
+    return tile_seg.to(torch.int32), tile_flag
+
+
 def _build_filter_runs(P, F):
     """Run-compressed table of u_k = P^T 1_k per subscan + the per-tile subscan lookup (csrc/filter_runs.cu),
     built on the device; False when the subscans are unsorted or the pointing has no runs."""
@@ -549,21 +567,10 @@ def _build_filter_runs(P, F):
             dv.ptr(F._seg_start), dv.ptr(F._seg_end), F.nseg, dv.ptr(runidx), dv.ptr(run_pix), dv.ptr(run_mom),
             dv.ptr(seg_first), dv.ptr(seg_nruns), st)
     del pixm, runidx
-    # first segment whose end lies beyond the first sample of every 256-sample tile
-    ntiles = (nt + 255) // 256
-    tile_t0 = torch.arange(ntiles, dtype=torch.int64, device=dev) * 256
-    tile_seg = torch.searchsorted(F._seg_end, tile_t0, right=True)
-    kk = torch.clamp(tile_seg, max=F.nseg - 1)
-    a, b = F._seg_start[kk], F._seg_end[kk]
-    t1 = torch.clamp(tile_t0 + 256, max=nt)
-    inside = (tile_seg < F.nseg) & (a <= tile_t0) & (t1 <= b)
-    outside = (tile_seg >= F.nseg) | (a >= t1)
-    tile_flag = torch.full((ntiles,), 2, dtype=torch.uint8, device=dev)
-    tile_flag[inside] = 1
-    tile_flag[outside] = 0
+    tile_seg, tile_flag = _tile_tables(F._seg_start, F._seg_end, F.nseg, nt)
     mu = torch.empty(max(F.nseg, 1), dtype=torch.float64, device=dev)
     return dict(run_pix=run_pix, run_mom=run_mom, seg_first=seg_first, seg_nruns=seg_nruns, nruns=nruns,
-                tile_seg=tile_seg.to(torch.int32), tile_flag=tile_flag, mu=mu)
+                tile_seg=tile_seg, tile_flag=tile_flag, mu=mu)
 
 
 def _filter_runs(P, F):
@@ -607,12 +614,80 @@ class _FusedFilterA(lp.LinearOperator):
         return y
 
 
+FILTER_POLY_RUN_TABLE = False     # experimental: single-TOD-pass P^T F_K P through a Legendre run table (not yet measured)
+POLY_RUN_MIN_PIVOT = 0.02         # subscans whose scaled Gram matrix has a smaller Cholesky pivot keep the per-subscan kernel
+
+
+def _build_poly_runs(P, F):
+    """Set-up of the single-pass Legendre A-matvec (csrc/filter_runs.cu): per subscan W (c = W S) and its
+    conditioning; the subscans the reference filters and whose Gram matrix is well conditioned ('easy')
+    get a run table of Legendre-weighted sums and tile tables; ill-conditioned ones ('hard': most of the
+    subscan flagged) stay with the per-subscan kernel; the others contribute nothing (the reference skips
+    them).  False when the path does not apply."""
+    order = F.poly_order
+    nk = order + 1
+    if not (1 <= order <= 4 and F._sorted and F.nseg > 0):
+        return False
+    nt, st = P.nrows, _stream()
+    dev = P._pix_dev.device
+    ss, se = F._seg_start_host, F._seg_end_host
+    W_all = torch.empty(F.nseg * nk * nk, dtype=torch.float64, device=dev)
+    info = torch.empty(2 * F.nseg, dtype=torch.float64, device=dev)
+    dv.call("cm2_filter_poly_gram", dv.ptr(P._pix_dev), dv.ptr(F._seg_start), dv.ptr(F._seg_end), F.nseg, order,
+            dv.ptr(W_all), dv.ptr(info), st)
+    info_h = dv.to_host(info).reshape(-1, 2)
+    cnt, piv = info_h[:, 0], info_h[:, 1]
+    alive = cnt > order
+    easy = alive & ((cnt == (se - ss)) | (piv >= POLY_RUN_MIN_PIVOT))
+    hard = alive & ~easy
+    ie, ih = np.nonzero(easy)[0], np.nonzero(hard)[0]
+    ne = len(ie)
+    if ne == 0:
+        return False
+    seg_start = dv.to_dev(ss[ie], torch.int64)
+    seg_end = dv.to_dev(se[ie], torch.int64)
+    W = W_all.view(F.nseg, nk * nk)[dv.to_dev(ie, torch.int64)].contiguous().view(-1)
+    del W_all, info
+    flags = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
+    pixm = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
+    dv.call("cm2_filter_runs_mark", dv.ptr(P._pix_dev), dv.ptr(seg_start), dv.ptr(seg_end), ne, nt,
+            dv.ptr(flags), dv.ptr(pixm), st)
+    runidx = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    scratch = torch.empty(int(dv.call("cm2_scan_scratch_bytes", nt)) // 8 + 1, dtype=torch.int64, device=dev)
+    dv.call("cm2_weights_old2new", dv.ptr(flags), nt, dv.ptr(runidx), dv.ptr(count), dv.ptr(scratch), st)
+    nruns = int(count.item())
+    del flags, scratch
+    if nruns == 0 or 2 * nruns > nt:
+        return False
+    run_pix = torch.empty(nruns, dtype=torch.int32, device=dev)
+    run_mom = torch.empty(3 * nk * nruns, dtype=torch.float64, device=dev)
+    seg_first = torch.empty(ne, dtype=torch.int64, device=dev)
+    seg_nruns = torch.empty(ne, dtype=torch.int32, device=dev)
+    dv.call("cm2_filter_poly_runs_fill", dv.ptr(pixm), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.pol,
+            dv.ptr(seg_start), dv.ptr(seg_end), ne, order, dv.ptr(runidx), dv.ptr(run_pix), dv.ptr(run_mom),
+            dv.ptr(seg_first), dv.ptr(seg_nruns), st)
+    del pixm, runidx
+    tile_seg, tile_flag = _tile_tables(seg_start, seg_end, ne, nt)
+    rt = dict(nseg=ne, seg_start=seg_start, seg_end=seg_end, W=W, run_pix=run_pix, run_mom=run_mom,
+              seg_first=seg_first, seg_nruns=seg_nruns, nruns=nruns, tile_seg=tile_seg, tile_flag=tile_flag,
+              coef=torch.empty(ne * nk, dtype=torch.float64, device=dev), nhard=len(ih))
+    if len(ih):
+        rt["hard_start"] = dv.to_dev(ss[ih], torch.int64)
+        rt["hard_end"] = dv.to_dev(se[ih], torch.int64)
+        rt["hard_maxlen"] = int((se[ih] - ss[ih]).max())
+    return rt
+
+
 class _FusedPolyFilterA(lp.LinearOperator):
     """P^T F_K P for the Legendre filter (poly_order 1..4) as one kernel: one CTA per subscan, the
-    subscan's P x kept in shared memory between the moment pass and the scatter pass."""
+    subscan's P x kept in shared memory between the moment pass and the scatter pass.  With
+    ``FILTER_POLY_RUN_TABLE`` (experimental) the well-conditioned subscans go through the single-TOD-pass
+    scheme of the offset filter instead: coefficients from a Legendre run table, then one streaming pass."""
 
     def __init__(self, P, F):
         self.P, self.F = P, F
+        self._runs = None
         n = P.pol * P.ncols
         super(_FusedPolyFilterA, self).__init__(n, n, matvec=self._run, symmetric=True, device=True)
 
@@ -621,12 +696,31 @@ class _FusedPolyFilterA(lp.LinearOperator):
         return (1 <= F.poly_order <= int(dv.call("cm2_amatvec_filter_poly_max_order")) and F._sorted
                 and (F._max_seg_len // 256 + 2) * 256 * 12 <= 200 * 1024)
 
+    def _per_subscan(self, seg_start, seg_end, nseg, max_len, x, y):
+        P, F = self.P, self.F
+        dv.call("cm2_amatvec_filter_poly", dv.ptr(P._pix_dev), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.nrows,
+                P.pol, dv.ptr(seg_start), dv.ptr(seg_end), nseg, max_len, F.poly_order, dv.ptr(x),
+                dv.ptr(y), P.ncols, _stream())
+        return y
+
     def _run(self, x):
         P, F = self.P, self.F
         y = dv.empty_f64(P.ncols * P.pol)
-        dv.call("cm2_amatvec_filter_poly", dv.ptr(P._pix_dev), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.nrows,
-                P.pol, dv.ptr(F._seg_start), dv.ptr(F._seg_end), F.nseg, F._max_seg_len, F.poly_order, dv.ptr(x),
-                dv.ptr(y), P.ncols, _stream())
+        if self._runs is None:
+            self._runs = _build_poly_runs(P, F) if FILTER_POLY_RUN_TABLE else False
+        rt = self._runs
+        if not rt:
+            return self._per_subscan(F._seg_start, F._seg_end, F.nseg, F._max_seg_len, x, y)
+        dv.call("cm2_filter_poly_seg_coef", dv.ptr(rt["run_pix"]), dv.ptr(rt["run_mom"]), dv.ptr(rt["seg_first"]),
+                dv.ptr(rt["seg_nruns"]), rt["nseg"], P.pol, F.poly_order, dv.ptr(rt["W"]), dv.ptr(x),
+                dv.ptr(rt["coef"]), _stream())
+        dv.call("cm2_amatvec_filter_poly_mu", dv.ptr(P._pix_dev), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.nrows,
+                P.pol, dv.ptr(rt["seg_start"]), dv.ptr(rt["seg_end"]), dv.ptr(rt["coef"]), dv.ptr(rt["tile_seg"]),
+                dv.ptr(rt["tile_flag"]), rt["nseg"], F.poly_order, dv.ptr(x), dv.ptr(y), P.ncols, 0, _stream())
+        if rt["nhard"]:
+            y2 = self._per_subscan(rt["hard_start"], rt["hard_end"], rt["nhard"], rt["hard_maxlen"], x,
+                                   dv.empty_f64(P.ncols * P.pol))
+            dv.call("cm2_axpby", 1.0, dv.ptr(y2), 1.0, dv.ptr(y), y.numel(), _stream())
         return y
 
 

@@ -172,6 +172,31 @@ int cm2_amatvec_filter_mu(const int32_t *pix, const double *cos2phi, const doubl
                           int64_t nseg, const double *x, double *y, int64_t npix,
                           cm2_stream_t stream);
 
+/* Single-TOD-pass P^T F_K P x for the Legendre filter, poly_order 1..4 (FilterLO.polyfilter
+ * interfaces/linearoperators.py:170-204 inside the composition of src/test_M2_precond_onto_real_data.py:37-41;
+ * csrc/filter_runs.cu).  The fitted polynomial of a subscan is sum_k c_k L_k(x_t) with c = W S, S the
+ * Legendre moments of the unflagged samples and W fixed by the pointing.  Set-up: poly_gram (per subscan
+ * W[nk*nk] and info = {unflagged samples, smallest pivot of the scaled Cholesky factor of the Gram matrix;
+ * 1 without flags, 0 for a subscan the reference skips}; the caller keeps the well-conditioned subscans),
+ * runs_mark + scan as for the offset filter, poly_runs_fill (run_mom[nruns][3*nk] = sums of L_k, L_k cos,
+ * L_k sin over each run).  Apply: poly_seg_coef (coef[nseg][nk] = W S from the run table), then
+ * amatvec_filter_poly_mu: y (+)= P^T (P x - polynomial) in one TOD pass; tile tables as for
+ * cm2_amatvec_filter_mu.  Experimental: not selected by default. */
+int cm2_filter_poly_gram(const int32_t *pix, const int64_t *seg_start, const int64_t *seg_end,
+                         int64_t nseg, int poly_order, double *W, double *info, cm2_stream_t stream);
+int cm2_filter_poly_runs_fill(const int32_t *pix_masked, const double *cos2phi, const double *sin2phi,
+                              int pol, const int64_t *seg_start, const int64_t *seg_end, int64_t nseg,
+                              int poly_order, const int32_t *runidx, int32_t *run_pix, double *run_mom,
+                              int64_t *seg_first, int32_t *seg_nruns, cm2_stream_t stream);
+int cm2_filter_poly_seg_coef(const int32_t *run_pix, const double *run_mom, const int64_t *seg_first,
+                             const int32_t *seg_nruns, int64_t nseg, int pol, int poly_order,
+                             const double *W, const double *x, double *coef, cm2_stream_t stream);
+int cm2_amatvec_filter_poly_mu(const int32_t *pix, const double *cos2phi, const double *sin2phi,
+                               int64_t nt, int pol, const int64_t *seg_start, const int64_t *seg_end,
+                               const double *seg_coef, const int32_t *tile_seg, const uint8_t *tile_flag,
+                               int64_t nseg, int poly_order, const double *x, double *y, int64_t npix,
+                               int accumulate, cm2_stream_t stream);
+
 /* d = F P x for the offset filter in one TOD pass (the first two factors of a chain such as
  * P.T*F*N*F*P): d_t = (P x)_t - mu_seg(t) inside subscans -- flagged samples included, as
  * FilterLO.mult does (interfaces/linearoperators.py:165) -- and 0 in the gaps; seg_mu from

@@ -198,3 +198,53 @@ def test_fused_filter_pointing_falls_back_without_runs(cm):
             out.append(FP * x)
             assert isinstance(FP.planned()[0], lo._FusedFilterP) and FP.planned()[0]._runs is False
     gc.close(out[1], out[0])
+
+
+# ---- experimental paths: written after the round's GPU budget was spent; run with CM2_EXPERIMENTAL=1 ----
+import os  # noqa: E402
+
+EXPERIMENTAL = os.environ.get("CM2_EXPERIMENTAL") == "1"
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="experimental path, not yet run on a B200 (set CM2_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("pol", [1, 3])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_poly_run_table_path(cm, pol, order):
+    """P^T F_K P through the Legendre run table (one TOD pass) == the per-subscan kernel == oracle, with
+    scattered flags, a subscan that keeps only its first third (ill-conditioned: stays with the per-subscan
+    kernel) and a subscan with fewer unflagged samples than the order (skipped by the reference)."""
+    import oracle
+    from cosmomap2_b200 import linearoperators as lo
+    sc = _raster(nt=300000, ndet=6, seed=8, flag_turnarounds=True)
+    rng = np.random.default_rng(3)
+    sc.pix[rng.random(sc.nt) < 0.02] = -1
+    a = 1 * sc.ns + int(sc.sub_start[3])
+    sc.pix[a + int(sc.sub_len[3]) // 3:a + int(sc.sub_len[3])] = -1
+    a = 4 * sc.ns + int(sc.sub_start[7])
+    keep = sc.pix[a]
+    sc.pix[a:a + int(sc.sub_len[7])] = -1
+    sc.pix[a] = keep
+    res = {}
+    for name, impl, table in (("oracle", oracle, None), ("table", cm, True), ("subscan", cm, False)):
+        pix = sc.pix.astype(np.int64)
+        pts = impl.ProcessTimeSamples(pix, sc.npix_full, pol=pol, phi=sc.phi)
+        npix = pts.get_new_pixel[0]
+        P = impl.SparseLO(npix, sc.nt, pix, pol=pol, angle_processed=pts)
+        F = impl.FilterLO(sc.nt, [sc.sub_len, sc.sub_start], sc.ns, sc.ndet, pix, poly_order=order)
+        x = np.random.default_rng(4).standard_normal(pol * npix)
+        if table is None:
+            res[name] = P.T * (F * (P * x))
+            continue
+        old = lo.FILTER_POLY_RUN_TABLE
+        lo.FILTER_POLY_RUN_TABLE = table
+        try:
+            A = P.T * F * P
+            res[name] = A * x
+            fused = [f for f in A.planned() if isinstance(f, lo._FusedPolyFilterA)][0]
+            assert bool(fused._runs) == table
+            if table:
+                assert fused._runs["nhard"] >= 1
+        finally:
+            lo.FILTER_POLY_RUN_TABLE = old
+    gc.close(res["subscan"], res["oracle"], what="per-subscan kernel")
+    gc.close(res["table"], res["oracle"], what="run-table path")

@@ -156,3 +156,34 @@ def test_small_utilities_of_the_reference_surface():
     one = np.arange(10.0)
     cm.subtract_offset(one, np.array([0, 9]), 1)
     assert one[0] == -4.5 and one[9] == 4.5 and one[5] == 5.0
+
+
+def test_tile_tables_against_brute_force():
+    """The per-tile subscan lookup the single-pass filter kernels use (linearoperators._tile_tables)."""
+    import torch
+    from cosmomap2_b200 import linearoperators as lo
+    rng = np.random.default_rng(0)
+    for trial in range(30):
+        nseg = int(rng.integers(1, 12))
+        lens = rng.integers(1, 900, nseg)
+        gaps = rng.integers(0, 400, nseg + 1)
+        start = np.cumsum(gaps[:-1]) + np.concatenate([[0], np.cumsum(lens[:-1])])
+        end = start + lens
+        nt = int(end[-1] + gaps[-1])
+        tile_seg, tile_flag = lo._tile_tables(torch.as_tensor(start), torch.as_tensor(end), nseg, nt)
+        ntiles = (nt + 255) // 256
+        assert tile_seg.dtype == torch.int32 and tile_seg.numel() == ntiles and tile_flag.numel() == ntiles
+        inside = np.zeros(nt, dtype=bool)
+        for a, b in zip(start, end):
+            inside[a:b] = True
+        for i in range(ntiles):
+            t0, t1 = 256 * i, min(256 * i + 256, nt)
+            k = int(np.searchsorted(end, t0, side="right"))        # first segment ending beyond t0
+            assert int(tile_seg[i]) == k
+            if not inside[t0:t1].any():
+                want = 0
+            elif k < nseg and start[k] <= t0 and t1 <= end[k]:
+                want = 1
+            else:
+                want = 2
+            assert int(tile_flag[i]) == want, (trial, i)

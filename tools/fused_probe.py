@@ -73,6 +73,18 @@ def main():
     out["FP_fused_GBs"] = (28.0 * nt + 24.0 * npix) / (t * 1e-3) / 1e9
     out["FP_chain_ms"] = tc
     out["FP_fused_vs_chain_relerr"] = float((d - dc).abs().max() / dc.abs().max())
+    if os.environ.get("CM2_EXPERIMENTAL") == "1":        # Legendre run-table path against the per-subscan kernel
+        for order in (1, 3):
+            Fk = cm.FilterLO(nt, [sub_len, sub_start], ns, ndet, pts._pix_dev, poly_order=order)
+            res = {}
+            for table in (False, True):
+                lo.FILTER_POLY_RUN_TABLE = table
+                Ak = P.T * Fk * P
+                tk = timeit(lambda: Ak._apply(x))
+                res[table] = Ak._apply(x)
+                out["amatvec_leg%d_%s_ms" % (order, "table" if table else "subscan")] = tk
+            lo.FILTER_POLY_RUN_TABLE = False
+            out["amatvec_leg%d_table_vs_subscan_relerr" % order] = float((res[True] - res[False]).abs().max() / res[False].abs().max())
     print(json.dumps(out))
 
 
