@@ -187,3 +187,90 @@ def test_tile_tables_against_brute_force():
             else:
                 want = 2
             assert int(tile_flag[i]) == want, (trial, i)
+
+
+def test_run_table_legendre_scheme_equals_polyfilter():
+    """The arithmetic behind the single-TOD-pass Legendre A-matvec (csrc/filter_runs.cu: c = W S with S from
+    a run table of Legendre-weighted sums, W = diag(1/||L_k||^2) without flags and the inverse Gram matrix
+    otherwise, ill-conditioned subscans left to the per-subscan kernel), restated in NumPy, against the
+    oracle's FilterLO.polyfilter on random subscan sets with scattered flags, heavy flags and a subscan
+    that keeps only its first third."""
+    import oracle
+
+    def legvals(x, nk):
+        L = np.empty((len(x), nk))
+        L[:, 0] = 1.0
+        if nk > 1:
+            L[:, 1] = x
+        for n in range(1, nk - 1):
+            L[:, n + 1] = ((2 * n + 1) * x * L[:, n] - n * L[:, n - 1]) / (n + 1)
+        return L
+
+    rng = np.random.default_rng(0)
+    worst, nhard = 0.0, 0
+    for trial in range(80):
+        order = int(rng.integers(1, 5))
+        nk = order + 1
+        nsub = int(rng.integers(1, 6))
+        lens = rng.integers(1, 300, nsub)
+        gaps = rng.integers(0, 30, nsub + 1)
+        starts = np.cumsum(gaps[:-1]) + np.concatenate([[0], np.cumsum(lens[:-1])])
+        nt = int(starts[-1] + lens[-1] + gaps[-1])
+        npix = 20
+        pix = np.sort(rng.integers(0, npix, nt)).astype(np.int64)
+        mode = trial % 4
+        if mode == 1:
+            pix[rng.random(nt) < 0.05] = -1
+        elif mode == 2:
+            pix[rng.random(nt) < 0.6] = -1
+        elif mode == 3:
+            s = int(rng.integers(0, nsub))
+            pix[starts[s] + lens[s] // 3:starts[s] + lens[s]] = -1
+        phi = rng.uniform(0, np.pi, nt)
+        c, sn = np.cos(2 * phi), np.sin(2 * phi)
+        x = rng.normal(size=3 * npix)
+        good = pix >= 0
+        d = np.zeros(nt)
+        d[good] = x[3 * pix[good]] + x[3 * pix[good] + 1] * c[good] + x[3 * pix[good] + 2] * sn[good]
+        ref = oracle.FilterLO(nt, [lens, starts], nt, 1, pix, poly_order=order) * d
+        out = np.zeros(nt)
+        for a, ln in zip(starts, lens):
+            m = good[a:a + ln]
+            if m.sum() <= order:
+                continue                                    # the reference skips the subscan
+            L = legvals(np.linspace(-1, 1, ln) if ln > 1 else np.array([-1.0]), nk)
+            S = np.zeros(nk)                                # moments from the run table
+            t = a
+            while t < a + ln:
+                if pix[t] < 0:
+                    t += 1
+                    continue
+                u = t
+                while u < a + ln and pix[u] == pix[t]:
+                    u += 1
+                idx = np.arange(t, u)
+                p = pix[t]
+                S += (L[idx - a].sum(0) * x[3 * p] + (L[idx - a] * c[idx, None]).sum(0) * x[3 * p + 1]
+                      + (L[idx - a] * sn[idx, None]).sum(0) * x[3 * p + 2])
+                t = u
+            if m.sum() == ln:
+                W = np.diag(1.0 / (L * L).sum(0))
+            else:
+                G = L[m].T @ L[m]
+                dsc = 1.0 / np.sqrt(np.diag(G))
+                Gs = G * dsc[:, None] * dsc[None, :]
+                try:
+                    minpiv = (np.diag(np.linalg.cholesky(Gs)) ** 2).min()
+                except np.linalg.LinAlgError:
+                    minpiv = 0.0
+                if minpiv < 0.02:                           # POLY_RUN_MIN_PIVOT: the per-subscan kernel's job
+                    nhard += 1
+                    out[a:a + ln] = ref[a:a + ln]
+                    continue
+                W = np.linalg.inv(Gs) * dsc[:, None] * dsc[None, :]
+            val = d[a:a + ln] - L @ (W @ S)
+            out[a:a + ln][m] = val[m]
+        if good.any():
+            worst = max(worst, np.abs(out - ref)[good].max() / max(np.abs(d).max(), 1e-300))
+    assert worst < 1e-11, worst
+    assert nhard > 0                                        # the ill-conditioned branch was exercised
