@@ -6,7 +6,8 @@ bench.py -- BASELINE.json's metric on BASELINE.json's configuration.
     workload : configs[1] -- synthetic raster scan, 1e8 samples per GPU, IQU nside=512, white noise
                (64 detector blocks), block-diagonal-preconditioned PCG on A = P^T N^-1 P
     N GPUs   : weak scaling -- every rank owns its own 64 detectors x 1e8/64 samples of the same sky
-               patch; one NCCL all-reduce of the map-domain A p per iteration
+               patch; per iteration one local TOD pass + one kernel that fuses the map exchange over
+               NVLink peer memory with the pixel-sharded M_BD / CG vector work (csrc/pcg_sharded.cu)
 
     python bench.py --gpus N --steps K --warmup W        (torchrun launches it for N > 1)
     python bench.py --impl reference ...                  (CPU arm: the oracle port on host cores)
@@ -58,7 +59,7 @@ def emit(line):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nt", type=int, default=100000000, help="TOD samples per GPU (configs[1]: 1e8)")
@@ -188,7 +189,7 @@ def main():
 
     import cosmomap2_b200 as cm
     from cosmomap2_b200 import synthetic, _cabi, distributed
-    from cosmomap2_b200.pcg import PCG
+    from cosmomap2_b200.pcg import make_solver
     from cosmomap2_b200 import _device as dv
 
     def barrier():
@@ -246,7 +247,11 @@ def main():
     del x_sol
 
     # ---- device-resident timing -----------------------------------------------------------------------
-    solver = PCG(A, Mbd, n)
+    # N = 1: pcg.PCG (A apply + one cooperative kernel for the pixel-domain tail); N > 1: the pixel-sharded
+    # solver (distributed.ShardedPCG: local TOD pass + ONE kernel fusing reduce-scatter, M_BD, CG vector work
+    # and all-gather over NVLink peer memory), NCCL all-reduce + replicated tail if peer memory is unavailable
+    solver = make_solver(A, Mbd, n)
+    sharded = isinstance(solver, distributed.ShardedPCG)
 
     def one_step():
         solver.start(b)            # r <- b, x <- 0, z = M r, rho, ||r||^2 (device)
@@ -259,11 +264,12 @@ def main():
     if world > 1 and getattr(A, "_p2p", None) is not None:
         # the peer-memory exchange must never have timed out; if it did on any rank, every rank
         # falls back to NCCL for the measurement (and says so in `config.parallelism`)
-        bad = torch.tensor([1.0 if A._p2p.error() != 0 else 0.0], device="cuda")
-        dist.all_reduce(bad)
-        if bad.item() != 0:
-            sys.stderr.write("[bench] P2P all-reduce timed out on some rank: falling back to NCCL\n")
-            A.close()
+        bad = (sharded and solver.failed()) or A._p2p.error() != 0
+        if distributed.agree_failed(bad):
+            sys.stderr.write("[bench] peer-memory exchange timed out on some rank: falling back to NCCL\n")
+            A.disable_p2p("timeout during warm-up")
+            solver = make_solver(A, Mbd, n)
+            sharded = False
             for _ in range(3):
                 one_step()
             barrier()
@@ -289,12 +295,13 @@ def main():
     t_a_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in a_events]))
     assert bool(torch.isfinite(solver.x).all().item()), "PCG state is not finite"
 
-    # keep the GPU under the same load for ~1.5 s so that nvidia-smi sees the clocks of this loop
-    t_end = time.time() + 1.5
-    while time.time() < t_end:
-        for _ in range(20):
-            one_step()
-        torch.cuda.synchronize()
+    # keep the GPU under the same load for ~1.5 s so that nvidia-smi sees the clocks of this loop.  Every
+    # rank runs the SAME number of extra steps (each one contains a peer exchange: a per-rank wall-clock
+    # bound would leave unmatched exchanges behind), derived from the measured step time.
+    n_extra = int(min(20000, max(20, 1.5e3 / max(ms_per_step, 1e-3))))
+    for _ in range(n_extra):
+        one_step()
+    barrier()
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     if clocks is not None:
@@ -305,14 +312,15 @@ def main():
     b_host = dv.pinned_array(n)
     b_host[...] = dv.to_host(b)
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    gather = "shard" if sharded else "all"   # sharded: every rank moves only ITS pixel slice of b and x over PCIe
     for _ in range(4):                 # warm-up, results kept alive exactly as in the timed loop
-        x_h, _info = cm.cg(A, b_host, M=Mbd, rtol=1e-30, maxiter=1)
+        x_h, _info = cm.cg(A, b_host, M=Mbd, rtol=1e-30, maxiter=1, gather=gather)
     barrier()
     t0 = time.perf_counter()
     per = []
     for _ in range(e2e_steps):
         t00 = time.perf_counter()
-        x_h, _info = cm.cg(A, b_host, M=Mbd, rtol=1e-30, maxiter=1)
+        x_h, _info = cm.cg(A, b_host, M=Mbd, rtol=1e-30, maxiter=1, gather=gather)
         per.append(time.perf_counter() - t00)
     barrier()
     dt = time.perf_counter() - t0
@@ -364,18 +372,27 @@ def main():
                        "samples_per_pixel_crossing": sc.samples_per_pixel,
                        "step": "one PCG iteration from a fresh residual (A apply + M_BD apply + CG vector work + ||r|| readback)",
                        "l2": "inputs (2.0 GB TOD per pass) larger than L2 (126 MB); no flush needed",
-                       "parallelism": ("tod sharded by detector x%d, map all-reduce (%s)"
-                                       % (world, "own kernel over NVLink peer memory" if getattr(A, "_p2p", None) is not None
-                                          else "NCCL")) if world > 1 else "single GPU",
+                       "parallelism": (("tod sharded by detector x%d; per iteration one local k_amatvec_white + ONE kernel "
+                                        "k_pcg_bd_sharded over NVLink peer memory (reduce-scatter of A p by peer loads, "
+                                        "pixel-sharded M_BD + CG vector work, all-gather of p by peer stores; 3 doubles of "
+                                        "scalars exchanged by flag-guarded peer stores); no NCCL call in the iteration" % world)
+                                       if sharded else
+                                       ("tod sharded by detector x%d, map all-reduce (%s), replicated pixel-domain tail"
+                                        % (world, "own kernel over NVLink peer memory" if getattr(A, "_p2p", None) is not None
+                                           else "NCCL"))) if world > 1 else "single GPU",
                        "check": check},
             "roofline": {"bound": "hbm", "kernel": "k_amatvec_white<3> (cm2_amatvec_white)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": t_a_ms, "frac_of_8TBs_spec": achieved / 8000.0},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n + 128,
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": 8 * n if (sharded or world == 1) else 8 * n * world,
+                    "d2h_bytes_per_step": (8 * n if (sharded or world == 1) else 8 * n * world) + 128 * world,
+                    "bytes_are": "job totals over all ranks" + ("; every rank moves only its 1/%d pixel slice of b and x" % world
+                                                                 if sharded else ""),
                     "steps": e2e_steps,
-                    "path": "x, info = cosmomap2_b200.cg(A, b_host, M=Mbd, maxiter=1): b from pinned host memory, one full "
-                            "PCG iteration (the same step as `value`), x back to the host",
+                    "path": "x, info = cosmomap2_b200.cg(A, b_host, M=Mbd, maxiter=1%s): b from pinned host memory, one full "
+                            "PCG iteration (the same step as `value`), x back to the host" % (', gather="shard"' if sharded else ""),
                     "scipy_driver": {"value": e2e_scipy, "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * n,
                                      "d2h_bytes_per_step": 2 * 8 * n,
                                      "path": "scipy.sparse.linalg.cg(A, b_host, M=Mbd, maxiter=1) over the drop-in operators: "
@@ -392,6 +409,8 @@ def main():
                 "host_cores_available": os.cpu_count()}
         emit(line)
     if world > 1:
+        if sharded and solver.failed():
+            raise RuntimeError("sharded PCG: a peer-flag wait timed out during the benchmark")
         A.check()
         A.close()
         dist.barrier()

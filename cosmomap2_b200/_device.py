@@ -38,6 +38,47 @@ def empty_f64(n):
     return torch.empty(int(n), dtype=torch.float64, device=device())
 
 
+# ---- map-domain output target ----------------------------------------------------------------
+# A caller that needs the result of an operator in a specific buffer (the multi-GPU solver wants the
+# local A p in its peer-visible exchange buffer, not in a fresh allocation that then has to be copied)
+# sets a one-shot target; the operators that produce map-domain vectors allocate their output with
+# ``out_f64`` and pick it up when the size matches.  ``land`` copies only if nobody did.
+_out_target = [None]
+
+
+class map_output(object):
+    """``with map_output(buf): y = op._apply(x)`` -- y lands in ``buf`` when the producing operator
+    supports it; use ``land(y, buf)`` afterwards to cover the ones that do not."""
+
+    def __init__(self, buf):
+        self.buf = buf
+
+    def __enter__(self):
+        self.prev = _out_target[0]
+        _out_target[0] = self.buf
+        return self
+
+    def __exit__(self, *exc):
+        _out_target[0] = self.prev
+        return False
+
+
+def out_f64(n):
+    """Output buffer for a map-domain result: the one-shot target of ``map_output`` if its size is n."""
+    t = _out_target[0]
+    if t is not None and t.numel() == int(n):
+        _out_target[0] = None
+        return t
+    return empty_f64(n)
+
+
+def land(y, buf):
+    """Make sure ``y`` is stored in ``buf`` (no-op if it already is)."""
+    if y.data_ptr() != buf.data_ptr():
+        buf.copy_(y)
+    return buf
+
+
 def zeros_f64(n):
     return torch.zeros(int(n), dtype=torch.float64, device=device())
 
@@ -57,6 +98,8 @@ def to_dev(a, dtype=None):
     arr = np.ascontiguousarray(a)
     if arr.dtype == np.bool_:
         arr = arr.astype(np.uint8)
+    if not arr.dtype.isnative:         # h5py hands out the reference's big-endian datasets as '>i4' / '>f8'
+        arr = arr.astype(arr.dtype.newbyteorder("="))
     if not arr.flags.writeable:
         arr = arr.copy()
     src = torch.from_numpy(arr)

@@ -114,6 +114,27 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
     }
     return t;  // valid in warp 0
 }
+// z = M_BD r for pixel j: inv[npix][6] holds the upper triangle {a00,a01,a02,a11,a12,a22} of the per-pixel
+// inverse block (zeros where the reference's |det| test fails, linearoperators.py:795, 821)
+template <int POL>
+__device__ __forceinline__ void bd_z(const double *__restrict__ inv, int64_t j, const double (&r)[POL], double (&z)[POL]) {
+    if constexpr (POL == 1) {
+        z[0] = __ldg(inv + 6 * j) * r[0];
+    } else {
+        const double2 *b2 = reinterpret_cast<const double2 *>(inv + 6 * j);
+        if constexpr (POL == 2) {
+            const double2 q1 = __ldg(b2 + 1), q2 = __ldg(b2 + 2);
+            z[0] = q1.y * r[0] + q2.x * r[1];
+            z[1] = q2.x * r[0] + q2.y * r[1];
+        } else {
+            const double2 q0 = __ldg(b2), q1 = __ldg(b2 + 1), q2 = __ldg(b2 + 2);
+            z[0] = q0.x * r[0] + q0.y * r[1] + q1.x * r[2];
+            z[1] = q0.y * r[0] + q1.y * r[1] + q2.x * r[2];
+            z[2] = q1.x * r[0] + q2.x * r[1] + q2.y * r[2];
+        }
+    }
+}
+
 // ---- Legendre subscan filter helpers (filter_poly.cu, tod_pass.cu) ------------------------------
 // Legendre P_0..P_{NK-1} at x by the three-term recurrence
 template <int NK>

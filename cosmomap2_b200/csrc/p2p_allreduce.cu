@@ -12,8 +12,8 @@
 // local, only the pixel-domain vector is exchanged).
 //
 // Buffers and flags are torch CUDA allocations shared through CUDA IPC (torch plumbing); this file
-// only sees pointer tables.  Spin waits carry a clock64() timeout (~2 s) and raise an error word
-// instead of hanging the device.
+// only sees pointer tables.  Spin waits carry a wall-clock timeout (%globaltimer, 20 s by default)
+// and raise an error word instead of hanging the device.
 #include "cm2_common.cuh"
 
 namespace cm2 {
@@ -25,7 +25,8 @@ constexpr int AR_THREADS = 512;
 struct ARSignals {
     unsigned int start[AR_MAX_BLOCKS][AR_MAX_WORLD];
     unsigned int end[AR_MAX_BLOCKS][AR_MAX_WORLD];
-    unsigned int error;
+    unsigned int error;   // generation of the first wait that timed out (0 = none), sticky
+    unsigned int abort;   // local: stop waiting
 };
 
 struct ARPtrs {
@@ -43,8 +44,20 @@ __device__ __forceinline__ unsigned int ld_flag(const unsigned int *p) {
     return v;
 }
 
-// which = 0: start flags, 1: end flags
-__device__ __forceinline__ void peer_barrier(const ARPtrs &P, int rank, int world, unsigned int gen, int which) {
+__device__ __forceinline__ long long now_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// which = 0: start flags, 1: end flags.  Flags carry the generation of the call; the compare is
+// monotone and wrap-safe (a flag that has already moved on to a later generation still satisfies the
+// wait), and a wait that times out raises `error` (first generation that failed, sticky) and `abort`,
+// which makes every later wait of this rank fall through at once: the rank never hangs and never
+// spends more than one timeout in total; the host reads `error` (P2PAllReduce.error) and all ranks
+// switch to NCCL together (distributed.py).
+__device__ __forceinline__ void peer_barrier(const ARPtrs &P, int rank, int world, unsigned int gen, int which,
+                                             long long timeout_ns) {
     __syncthreads();
     if ((int)threadIdx.x < world) {
         const int t = threadIdx.x;
@@ -53,11 +66,17 @@ __device__ __forceinline__ void peer_barrier(const ARPtrs &P, int rank, int worl
         unsigned int *dst = which == 0 ? &peer->start[blockIdx.x][rank] : &peer->end[blockIdx.x][rank];
         const unsigned int *src = which == 0 ? &self->start[blockIdx.x][t] : &self->end[blockIdx.x][t];
         st_flag(dst, gen);
-        const long long t0 = clock64();
-        while (ld_flag(src) != gen) {
-            if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz: give up loudly instead of hanging
-                self->error = gen;
-                break;
+        if ((int)(ld_flag(src) - gen) < 0) {
+            const long long t0 = now_ns();
+            unsigned int polls = 0;
+            while ((int)(ld_flag(src) - gen) < 0) {
+                if ((++polls & 255u) != 0) continue;
+                if (*((volatile unsigned int *)&self->abort) != 0) break;
+                if (now_ns() - t0 > timeout_ns) {          // give up loudly instead of hanging
+                    atomicCAS(&self->error, 0u, gen);
+                    *((volatile unsigned int *)&self->abort) = 1u;
+                    break;
+                }
             }
         }
     }
@@ -68,8 +87,9 @@ __device__ __forceinline__ void peer_barrier(const ARPtrs &P, int rank, int worl
 // flight without spilling (NVLink load latency is ~2-3 us: the exchange is latency-bound unless
 // enough loads are outstanding).
 template <int WORLD, int UNROLL>
-__global__ void __launch_bounds__(AR_THREADS) k_allreduce_p2p(ARPtrs P, int rank, int64_t n, unsigned int gen) {
-    peer_barrier(P, rank, WORLD, gen, 0);
+__global__ void __launch_bounds__(AR_THREADS) k_allreduce_p2p(ARPtrs P, int rank, int64_t n, unsigned int gen,
+                                                                  long long timeout_ns) {
+    peer_barrier(P, rank, WORLD, gen, 0, timeout_ns);
     const int64_t n2 = n / 2;   // my slice, in units of double2
     const int64_t lo = n2 * rank / WORLD, hi = n2 * (rank + 1) / WORLD;
     const int64_t stride = (int64_t)gridDim.x * AR_THREADS;
@@ -100,17 +120,26 @@ __global__ void __launch_bounds__(AR_THREADS) k_allreduce_p2p(ARPtrs P, int rank
         for (int g = 0; g < WORLD; ++g) P.recv[g][n - 1] = s;
     }
     __threadfence_system();
-    peer_barrier(P, rank, WORLD, gen, 1);
+    peer_barrier(P, rank, WORLD, gen, 1, timeout_ns);
 }
+
+static long long g_ar_timeout_ns = 20000000000LL;   // 20 s
 
 template <int WORLD, int UNROLL>
 static void launch_ar(const ARPtrs &P, int rank, int64_t n, unsigned int gen, int grid, cudaStream_t st) {
-    k_allreduce_p2p<WORLD, UNROLL><<<grid, AR_THREADS, 0, st>>>(P, rank, n, gen);
+    k_allreduce_p2p<WORLD, UNROLL><<<grid, AR_THREADS, 0, st>>>(P, rank, n, gen, g_ar_timeout_ns);
 }
 
 }  // namespace cm2
 
 using namespace cm2;
+
+/* timeout of the peer-flag waits in seconds (default 20); returns the previous value */
+extern "C" double cm2_allreduce_p2p_set_timeout(double seconds) {
+    const double old = 1e-9 * (double)g_ar_timeout_ns;
+    if (seconds > 0.0) g_ar_timeout_ns = (long long)(seconds * 1e9);
+    return old;
+}
 
 extern "C" int64_t cm2_allreduce_p2p_signal_bytes(void) { return (int64_t)sizeof(ARSignals); }
 

@@ -146,25 +146,6 @@ __global__ void __launch_bounds__(VB) k_update_xr(const double *__restrict__ p, 
 
 // ---- M = M_BD path: the preconditioner apply is pixel-local, so z = M r and rho = r.z ride in
 // the same kernel that updates r (one pass over the pixel-domain vectors per iteration) ---------
-template <int POL>
-__device__ __forceinline__ void bd_z(const double *__restrict__ inv, int64_t j, const double (&r)[POL], double (&z)[POL]) {
-    if constexpr (POL == 1) {
-        z[0] = __ldg(inv + 6 * j) * r[0];
-    } else {
-        const double2 *b2 = reinterpret_cast<const double2 *>(inv + 6 * j);
-        if constexpr (POL == 2) {
-            const double2 q1 = __ldg(b2 + 1), q2 = __ldg(b2 + 2);
-            z[0] = q1.y * r[0] + q2.x * r[1];
-            z[1] = q2.x * r[0] + q2.y * r[1];
-        } else {
-            const double2 q0 = __ldg(b2), q1 = __ldg(b2 + 1), q2 = __ldg(b2 + 2);
-            z[0] = q0.x * r[0] + q0.y * r[1] + q1.x * r[2];
-            z[1] = q0.y * r[0] + q1.y * r[1] + q2.x * r[2];
-            z[2] = q1.x * r[0] + q2.x * r[1] + q2.y * r[2];
-        }
-    }
-}
-
 // start: z = M r, rho = r.z, |r|^2, flags.  With b != nullptr it also performs the x0 = 0 start of
 // the solve in the same pass: r = b, x = 0.
 template <int POL>
@@ -416,6 +397,10 @@ extern "C" int cm2_pcg_bd_update(const double *inv, int64_t npix, int pol, const
     return CM2_OK;
 }
 
+// test hook (cm2_pcg_bd_iter_refuse): make the cooperative launch fail the way a GPU that refuses
+// cooperative launches does (too many CTAs for co-residency), to exercise the fallback
+static int g_refuse_coop = 0;
+
 template <int POL>
 static int launch_bd_iter(const double *inv, int64_t npix, double *p, const double *q, double *x, double *r, double *z,
                           double *scal, cudaStream_t st) {
@@ -427,11 +412,21 @@ static int launch_bd_iter(const double *inv, int64_t npix, double *p, const doub
     if (g > MAXP) g = MAXP;
     const int64_t need = (npix + VB - 1) / VB;
     if (need < g) g = need < 1 ? 1 : need;
+    if (g_refuse_coop) g = (int64_t)sm_count() * 64;     // more CTAs than can be co-resident: the launch is refused
     void *args[] = {(void *)&inv, (void *)&npix, (void *)&p, (void *)&q, (void *)&x, (void *)&r, (void *)&z, (void *)&scal};
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_bd_iter<POL>, dim3((unsigned)g), dim3(VB), args, 0, st);
-    if (e != cudaSuccess) return set_error(CM2_ERR_CUDA, "cm2_pcg_bd_iter: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        cudaGetLastError();      // clear the runtime's sticky last-error: the caller falls back to the 3-kernel tail
+        return set_error(CM2_ERR_CUDA, "cm2_pcg_bd_iter: %s", cudaGetErrorString(e));
+    }
     count_launch();
     return CM2_OK;
+}
+
+extern "C" int cm2_pcg_bd_iter_refuse(int on) {
+    const int old = g_refuse_coop;
+    g_refuse_coop = on ? 1 : 0;
+    return old;
 }
 
 extern "C" int cm2_pcg_bd_iter(const double *inv, int64_t npix, int pol, double *p, const double *q, double *x,

@@ -77,7 +77,7 @@ class SparseLO(lp.LinearOperator):
     mult_qu = mult_iqu = mult
 
     def rmult(self, v):                                   # :385-410, 439-462, 498-526
-        y = dv.empty_f64(self.ncols * self.pol)
+        y = dv.out_f64(self.ncols * self.pol)
         dv.call("cm2_pointing_apply_t", dv.ptr(self._pix_dev), dv.ptr(self._cos_dev), dv.ptr(self._sin_dev),
                 self.nrows, self.pol, dv.ptr(v), dv.ptr(y), self.ncols, _stream())
         return y
@@ -507,7 +507,7 @@ class _FusedWhiteA(lp.LinearOperator):
 
     def _run(self, x):
         P = self.P
-        y = dv.empty_f64(P.ncols * P.pol)
+        y = dv.out_f64(P.ncols * P.pol)
         if self.N is None:
             w, nb, bs, startp = None, 0, 0, None
         else:
@@ -598,7 +598,7 @@ class _FusedFilterA(lp.LinearOperator):
 
     def _run(self, x):
         P, F = self.P, self.F
-        y = dv.empty_f64(P.ncols * P.pol)
+        y = dv.out_f64(P.ncols * P.pol)
         if self._runs is None:
             self._runs = _filter_runs(P, F)
         rt = self._runs
@@ -705,7 +705,7 @@ class _FusedPolyFilterA(lp.LinearOperator):
 
     def _run(self, x):
         P, F = self.P, self.F
-        y = dv.empty_f64(P.ncols * P.pol)
+        y = dv.out_f64(P.ncols * P.pol)
         if self._runs is None:
             self._runs = _build_poly_runs(P, F) if FILTER_POLY_RUN_TABLE else False
         rt = self._runs
@@ -766,7 +766,7 @@ class _FusedToeplitzA(lp.LinearOperator):
 
     def _run(self, x):
         P, N = self.P, self.N
-        y = dv.empty_f64(P.ncols * P.pol)
+        y = dv.out_f64(P.ncols * P.pol)
         if N._band_dev is None:
             N._band_dev = dv.to_dev_f64(N._band_host.reshape(-1))
             N._fft = None

@@ -63,7 +63,9 @@ class PCG(object):
         self.z = dv.empty_f64(n) if self.bd is not None else None
         self._pin = [torch.empty(NSCAL, dtype=torch.float64).pin_memory() for _ in range(2)]
         self._ev = [torch.cuda.Event(), torch.cuda.Event()]
-        self._coop = True         # one cooperative launch for the pixel-domain tail (falls back if refused)
+        # one cooperative launch for the pixel-domain tail; if the device refuses cooperative launches
+        # (attribute 0 under some sharing modes, or a refused launch at run time) the 3-kernel tail runs
+        self._coop = True
         self._queued = 0          # iterations launched since start()
         self._snap = 0            # snapshots enqueued
 
@@ -91,9 +93,12 @@ class PCG(object):
         return float(np.sqrt(s[3].item())), bool(s[7].item() != 0.0), int(s[8].item())
 
     # ---- recurrence --------------------------------------------------------------------------
-    def start(self, b, x0=None, atol=0.0):
-        """x <- x0 (or 0), r <- b - A x0, device scalars reset.  ``b`` is a CUDA fp64 tensor."""
+    def start(self, b, x0=None, atol=0.0, rtol=0.0):
+        """x <- x0 (or 0), r <- b - A x0, device scalars reset.  ``b`` is a CUDA fp64 tensor.
+        ``rtol`` > 0 folds SciPy's ``atol = max(atol, rtol*||b||)`` in (one synchronising norm)."""
         n, st = self.n, dv.stream
+        if rtol:
+            atol = max(float(atol), float(rtol) * self.norm(b))
         if x0 is None and self.bd is not None:
             # x0 = 0 with M_BD: r = b, x = 0, z = M r, rho, ||r||^2 in ONE pass
             dv.call("cm2_pcg_bd_reset", dv.ptr(self.bd._inv_dev), self.bd._n, self.bd.pol, dv.ptr(self.r),
@@ -158,12 +163,63 @@ class PCG(object):
         return self.state()[0]
 
 
+def _run_loop(solver, maxiter, residuals):
+    """The asynchronous solve loop: the flag of iteration k is read while iteration k+1 is already
+    queued.  Returns info (0 = converged, maxiter = not)."""
+    s0 = solver._snap
+    solver._snapshot()                      # snapshot s0: state before iteration 0
+    for it in range(maxiter):
+        solver.step_async()                 # no-op on the device if `done` was already raised
+        solver._snapshot()                  # snapshot s0+it+1: state after iteration `it`
+        rnorm, done, _iters = solver._read_snapshot(s0 + it)   # state at the TOP of iteration `it`
+        if residuals is not None:
+            residuals.append(rnorm)
+        if done:
+            return 0                        # the queued iteration `it` did nothing
+    return maxiter
+
+
+def _cg_sharded(solver, A, b_in, want_numpy, rtol, atol, maxiter, residuals, gather):
+    """cg() over the pixel-sharded multi-GPU solver (distributed.ShardedPCG).  Returns None if the
+    peer-memory exchange failed on ANY rank (every rank then takes the replicated NCCL path)."""
+    lo, hi = solver.elo, solver.ehi
+    if want_numpy:
+        bs = dv.to_dev_f64(b_in[lo:hi])     # only this rank's slice crosses PCIe
+    else:
+        bs = b_in[lo:hi]
+    solver.start(bs, None, atol, rtol)
+    res = [] if residuals is not None else None
+    info = _run_loop(solver, maxiter, res)
+    from . import distributed
+    if distributed.agree_failed(solver.failed(), solver.group):
+        A.disable_p2p("a peer-flag wait of the sharded PCG timed out")
+        return None
+    if residuals is not None:
+        residuals.extend(res)
+    if gather == "shard":
+        x = solver.x
+        return (dv.to_host(x) if want_numpy else x.clone()), info
+    x = solver.gather_x()
+    return (dv.to_host(x) if want_numpy else x), info
+
+
+def make_solver(A, M, n):
+    """The PCG state machine for (A, M): the pixel-sharded multi-GPU solver when A is a
+    ``distributed.AllReduceLO`` over peer memory and M the block-diagonal preconditioner, else ``PCG``."""
+    f = getattr(A, "sharded_solver", None)
+    s = f(M) if f is not None else None
+    return s if s is not None else PCG(A, M, n)
+
+
 def cg(A, b, x0=None, *, rtol=1e-5, atol=0., maxiter=None, M=None, callback=None, tol=None,
-       residuals=None):
+       residuals=None, gather="all"):
     """``x, info = cg(A, b, x0=None, rtol=1e-5, atol=0., maxiter=None, M=None, callback=None)``.
 
     ``tol`` is the legacy name of ``rtol`` used by the reference's call sites.  ``residuals``, if a
-    list, receives ||r||_2 as tested at the top of every iteration.
+    list, receives ||r||_2 as tested at the top of every iteration.  Multi-GPU (A a
+    ``distributed.AllReduceLO``): ``gather="all"`` returns the full x on every rank, ``"shard"`` only
+    this rank's pixel slice ``x[pol*lo:pol*hi]`` (``distributed.partition_pixels``) when the
+    pixel-sharded solver runs, so that b and x cross PCIe once per job instead of once per rank.
     """
     dv.require_cuda()
     if tol is not None:
@@ -176,14 +232,32 @@ def cg(A, b, x0=None, *, rtol=1e-5, atol=0., maxiter=None, M=None, callback=None
     n = b_in.shape[0]
     if isinstance(A, lp.LinearOperator) and A.shape != (n, n):
         raise ValueError("A and b have incompatible dimensions")
+    if maxiter is None:
+        maxiter = n * 10
+    if x0 is None and callback is None:
+        f = getattr(A, "sharded_solver", None)
+        sharded = f(M) if f is not None else None
+        if sharded is not None:
+            out_ = _cg_sharded(sharded, A, b_in, want_numpy, rtol, atol, maxiter, residuals, gather)
+            if out_ is not None:
+                return out_
+    while True:
+        x, info = _cg_replicated(A, b_in, x0, want_numpy, rtol, atol, maxiter, M, callback, residuals)
+        rec = getattr(A, "recover", None)
+        if rec is None or not rec():
+            return x, info
+        if residuals is not None:           # the peer-memory all-reduce failed mid-solve on some rank:
+            del residuals[:]                # every rank has switched to NCCL; solve again
+
+
+def _cg_replicated(A, b_in, x0, want_numpy, rtol, atol, maxiter, M, callback, residuals):
+    n = b_in.shape[0]
     solver = PCG(A, M, n)
     bd = dv.to_dev_f64(b_in)
     bnrm2 = solver.norm(bd)
     atol = max(float(atol), float(rtol) * bnrm2)
     if bnrm2 == 0:
         return (b_in.copy() if want_numpy else bd.clone()), 0
-    if maxiter is None:
-        maxiter = n * 10
     x0d = None
     if x0 is not None:
         x0d = dv.to_dev_f64(x0).reshape(-1)
@@ -207,15 +281,5 @@ def cg(A, b, x0=None, *, rtol=1e-5, atol=0., maxiter=None, M=None, callback=None
             callback(out(solver.x))
         return out(solver.x), maxiter
 
-    # asynchronous loop: the flag of iteration k is read while iteration k+1 is already queued
-    s0 = solver._snap
-    solver._snapshot()                      # snapshot s0: state before iteration 0
-    for it in range(maxiter):
-        solver.step_async()                 # no-op on the device if `done` was already raised
-        solver._snapshot()                  # snapshot s0+it+1: state after iteration `it`
-        rnorm, done, _iters = solver._read_snapshot(s0 + it)   # state at the TOP of iteration `it`
-        if residuals is not None:
-            residuals.append(rnorm)
-        if done:
-            return out(solver.x), 0         # the queued iteration `it` did nothing
-    return out(solver.x), maxiter
+    info = _run_loop(solver, maxiter, residuals)
+    return out(solver.x), info

@@ -278,6 +278,9 @@ int cm2_pcg_bd_update(const double *bd_inv, int64_t npix, int pol, const double 
                       cm2_stream_t stream);
 int cm2_pcg_bd_iter(const double *bd_inv, int64_t npix, int pol, double *p, const double *q,
                     double *x, double *r, double *z, double *scal, cm2_stream_t stream);
+/* test hook: on != 0 makes cm2_pcg_bd_iter ask for more CTAs than can be co-resident, so that the
+ * cooperative launch is refused like on a GPU that does not grant them; returns the previous value */
+int cm2_pcg_bd_iter_refuse(int on);
 
 /* ---- (f) next rows: the other time-domain filters and the map output step ----------------------
  * Subscan filter of polynomial order 0..cm2_filter_poly_max_order(), one CTA per subscan with the
@@ -336,6 +339,38 @@ int cm2_allreduce_p2p(const void *const *send_ptrs_host, void *const *recv_ptrs_
                       void *const *signal_ptrs_host, int rank, int world, int64_t n,
                       uint32_t generation, cm2_stream_t stream);
 int cm2_enable_peer_access(int peer_device);
+/* timeout of the peer-flag waits of cm2_allreduce_p2p in seconds (default 20; <= 0 only queries);
+ * returns the previous value.  A wait that times out never hangs: the error word at
+ * signal + cm2_allreduce_p2p_signal_bytes() - 8 (uint32) receives the generation that failed. */
+double cm2_allreduce_p2p_set_timeout(double seconds);
+
+/* ---- (e) multi-GPU: the M_BD PCG tail fused with the map exchange (reduce-scatter ->
+ * pixel-sharded M_BD / CG vector work -> all-gather), ONE cooperative kernel per iteration over NVLink
+ * peer memory.  Replaces, per iteration, scipy's cg loop body (scipy/_isolve/iterative.py:405-431)
+ * around  q = A p  (call sites src/test_BD_precond_onto_real_data.py:47,
+ * src/test_M2_precond_onto_real_data.py:117) for A = sum_g P_g^T N_g^-1 P_g sharded by detector
+ * (layout linearoperators.py:134-167):
+ *   reset != 0 : r = b, x = 0, z = M r, p = z (sent to every rank), rho, |r|^2,
+ *                atol_eff = max(atol, rtol*||b||); scal[10] = ||b||^2
+ *   reset == 0 : q = sum_g y_g on this rank's pixel slice (peer loads), p.q, alpha, x, r, z = M r,
+ *                rho', |r|^2, beta, p = z + beta p sent to every rank (peer stores), flags
+ * Rank g owns pixels [pix_lo[g], pix_lo[g+1]); pix_lo[g]*pol must be even.  Tables are HOST arrays of
+ * `world` DEVICE pointers: y / p / sig = every rank's peer-visible buffers (n doubles, n doubles,
+ * cm2_pcg_sharded_signal_bytes() zero-initialised bytes) mapped into this process; x / r / z / q
+ * (slice length), inv (6 doubles per slice pixel), b (slice of the right-hand side, reset only), scal
+ * (16 doubles, layout as above; [9] = generation of a timed-out wait, 0 = none) and part
+ * (cm2_pcg_sharded_work_doubles()) are private: entries [rank0, rank0 + nvirt) are used.  nvirt = 1
+ * is a real rank; nvirt = world with rank0 = 0 plays all ranks in one launch on one GPU (tests).
+ * `generation`: the same non-zero, strictly increasing value on every rank for every call. */
+int64_t cm2_pcg_sharded_signal_bytes(void);
+int64_t cm2_pcg_sharded_work_doubles(void);
+int cm2_pcg_bd_sharded(int reset, int pol, int world, int rank0, int nvirt,
+                       const int64_t *pix_lo_host, const void *const *y_tab, void *const *p_tab,
+                       void *const *sig_tab, void *const *x_tab, void *const *r_tab,
+                       void *const *z_tab, void *const *q_tab, const void *const *inv_tab,
+                       const void *const *b_tab, void *const *scal_tab, void *const *part_tab,
+                       uint32_t generation, double atol, double rtol, double timeout_s,
+                       cm2_stream_t stream);
 
 #ifdef __cplusplus
 }

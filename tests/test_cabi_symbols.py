@@ -12,7 +12,7 @@ def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     decls = {}
-    for m in re.finditer(r"\b(int|int64_t|const char \*)\s*(cm2_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"\b(int|int64_t|double|const char \*)\s*(cm2_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         args = m.group(3).strip()
         nargs = 0 if args in ("", "void") else len(args.split(","))
         decls[m.group(2)] = nargs
