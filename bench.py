@@ -77,10 +77,15 @@ def parse():
 # ---------------------------------------------------------------------------------------------
 def cpu_pcg_throughput(nt, iters, warmup=1, seed=0):
     """samples/s per PCG iteration of the oracle on a bounded sample of the same workload."""
+    import importlib.util
     import scipy.sparse.linalg as spla
     import oracle
     from oracle import cloops
-    from cosmomap2_b200 import synthetic
+    # the workload generator is plain NumPy: load it by path so that the CPU arm never imports the
+    # package (which maps the CUDA library) -- nothing of the product may be on the reference arm's path
+    spec = importlib.util.spec_from_file_location("cm2_synthetic", os.path.join(ROOT, "cosmomap2_b200", "synthetic.py"))
+    synthetic = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(synthetic)
     cloops.build()
     sc = synthetic.config_c2(nt=nt, seed=seed)
     pix = sc.pix.astype(np.int64)

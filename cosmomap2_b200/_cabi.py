@@ -74,6 +74,9 @@ SIGNATURES = {
     "cm2_defl_z_apply": (_int, [_vp, _i64, _int, _i64, _vp, _f64, _f64, _vp, _vp, _vp]),
     "cm2_coarse_apply": (_int, [_vp, _int, _vp, _vp, _vp]),
     "cm2_m2_apply": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
+    "cm2_dense_gram_work_doubles": (_i64, []),
+    "cm2_dense_gram": (_int, [_vp, _i64, _int, _vp, _i64, _int, _i64, _vp, _i64, _vp, _vp]),
+    "cm2_dense_combine": (_int, [_vp, _i64, _i64, _int, _vp, _i64, _int, _vp, _i64, _vp]),
     "cm2_dot": (_int, [_vp, _vp, _i64, _vp, _vp]),
     "cm2_axpby": (_int, [_f64, _vp, _f64, _vp, _i64, _vp]),
     "cm2_pcg_reset": (_int, [_vp, _i64, _vp, _f64, _vp]),
@@ -100,7 +103,7 @@ _NOT_STATUS = {"cm2_version", "cm2_last_error", "cm2_launch_count", "cm2_scan_sc
                "cm2_toeplitz_fft_points", "cm2_toeplitz_fft_scratch_bytes", "cm2_filter_poly_max_order", "cm2_filter_poly_set_tma",
                "cm2_amatvec_filter_poly_max_order", "cm2_amatvec_toeplitz_max_band",
                "cm2_amatvec_white_set_prefetch", "cm2_allreduce_p2p_set_timeout", "cm2_pcg_bd_iter_refuse",
-               "cm2_pcg_sharded_signal_bytes", "cm2_pcg_sharded_work_doubles"}
+               "cm2_pcg_sharded_signal_bytes", "cm2_pcg_sharded_work_doubles", "cm2_dense_gram_work_doubles"}
 
 
 def _load():

@@ -146,6 +146,19 @@ def call(name, *args):
 _registry = {}
 
 
+def _fingerprint(arr):
+    """Cheap content stamp of a host array: exact for arrays up to 2^20 elements, a strided sample of
+    2^16 elements plus both ends beyond that (a full pass would cost as much as the upload it saves)."""
+    flat = arr.reshape(-1)
+    n = flat.shape[0]
+    if n <= (1 << 20):
+        return (n, int(np.bitwise_xor.reduce(flat.view(np.uint32 if flat.dtype.itemsize == 4 else np.uint64))) if n else 0,
+                int(flat.sum(dtype=np.int64)) if n else 0)
+    step = n >> 16
+    samp = flat[::step]
+    return (n, int(samp.sum(dtype=np.int64)), int(flat[:1024].sum(dtype=np.int64)), int(flat[-1024:].sum(dtype=np.int64)))
+
+
 def register_host_image(arr, tensor):
     if not isinstance(arr, np.ndarray):
         return
@@ -154,19 +167,32 @@ def register_host_image(arr, tensor):
     def _drop(_ref, key=key):
         _registry.pop(key, None)
     try:
-        _registry[key] = (weakref.ref(arr, _drop), tensor)
+        _registry[key] = (weakref.ref(arr, _drop), tensor, _fingerprint(arr))
     except TypeError:
         pass
 
 
 def lookup_host_image(arr):
+    """The device image registered for this very host array, if the array still holds what was
+    registered.  Large arrays are only spot-checked (see ``_fingerprint``): code that edits ``pixs`` in
+    place after ProcessTimeSamples (extra flagging) should call ``invalidate_host_image(pixs)``."""
     if not isinstance(arr, np.ndarray):
         return None
     hit = _registry.get(id(arr))
     if hit is None:
         return None
-    ref, tensor = hit
-    return tensor if ref() is arr else None
+    ref, tensor, stamp = hit
+    if ref() is not arr:
+        return None
+    if _fingerprint(arr) != stamp:
+        _registry.pop(id(arr), None)          # the caller changed the array: upload it again
+        return None
+    return tensor
+
+
+def invalidate_host_image(arr):
+    """Forget the device image of a host array (call after modifying it in place)."""
+    _registry.pop(id(arr), None)
 
 
 def pix_to_dev(pix):

@@ -19,6 +19,7 @@ import torch
 from scipy.linalg import eigh
 
 from . import _device as dv
+from . import dense
 from . import linop as lp
 from .utilities import dgemm, norm2  # noqa: F401
 
@@ -103,9 +104,9 @@ def build_Z(z, y, w, eps):
     U = np.asarray(y)[:, sel]
     if isinstance(w[0], torch.Tensor):
         W = torch.stack(list(w[:m]))                           # m x n
-        return torch.matmul(dv.to_dev_f64(np.ascontiguousarray(U.T)), W).t(), r
+        return dense.combine(W, U).t(), r
     W = np.asarray(w)[:m]
-    return dv.to_host(torch.matmul(dv.to_dev_f64(np.ascontiguousarray(U.T)), dv.to_dev_f64(W))).T, r
+    return dv.to_host(dense.combine(dv.to_dev_f64(W), U)).T, r
 
 
 def krypy_arnoldi(A, x0, M=None, maxiter=None, ortho="dmgs", tol_invariant=1e-14):
@@ -185,21 +186,35 @@ def krypy_ritz(H, V=None, hermitian=True):
     Z = None
     if V is not None:
         if isinstance(V, torch.Tensor):
-            Z = torch.matmul(V[:, :n], dv.to_dev_f64(U))
+            Z = dense.combine(V[:, :n].t(), U).t()
         else:
-            Z = dv.to_host(torch.matmul(dv.to_dev_f64(np.ascontiguousarray(V[:, :n])), dv.to_dev_f64(U)))
+            Z = dv.to_host(dense.combine(dv.to_dev_f64(np.ascontiguousarray(V[:, :n].T)), U)).T
     return theta, U, resnorm, Z
 
 
-def find_ritz_eigenvalues(h, v, threshold=1.e-2, eigenvalues=False, filename=None):
-    """interfaces/deflationlib.py:204-219 -> ``(Z, r)`` (and the selected theta if asked)."""
+def find_ritz_eigenvalues(h, v, threshold=1.e-2, eigenvalues=False, filename=None, resnorm_tol=None):
+    """interfaces/deflationlib.py:204-219 -> ``(Z, r)`` (and the selected theta if asked).  Like the
+    reference, the full set of Ritz vectors and values is written to ``filename`` when given
+    (``write_ritz_eigenvectors_to_hdf5(z, filename, eigvals=eig)``, :214-215) -- the checkpoint that
+    lets a re-run skip the Arnoldi phase.
+
+    ``resnorm_tol`` (extension, default None = the reference's selection by value only): additionally
+    require the Ritz residual ``|h_{m+1,m} U[m-1,i]|`` that ``kp.utils.ritz`` returns (:205) to be at most
+    ``resnorm_tol * max(|theta_i|, eps^(2/3))``: an unconverged Ritz vector in Z makes the two-level
+    preconditioner WORSE than M_BD (measured: 86 -> 121 iterations with 40 Arnoldi steps, 10 with 120)."""
     eig, u, resnorm, z = krypy_ritz(h, V=v, hermitian=True)
+    if filename is not None:
+        from . import IOfiles
+        IOfiles.write_ritz_eigenvectors_to_hdf5(dv.to_host(z) if isinstance(z, torch.Tensor) else z, filename,
+                                                eigvals=eig)
     sel = eig < threshold
+    if resnorm_tol is not None:
+        sel &= resnorm <= float(resnorm_tol) * np.maximum(np.abs(eig), np.finfo(np.float64).eps ** (2.0 / 3.0))
     r = int(np.count_nonzero(sel))
-    if eigenvalues:
+    if eigenvalues or resnorm_tol is not None:
         idx = np.nonzero(sel)[0]
         zsel = z[:, torch.as_tensor(idx, device=z.device)] if isinstance(z, torch.Tensor) else z[:, idx]
-        return zsel, r, eig[sel]
+        return (zsel, r, eig[sel]) if eigenvalues else (zsel, r)
     return z[:, :r], r
 
 
@@ -328,12 +343,10 @@ def eigsh(A, k=6, M=None, Minv=None, which="SM", ncv=None, tol=0, maxiter=None, 
         ell = min(k + nconv + max((m - k) // 2 - nconv, 0), m - 1)
         ell = max(ell, k)
         keep = order[:ell]
-        Yk = dv.to_dev_f64(np.ascontiguousarray(Y[:, keep].T))             # ell x m
-        Vn = torch.matmul(Yk, V[:m])
-        V[:ell].copy_(Vn)
+        Yk = Y[:, keep]                                                     # m x ell
+        V[:ell].copy_(dense.combine(V[:m], Yk))
         if Minv is not None:
-            Pn = torch.matmul(Yk, P[:m])
-            P[:ell].copy_(Pn)
+            P[:ell].copy_(dense.combine(P[:m], Yk))
             P[ell].copy_(P[m])
         V[ell].copy_(V[m])
         coupling = H[m, m - 1] * Y[m - 1, keep]
@@ -346,7 +359,7 @@ def eigsh(A, k=6, M=None, Minv=None, which="SM", ncv=None, tol=0, maxiter=None, 
     converged = res[idx] <= tol_eff * np.maximum(eps23, np.abs(w))
     Z = None
     if return_eigenvectors or not converged.all():
-        Z = torch.matmul(dv.to_dev_f64(np.ascontiguousarray(Y[:, idx].T)), V[:m_eff]).t().contiguous()
+        Z = dense.combine(V[:m_eff], Y[:, idx]).t().contiguous()
     if not converged.all():
         good = np.nonzero(converged)[0]
         raise ArpackNoConvergence("eigsh: %d of %d wanted eigenpairs converged in %d restarts"
@@ -356,3 +369,46 @@ def eigsh(A, k=6, M=None, Minv=None, which="SM", ncv=None, tol=0, maxiter=None, 
     if not return_eigenvectors:
         return w
     return (w, Z) if device else (w, dv.to_host(Z))
+
+
+def scan_coarse_space(P, r, samples_per_detector, group=None):
+    """A-priori deflation space for a filtered raster scan (an ADDITION to the reference's two routes to
+    Z -- ARPACK in its tests, Arnoldi/Ritz in src/test_M2_precond_onto_real_data.py:13-50 -- for the same
+    ``DeflationLO`` / ``CoarseLO`` / ``M2 = Mbd*R + Zd*E*Zd.T`` machinery).
+
+    With a subscan filter F the small eigenvalues of ``M_BD P^T F P`` belong to maps that are constant
+    along every subscan: for a raster scan, intensity maps that vary only ACROSS the scan direction, one
+    mode per map row (SURVEY 8d caveat; measured on the oracle: 32 rows -> exactly 32 eigenvalues below
+    0.13, the rest above 0.48).  Krylov methods need about as many A applies to resolve those vectors as
+    CG needs to solve the system, so a Ritz-built Z cannot pay for itself on one right-hand side.  The
+    scan tells us the space directly: pixels are ordered by WHEN the scan visits them (the cross-scan
+    drift is monotone in time), and column k of Z is the intensity indicator of the pixels whose mean
+    visiting time falls in the k-th of ``r`` equal time bands.  Cost: one pol-1 scatter of the TOD, no
+    A apply; ``A Z`` then costs r applies.
+
+    ``P``: the SparseLO of this rank; ``samples_per_detector``: length of one detector timeline (the
+    ``samples_per_bolopair`` of FilterLO).  Multi-GPU: numerator and hits are summed over ``group`` so
+    every rank builds the same Z.  Returns Zt, an (r, n) CUDA tensor (row k = column k of Z)."""
+    from . import distributed
+    dv.require_cuda()
+    nt, npix, pol = P.nrows, P.ncols, P.pol
+    ns = int(samples_per_detector)
+    t = torch.arange(nt, dtype=torch.int64, device=P._pix_dev.device)
+    coord = ((t % ns).to(torch.float64) + 0.5) / float(ns)
+    del t
+    num, den = dv.empty_f64(npix), dv.empty_f64(npix)
+    st = dv.stream()
+    dv.call("cm2_pointing_apply_t", dv.ptr(P._pix_dev), None, None, nt, 1, dv.ptr(coord), dv.ptr(num), npix, st)
+    coord.fill_(1.0)
+    dv.call("cm2_pointing_apply_t", dv.ptr(P._pix_dev), None, None, nt, 1, dv.ptr(coord), dv.ptr(den), npix, st)
+    del coord
+    if distributed.is_distributed(group):
+        distributed.all_reduce_sum_(num, group)
+        distributed.all_reduce_sum_(den, group)
+    seen = den > 0
+    band = torch.clamp((num / torch.clamp(den, min=1.0) * r).to(torch.int64), 0, r - 1)
+    Zt = torch.zeros((int(r), pol * npix), dtype=torch.float64, device=num.device)
+    if pol != 2:                                   # the intensity component (pol = 2 maps have none)
+        idx = torch.nonzero(seen).reshape(-1)
+        Zt[band[idx], pol * idx] = 1.0
+    return Zt

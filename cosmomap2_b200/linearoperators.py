@@ -1042,11 +1042,8 @@ class CoarseLO(lp.LinearOperator):
         zt = _columns_dev(Z)
         azt = _columns_dev(Az)
         n = zt.shape[1]
-        work = dv.empty_f64(int(dv.call("cm2_defl_work_doubles", int(r))))
-        e_dev = dv.empty_f64(r * r)
-        dv.call("cm2_defl_zt_apply", dv.ptr(zt), n, int(r), n, dv.ptr(azt), int(r), n, dv.ptr(e_dev),
-                dv.ptr(work), _stream())
-        self.E = dv.to_host(e_dev).reshape(r, r).T.copy()         # column-major r x r -> E[i, j]
+        from . import dense
+        self.E = dv.to_host(dense.gram(zt[:r], azt[:r])).copy()   # E = Z^T (A Z), one pass over Z and AZ (DMMA)
         self.r = int(r)
         self.apply = apply
         if apply == "eig":

@@ -14,8 +14,9 @@ from . import _device as dv
 
 
 def dgemm(A, B):
-    """``dgemm(A, B) = A^T . B^T`` (utilities/linear_algebra_funcs.py:16-29).  A plain library
-    GEMM: cuBLAS DGEMM through torch on the device."""
+    """``dgemm(A, B) = A^T . B^T`` (utilities/linear_algebra_funcs.py:16-29), on the fp64 tensor cores
+    by the library's own one-pass kernel (cm2_dense_gram): the reference calls it as
+    ``dgemm(Z, Az.T)`` = ``Z^T (A Z)`` with tall-skinny Z (linearoperators.py:1019)."""
     if type(A) == list:
         A = np.asarray(A, order="F")
     if type(B) == list:
@@ -23,7 +24,10 @@ def dgemm(A, B):
     host = not (isinstance(A, torch.Tensor) or isinstance(B, torch.Tensor))
     At = dv.to_dev_f64(np.asarray(A) if not isinstance(A, torch.Tensor) else A)
     Bt = dv.to_dev_f64(np.asarray(B) if not isinstance(B, torch.Tensor) else B)
-    out = torch.matmul(At.t(), Bt.t())
+    from . import dense
+    # A: k x m, B: n x k  ->  A^T B^T (m x n) = X^T Y with X = A (k x m), Y = B^T (k x n): the kernel wants
+    # the columns of X and Y contiguous, i.e. A^T (m, k) and B (n, k) row-contiguous
+    out = dense.gram(At.t().contiguous(), Bt.contiguous())
     return dv.to_host(out) if host else out
 
 

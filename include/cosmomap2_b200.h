@@ -241,6 +241,21 @@ int cm2_m2_apply(const double *Z, const double *AZ, int64_t n, int r, int64_t ld
                  const double *Einv, const double *bd_inv, int64_t npix, int pol,
                  const double *v, double *y, double *work, cm2_stream_t stream);
 
+/* ---- a11 / a12: the dense tall-skinny contractions on the fp64 tensor cores (DMMA m8n8k4) ----------
+ * Tall matrices are column-major with a leading dimension (every column contiguous).
+ *   gram   : out (r1 x r2, column-major, ldo) = X^T Y, X: n x r1 (ldx), Y: n x r2 (ldy); ONE pass over X
+ *            and Y per 32 x 32 panel of out.  E = Z^T (A Z): CoarseLO.__init__ -> dgemm(Z, Az.T),
+ *            interfaces/linearoperators.py:1019, utilities/linear_algebra_funcs.py:16-29.
+ *            work: cm2_dense_gram_work_doubles() doubles.
+ *   combine: Z (n x r, ldz) = V (n x m, ldv) U (m x r, ldu); Z must not overlap V.  Ritz vectors
+ *            V[:, :m] U (kp.utils.ritz, interfaces/deflationlib.py:204-219), build_Z (:140-184), and
+ *            the thick restart of cosmomap2_b200.eigsh. */
+int64_t cm2_dense_gram_work_doubles(void);
+int cm2_dense_gram(const double *X, int64_t ldx, int r1, const double *Y, int64_t ldy, int r2,
+                   int64_t n, double *out, int64_t ldo, double *work, cm2_stream_t stream);
+int cm2_dense_combine(const double *V, int64_t ldv, int64_t n, int m, const double *U, int64_t ldu,
+                      int r, double *Z, int64_t ldz, cm2_stream_t stream);
+
 /* ---- a14: PCG vector work (scipy _isolve/iterative.py:405-431) ------------------------------- */
 /* out[0] = a.b */
 int cm2_dot(const double *a, const double *b, int64_t n, double *out, cm2_stream_t stream);

@@ -223,6 +223,16 @@ def case_pcg_and_deflation():
         x, info = spla.cg(A, b, x0=np.zeros(n), M=Mbd, rtol=1e-8, maxiter=200, callback=cb)
         out = dict(pix_in=pix0, phi=phi, d=d, t=np.array(t), nb=nb, npix_old=npix_old, pol=pol,
                    npix=npix, b=b, cg_x=x, cg_info=info, cg_iters=len(hist), cg_hist=np.array(hist))
+        # iterates after fixed iteration counts (exit test off) and the fully converged solution: the
+        # quantities north_star's 1e-10 applies to (a solution stopped at rtol = 1e-8 is only defined
+        # to about 1e-8 * cond, whatever the implementation)
+        xs_fix = []
+        spla.cg(A, b, x0=np.zeros(n), M=Mbd, rtol=0.0, atol=0.0, maxiter=8, callback=lambda xk: xs_fix.append(xk.copy()))
+        out["cg_x_iter"] = np.array(xs_fix)
+        hist_t = []
+        xt, info_t = spla.cg(A, b, x0=np.zeros(n), M=Mbd, rtol=1e-13, maxiter=500,
+                             callback=lambda xk: hist_t.append(np.linalg.norm(b - A * xk)))
+        out.update(cg_x_tight=xt, cg_info_tight=info_t, cg_iters_tight=len(hist_t), cg_hist_tight=np.array(hist_t))
         # --- deflation space through ARPACK exactly as tests/test_2level_preconditioner.py:33
         x0 = np.ones(n)
         eigv, Z = spla.eigsh(A, M=B, Minv=Mbd, k=5, v0=x0, which="SM", ncv=15, tol=1e-10)
@@ -246,6 +256,12 @@ def case_pcg_and_deflation():
         x2, info2 = spla.cg(A, b, x0=np.zeros(n), M=M2, rtol=1e-8, maxiter=200,
                             callback=lambda xk: hist2.append(np.linalg.norm(b - A * xk)))
         out.update(cg2_x=x2, cg2_info=info2, cg2_iters=len(hist2), cg2_hist=np.array(hist2))
+        hist2t = []
+        x2t, info2t = spla.cg(A, b, x0=np.zeros(n), M=M2, rtol=1e-13, maxiter=500,
+                              callback=lambda xk: hist2t.append(np.linalg.norm(b - A * xk)))
+        out.update(cg2_x_tight=x2t, cg2_info_tight=info2t, cg2_iters_tight=len(hist2t), cg2_hist_tight=np.array(hist2t),
+                   E_eigvals=np.linalg.eigvalsh(0.5 * (E_lu.E + E_lu.E.T)) if hasattr(E_lu, "E") else
+                   np.linalg.eigvalsh(0.5 * (R.dgemm(Z, Az.T) + R.dgemm(Z, Az.T).T)))
         # --- in-tree Arnoldi on Mbd*A (src/test_M2_precond_onto_real_data.py:42-44)
         # tol=1e-3 terminates through the reference's element-wise stop test (deflationlib.py:101);
         # tol=1e-5 runs into inner_m and raises (deflationlib.py:111-112) -- both are recorded.
@@ -356,6 +372,10 @@ def case_fused_chains():
 
 if __name__ == "__main__":
     print("scipy", scipy.__version__, "numpy", np.__version__)
+    if len(sys.argv) > 1:                      # python make_golden.py case_pcg_and_deflation ...
+        for nm in sys.argv[1:]:
+            globals()[nm]()
+        sys.exit(0)
     case_process_and_pointing()
     case_obspix2()
     case_toeplitz()

@@ -44,7 +44,14 @@ def _build(impl, sc, pol, noise=None, filt=False, w_from_noise=True):
     return npix, P, Mbd, A, b, pts
 
 
-def _solve_both(cm, sc, pol, rtol, maxiter, **kw):
+TIGHT = 1e-13      # "fully converged": the solution is then defined to ~cond * 1e-13 whatever the rounding path
+
+
+def _solve_both(cm, sc, pol, rtol, maxiter, tight_maxiter=None, **kw):
+    """The reference's call (rtol, maxiter) on both sides: exit code, iteration count +-1, residual history
+    within 1e-10 of ||b|| (north_star).  A map stopped at a loose rtol is only defined to about that rtol, so
+    the MAPS are compared at 1e-10 on a second, fully converged solve when ``tight_maxiter`` is given
+    (returned instead of the loose ones)."""
     import oracle
     out = []
     for impl, solver in ((oracle, spla.cg), (cm, cm.cg)):
@@ -52,6 +59,9 @@ def _solve_both(cm, sc, pol, rtol, maxiter, **kw):
         hist = []
         x, info = solver(A, b, M=Mbd, rtol=rtol, maxiter=maxiter,
                          callback=lambda xk: hist.append(np.linalg.norm(b - A * np.asarray(xk))))
+        if tight_maxiter:
+            x, info_t = solver(A, b, M=Mbd, rtol=TIGHT, maxiter=tight_maxiter)
+            assert info_t == 0, "the tight solve did not converge"
         out.append((npix, b, x, info, np.array(hist)))
     (n0, b0, x0, i0, h0), (n1, b1, x1, i1, h1) = out
     assert n0 == n1 and i0 == i1
@@ -59,8 +69,7 @@ def _solve_both(cm, sc, pol, rtol, maxiter, **kw):
     gc.close(b1, b0, what="rhs")
     k = min(len(h0), len(h1))
     if k:
-        floor = 1e-11 * np.linalg.norm(b0)      # residuals at rounding level are not comparable
-        assert np.all(np.abs(h1[:k] - h0[:k]) <= 1e-6 * h0[:k] + floor), "residual history differs"
+        assert np.all(np.abs(h1[:k] - h0[:k]) <= 1e-10 * np.linalg.norm(b0)), "residual history differs"
     return x0, x1, h0, h1
 
 
@@ -72,7 +81,7 @@ def test_config0_ces_standin_unweighted_bd_pcg(cm):
                                flag_turnarounds=True)
     for pol in (1, 3):
         x0, x1, h0, h1 = _solve_both(cm, sc, pol, 1e-3, 10)
-        gc.close(x1, x0, rtol=1e-9, what="map pol=%d" % pol)
+        gc.close(x1, x0, rtol=1e-10, what="map pol=%d" % pol)
         assert len(h1) == 1          # exactly preconditioned: one iteration (src/test_BD...:52)
 
 
@@ -81,11 +90,11 @@ def test_config1_white_noise_bd_pcg(cm):
     from cosmomap2_b200 import synthetic
     sc = synthetic.raster_scan(800000, nside=64, ndet=16, nx=100, ny=60, samples_per_pixel=8.0, seed=2)
     x0, x1, h0, h1 = _solve_both(cm, sc, 3, 1e-10, 20, noise="white")
-    gc.close(x1, x0, rtol=1e-9, what="map")
+    gc.close(x1, x0, rtol=1e-10, what="map")
     assert len(h1) == 1
     # mismatched preconditioner (unit-weight M_BD): several iterations, same history on both sides
-    x0, x1, h0, h1 = _solve_both(cm, sc, 3, 1e-10, 100, noise="white", w_from_noise=False)
-    gc.close(x1, x0, rtol=1e-8, what="map (unit-weight M_BD)")
+    x0, x1, h0, h1 = _solve_both(cm, sc, 3, 1e-10, 100, tight_maxiter=300, noise="white", w_from_noise=False)
+    gc.close(x1, x0, rtol=1e-10, what="map (unit-weight M_BD)")
     assert len(h1) > 3
 
 
@@ -96,8 +105,8 @@ def test_config2_toeplitz_noise_bd_pcg(cm, nband):
     sc = synthetic.raster_scan(400000, nside=64, ndet=8, nx=90, ny=50, samples_per_pixel=6.0, seed=4,
                                flag_turnarounds=True)
     bands = synthetic.toeplitz_bands(sc.ndet, nband, seed=1)
-    x0, x1, h0, h1 = _solve_both(cm, sc, 3, 1e-9, 200, noise=bands)
-    gc.close(x1, x0, rtol=1e-7, what="map")
+    x0, x1, h0, h1 = _solve_both(cm, sc, 3, 1e-9, 200, tight_maxiter=500, noise=bands)
+    gc.close(x1, x0, rtol=1e-10, what="map")
     assert len(h1) > 2
 
 
@@ -107,9 +116,18 @@ def test_config2_subscan_filter_bd_pcg(cm):
     import oracle
     sc = synthetic.raster_scan(400000, nside=64, ndet=8, nx=90, ny=50, samples_per_pixel=6.0, seed=5,
                                flag_turnarounds=True)
+    # the reference's own call first (history, count), then a converged solve: A x = b - r, so the two A x
+    # differ by at most |r0| + |r1| <= 2e-12 ||b|| plus rounding -- compared at 1e-10
     x0, x1, h0, h1 = _solve_both(cm, sc, 1, 1e-4, 25, filt=True)
     npix, P, Mbd, A, b, pts = _build(oracle, sc, 1, filt=True)
-    gc.close(A * x1, A * x0, rtol=1e-6, what="A x (null space of P^T F P projected out)")
+    xs = []
+    for impl, solver in ((oracle, spla.cg), (cm, cm.cg)):
+        npix_i, P_i, M_i, A_i, b_i, _ = _build(impl, sc, 1, filt=True)
+        x, info = solver(A_i, b_i, M=M_i, rtol=1e-12, maxiter=2000)
+        assert info == 0
+        xs.append(x)
+    scale = np.max(np.abs(b))
+    assert np.max(np.abs(A * xs[1] - A * xs[0])) <= 1e-10 * scale, "A x differs (null space of P^T F P projected out)"
 
 
 def test_config3_two_level_from_arnoldi(cm):
@@ -139,16 +157,21 @@ def test_config3_two_level_from_arnoldi(cm):
         xb, ib = solver(A, b, M=Mbd, rtol=1e-9, maxiter=300, callback=lambda xk: it_bd.append(1))
         xm, im = solver(A, b, M=M2, rtol=1e-9, maxiter=300, callback=lambda xk: it_m2.append(1))
         assert ib == 0 and im == 0
+        xb, ib = solver(A, b, M=Mbd, rtol=TIGHT, maxiter=600)      # converged maps for the 1e-10 comparison
+        xm, im = solver(A, b, M=M2, rtol=TIGHT, maxiter=600)
+        assert ib == 0 and im == 0
         res.append(dict(theta=theta, Z=np.asarray(Z), xb=xb, xm=xm, nbd=len(it_bd), nm2=len(it_m2)))
     o, g = res
-    gc.close(g["theta"][:10], o["theta"][:10], rtol=1e-8, what="Ritz values")
+    gc.close(g["theta"][:10], o["theta"][:10], rtol=1e-10, what="Ritz values")
     # same deflation subspace (Z is defined up to rotation/sign): compare projectors on a probe
     probe = np.random.default_rng(0).standard_normal(o["Z"].shape[0])
     po = o["Z"].dot(np.linalg.lstsq(o["Z"], probe, rcond=None)[0])
     pg = g["Z"].dot(np.linalg.lstsq(g["Z"], probe, rcond=None)[0])
-    gc.close(pg, po, rtol=1e-6, what="deflation subspace projector")
-    gc.close(g["xb"], o["xb"], rtol=1e-7, what="M_BD solution")
-    gc.close(g["xm"], o["xm"], rtol=1e-7, what="M_2lvl solution")
+    # the 6-dimensional Ritz subspace is defined up to (rounding) / (gap between theta_6 and theta_7, ~1e-2
+    # of the spectrum here): 1e-10 holds for the Ritz VALUES above, 1e-9 for the projector
+    gc.close(pg, po, rtol=1e-9, what="deflation subspace projector")
+    gc.close(g["xb"], o["xb"], rtol=1e-10, what="M_BD solution")
+    gc.close(g["xm"], o["xm"], rtol=1e-10, what="M_2lvl solution")
     assert abs(g["nbd"] - o["nbd"]) <= 1 and abs(g["nm2"] - o["nm2"]) <= 1
     assert g["nm2"] <= g["nbd"] + 3     # Ritz vectors after 30 steps are only roughly converged
 
@@ -189,7 +212,7 @@ def test_config0_from_a_ces_file(cm, tmp_path):
         assert n0 == n1 and i0 == 0 and i1 == 0
         gc.exact(o1, o0, "observed HEALPix pixels")
         gc.close(b1, b0, what="rhs from file")
-        gc.close(x1, x0, rtol=1e-9, what="map from file, pol=%d" % pol)
+        gc.close(x1, x0, rtol=1e-10, what="map from file, pol=%d" % pol)
         for a, bb in zip(h1, h0):
-            gc.close(a, bb, rtol=1e-9, what="HEALPix map")
+            gc.close(a, bb, rtol=1e-10, what="HEALPix map")
             assert np.count_nonzero(a) <= n1

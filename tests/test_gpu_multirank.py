@@ -114,15 +114,18 @@ def test_cooperative_launch_refused_falls_back():
     import cosmomap2_b200 as cm
     from cosmomap2_b200 import _device as dv
     from multirank import split_problem
-    sc = _scan(nt=40000)
-    A, _, Mbd, b, npix = split_problem(sc, 3, 1, cm)
-    x0, info0 = cm.cg(A, b, M=Mbd, rtol=1e-10, maxiter=30)
+    sc = _scan()
+    A, _, Mbd, b, npix = split_problem(sc, 3, 1, cm, correlated=True)
+    r0, r1 = [], []
+    x0, info0 = cm.cg(A, b, M=Mbd, rtol=1e-10, maxiter=60, residuals=r0)
+    assert info0 == 0, r0
     old = dv.call("cm2_pcg_bd_iter_refuse", 1)
     try:
-        x1, info1 = cm.cg(A, b, M=Mbd, rtol=1e-10, maxiter=30)
+        x1, info1 = cm.cg(A, b, M=Mbd, rtol=1e-10, maxiter=60, residuals=r1)
     finally:
         dv.call("cm2_pcg_bd_iter_refuse", old)
-    assert info0 == 0 and info1 == 0
+    assert info1 == 0, (r0, r1)
+    assert len(r0) == len(r1)
     assert np.max(np.abs(x1 - x0)) / np.max(np.abs(x0)) < 1e-12
 
 

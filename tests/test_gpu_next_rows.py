@@ -304,7 +304,7 @@ def test_reference_hdf5_fixture_through_the_solve(cm, name, pixscale, pol):
     assert o["npix"] == g["npix"] and o["info"] == 0 and g["info"] == 0
     gc.exact(g["pix"], o["pix"], "relabelled pixels of the fixture")
     gc.close(g["b"], o["b"], what="b")
-    gc.close(g["x"], o["x"], rtol=1e-9, what="x")
+    gc.close(g["x"], o["x"], rtol=1e-10, what="x")
     if "toep" in o:
         gc.close(g["toep"], o["toep"], what="P^T N_toeplitz P x")
 
