@@ -286,20 +286,12 @@ __global__ void __launch_bounds__(BLOCK) k_pointing_apply_t(const int32_t *__res
     }
 }
 
-// L2 prefetch of one warp tile of the TOD stream (one lane issues three bulk prefetches: 1 kB of pix,
-// 2 kB of cos, 2 kB of sin), used PF tiles ahead of the loads: the loads then find their lines in L2
-// instead of waiting for DRAM.  Experimental (cm2_amatvec_white_set_prefetch), off by default.
-__device__ __forceinline__ void prefetch_tile_l2(const void *p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 // Fused y = P^T diag(w) P x.  The next tile's pix/cos/sin loads are issued between the compress
 // and the merge phase of the current tile, so their DRAM latency overlaps the shuffles and REDs.
-template <int POL, bool PF = false>
+template <int POL>
 __global__ void __launch_bounds__(BLOCK) k_amatvec_white(const int32_t *__restrict__ pix, const double *__restrict__ cs,
                                                          const double *__restrict__ sn, int64_t nt, BlockW bw,
-                                                         const double *__restrict__ x, double *__restrict__ y,
-                                                         int pf_dist = 0) {
+                                                         const double *__restrict__ x, double *__restrict__ y) {
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
     const int64_t ntiles = (nt + TILE - 1) / TILE;
@@ -318,13 +310,6 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_white(const int32_t *__restri
         double c[K], s[K];
         load_pix(pix, t0, nt, p);
         if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
-        if constexpr (PF) {                     // pull the tile this warp reads pf_dist trips from now into L2
-            const int64_t tp = (tile + (int64_t)pf_dist * nwarps) * TILE;
-            if (lane == 0 && tp + TILE <= nt) {
-                prefetch_tile_l2(pix + tp, TILE * 4);
-                if (POL > 1) { prefetch_tile_l2(cs + tp, TILE * 8); prefetch_tile_l2(sn + tp, TILE * 8); }
-            }
-        }
         run_merge<POL, POL>(y, rs);             // previous tile (the empty state on the first trip emits nothing)
         double w[K], xv[K][POL], v[K];
         gather_x<POL>(x, p, xv);
@@ -1158,15 +1143,6 @@ static int check_blocks(const double *wblk, int64_t nblocks, int64_t blocksize, 
     return CM2_OK;
 }
 
-// experimental knob: tiles of L2 prefetch ahead of the fused white A-matvec's loads (0 = off, the default);
-// returns the previous value
-static int g_white_prefetch = 0;
-extern "C" int cm2_amatvec_white_set_prefetch(int tiles_ahead) {
-    const int old = g_white_prefetch;
-    g_white_prefetch = tiles_ahead < 0 ? 0 : (tiles_ahead > 64 ? 64 : tiles_ahead);
-    return old;
-}
-
 extern "C" int cm2_amatvec_white(const int32_t *pix, const double *c, const double *s, int64_t nt, int pol,
                                  const double *wblk, int64_t nblocks, int64_t blocksize, const int64_t *blk_start,
                                  const double *x, double *y, int64_t npix, cm2_stream_t stream) {
@@ -1179,14 +1155,6 @@ extern "C" int cm2_amatvec_white(const int32_t *pix, const double *c, const doub
     if (npix > 0) CM2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)npix * pol, st));
     if (nt == 0 || npix == 0) return CM2_OK;
     const BlockW bw = make_blockw(wblk, nblocks, blocksize, blk_start);
-    const int pf = g_white_prefetch;
-    if (pf > 0) {                              // experimental: L2 prefetch pf tiles ahead
-        if (pol == 1) k_amatvec_white<1, true><<<tod_grid(k_amatvec_white<1, true>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, x, y, pf);
-        else if (pol == 2) k_amatvec_white<2, true><<<tod_grid(k_amatvec_white<2, true>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, x, y, pf);
-        else k_amatvec_white<3, true><<<tod_grid(k_amatvec_white<3, true>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, x, y, pf);
-        CM2_LAUNCHED();
-        return CM2_OK;
-    }
     if (pol == 1) k_amatvec_white<1><<<tod_grid(k_amatvec_white<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, x, y);
     else if (pol == 2) k_amatvec_white<2><<<tod_grid(k_amatvec_white<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, x, y);
     else k_amatvec_white<3><<<tod_grid(k_amatvec_white<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, x, y);

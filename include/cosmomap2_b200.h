@@ -142,9 +142,6 @@ int cm2_amatvec_white(const int32_t *pix, const double *cos2phi, const double *s
                       int64_t nt, int pol, const double *wblk, int64_t nblocks,
                       int64_t blocksize, const int64_t *blk_start, const double *x, double *y,
                       int64_t npix, cm2_stream_t stream);
-/* Experimental knob of cm2_amatvec_white: bulk L2 prefetch of the TOD tile each warp will read
- * `tiles_ahead` loop trips later (0 = off, the default; clamped to 64).  Returns the previous value. */
-int cm2_amatvec_white_set_prefetch(int tiles_ahead);
 /* y = P^T F P x with the offset filter (src/test_M2_precond_onto_real_data.py:86) */
 int cm2_amatvec_filter(const int32_t *pix, const double *cos2phi, const double *sin2phi,
                        int64_t nt, int pol, const int64_t *seg_start, const int64_t *seg_end,

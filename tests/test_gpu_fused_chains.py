@@ -200,13 +200,7 @@ def test_fused_filter_pointing_falls_back_without_runs(cm):
     gc.close(out[1], out[0])
 
 
-# ---- experimental paths: written after the round's GPU budget was spent; run with CM2_EXPERIMENTAL=1 ----
-import os  # noqa: E402
-
-EXPERIMENTAL = os.environ.get("CM2_EXPERIMENTAL") == "1"
-
-
-@pytest.mark.skipif(not EXPERIMENTAL, reason="experimental path, not yet run on a B200 (set CM2_EXPERIMENTAL=1)")
+# ---- the run-table Legendre A-matvec (promoted in round 2 after its first B200 run: order 1 0.61 vs 0.79 ms) ----
 @pytest.mark.parametrize("pol", [1, 3])
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
 def test_poly_run_table_path(cm, pol, order):
@@ -248,25 +242,3 @@ def test_poly_run_table_path(cm, pol, order):
             lo.FILTER_POLY_RUN_TABLE = old
     gc.close(res["subscan"], res["oracle"], what="per-subscan kernel")
     gc.close(res["table"], res["oracle"], what="run-table path")
-
-
-@pytest.mark.skipif(not EXPERIMENTAL, reason="experimental path, not yet run on a B200 (set CM2_EXPERIMENTAL=1)")
-def test_white_amatvec_l2_prefetch_variant(cm):
-    """cm2_amatvec_white_set_prefetch only moves data into L2 earlier: same result for every distance,
-    including distances that point beyond the end of the TOD."""
-    from cosmomap2_b200 import _cabi
-    sc = _raster(nt=300000, ndet=6, seed=2, flag_turnarounds=True)
-    pix = sc.pix.astype(np.int64)
-    N = cm.BlockLO(sc.ns, sc.weights)
-    pts = cm.ProcessTimeSamples(pix, sc.npix_full, pol=3, phi=sc.phi, w=N.diag)
-    npix = pts.get_new_pixel[0]
-    P = cm.SparseLO(npix, sc.nt, pix, pol=3, angle_processed=pts)
-    A = P.T * N * P
-    x = np.random.default_rng(1).standard_normal(3 * npix)
-    ref = A * x
-    try:
-        for pf in (1, 2, 8, 64):
-            assert _cabi.call("cm2_amatvec_white_set_prefetch", pf) >= 0
-            gc.close(A * x, ref, rtol=1e-12, what="prefetch distance %d" % pf)
-    finally:
-        _cabi.call("cm2_amatvec_white_set_prefetch", 0)

@@ -73,20 +73,7 @@ def main():
     out["FP_fused_GBs"] = (28.0 * nt + 24.0 * npix) / (t * 1e-3) / 1e9
     out["FP_chain_ms"] = tc
     out["FP_fused_vs_chain_relerr"] = float((d - dc).abs().max() / dc.abs().max())
-    if os.environ.get("CM2_EXPERIMENTAL") == "1":        # L2 prefetch distance of the fused white A-matvec
-        from cosmomap2_b200 import _cabi
-        Nw = cm.BlockLO(ns, list(np.random.default_rng(5).uniform(0.5, 1.5, ndet)))
-        Aw = P.T * Nw * P
-        for _ in range(1500):                              # settle the clocks under load first
-            Aw._apply(x)
-        y0 = Aw._apply(x)
-        for pf in (0, 1, 2, 4, 8, 0):
-            _cabi.call("cm2_amatvec_white_set_prefetch", pf)
-            tw = timeit(lambda: Aw._apply(x), reps=200, warm=20)
-            out["amatvec_white_pf%d_ms%s" % (pf, "_again" if ("amatvec_white_pf%d_ms" % pf) in out else "")] = tw
-            out["amatvec_white_pf%d_relerr" % pf] = float((Aw._apply(x) - y0).abs().max() / y0.abs().max())
-        _cabi.call("cm2_amatvec_white_set_prefetch", 0)
-    if os.environ.get("CM2_EXPERIMENTAL") == "1":        # Legendre run-table path against the per-subscan kernel
+    if True:                                              # Legendre run-table path against the per-subscan kernel
         for order in (1, 3):
             Fk = cm.FilterLO(nt, [sub_len, sub_start], ns, ndet, pts._pix_dev, poly_order=order)
             res = {}
@@ -96,7 +83,7 @@ def main():
                 tk = timeit(lambda: Ak._apply(x))
                 res[table] = Ak._apply(x)
                 out["amatvec_leg%d_%s_ms" % (order, "table" if table else "subscan")] = tk
-            lo.FILTER_POLY_RUN_TABLE = False
+            lo.FILTER_POLY_RUN_TABLE = True
             out["amatvec_leg%d_table_vs_subscan_relerr" % order] = float((res[True] - res[False]).abs().max() / res[False].abs().max())
     print(json.dumps(out))
 
