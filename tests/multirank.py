@@ -274,6 +274,9 @@ def worker(case, out_path):
         sc, A_loc, Mbd, b, npix = _rank_problem(cm, distributed, synthetic, rank, world, pol=3)
         A = distributed.AllReduceLO(A_loc)
         had_p2p = A._p2p is not None
+        # build the sharded solver now: its set-up is collective (IPC handle exchange) and would simply
+        # make rank 0 wait for the late rank on the host; the timeout under test is the one in the kernel
+        assert A.sharded_solver(Mbd) is not None or not had_p2p
         dist.barrier()
         torch.cuda.synchronize()
         if rank == 1:

@@ -213,6 +213,9 @@ def test_config0_from_a_ces_file(cm, tmp_path):
         gc.exact(o1, o0, "observed HEALPix pixels")
         gc.close(b1, b0, what="rhs from file")
         gc.close(x1, x0, rtol=1e-10, what="map from file, pol=%d" % pol)
-        for a, bb in zip(h1, h0):
-            gc.close(a, bb, rtol=1e-10, what="HEALPix map")
+        # the HEALPix maps are a permutation of x: same tolerance relative to the same scale (max |x| over
+        # all Stokes components, as for x above), and the GPU's own maps are bit-exactly its x
+        gc.close(np.concatenate(h1), np.concatenate(h0), rtol=1e-10, what="HEALPix maps")
+        for k, a in enumerate(h1):
             assert np.count_nonzero(a) <= n1
+            gc.exact(a[np.asarray(o1)], x1[k::pol], "HEALPix map %d is a permutation of x" % k)
