@@ -371,43 +371,72 @@ def eigsh(A, k=6, M=None, Minv=None, which="SM", ncv=None, tol=0, maxiter=None, 
     return (w, Z) if device else (w, dv.to_host(Z))
 
 
-def scan_coarse_space(P, r, samples_per_detector, group=None):
+def scan_coarse_space(P, r, samples_per_detector, group=None, A=None, Mbd=None, smooth=2):
     """A-priori deflation space for a filtered raster scan (an ADDITION to the reference's two routes to
     Z -- ARPACK in its tests, Arnoldi/Ritz in src/test_M2_precond_onto_real_data.py:13-50 -- for the same
     ``DeflationLO`` / ``CoarseLO`` / ``M2 = Mbd*R + Zd*E*Zd.T`` machinery).
 
     With a subscan filter F the small eigenvalues of ``M_BD P^T F P`` belong to maps that are constant
     along every subscan: for a raster scan, intensity maps that vary only ACROSS the scan direction, one
-    mode per map row (SURVEY 8d caveat; measured on the oracle: 32 rows -> exactly 32 eigenvalues below
-    0.13, the rest above 0.48).  Krylov methods need about as many A applies to resolve those vectors as
-    CG needs to solve the system, so a Ritz-built Z cannot pay for itself on one right-hand side.  The
-    scan tells us the space directly: pixels are ordered by WHEN the scan visits them (the cross-scan
-    drift is monotone in time), and column k of Z is the intensity indicator of the pixels whose mean
-    visiting time falls in the k-th of ``r`` equal time bands.  Cost: one pol-1 scatter of the TOD, no
-    A apply; ``A Z`` then costs r applies.
+    mode per map row (SURVEY 8d caveat; dense spectrum of a 24-row oracle problem: exactly 24 eigenvalues
+    below 0.19, the rest above 0.48).  Krylov methods need about as many A applies to resolve those vectors
+    as CG needs to solve the system, so a Ritz-built Z cannot pay for itself on one right-hand side.  The
+    scan tells us the space directly: the cross-scan drift is monotone in time, so WHEN a pixel is visited
+    orders the rows, and column k of Z is the intensity indicator of the pixels of the k-th of ``r`` bands
+    of that ordering (a subdomain / Nicolaides coarse space: the bands are 1-D subdomains across the scan).
+
+    * the visiting time is averaged on the CIRCLE (mean of cos / sin of 2 pi t / T per pixel, band = arc of
+      the mean angle): a scan whose drift wraps around the patch visits the seam rows at both ends of the
+      timeline and a linear mean would put them into the middle bands (measured on a 300-row problem, r = 32:
+      199 M_BD iterations -> 149 with the linear mean, 49 with the circular one);
+    * detectors see a pixel row at slightly different times, so the mean angle jitters inside a row and a
+      band edge would split rows; ``smooth`` sweeps of the smoother ``c <- c - [M_BD A (c, 0, 0)]_I`` (needs
+      ``A`` and ``Mbd``; one A apply per sweep and coordinate) pull the coordinate of every pixel to the
+      mean of the subscans that cross it, which makes it constant along rows (rows split: 229 -> 22 of 300
+      after two sweeps; iterations 49 -> 40; with the true row index as coordinate: 41).
+
+    Cost: two pol-1 scatters of the TOD + ``2 * smooth`` A applies; ``A Z`` then costs r applies.
 
     ``P``: the SparseLO of this rank; ``samples_per_detector``: length of one detector timeline (the
-    ``samples_per_bolopair`` of FilterLO).  Multi-GPU: numerator and hits are summed over ``group`` so
-    every rank builds the same Z.  Returns Zt, an (r, n) CUDA tensor (row k = column k of Z)."""
+    ``samples_per_bolopair`` of FilterLO).  Multi-GPU: the sums are taken over ``group`` (and ``A`` is the
+    AllReduceLO), so every rank builds the same Z.  Returns Zt, an (r, n) CUDA tensor (row k = column k of Z)."""
     from . import distributed
     dv.require_cuda()
     nt, npix, pol = P.nrows, P.ncols, P.pol
     ns = int(samples_per_detector)
-    t = torch.arange(nt, dtype=torch.int64, device=P._pix_dev.device)
-    coord = ((t % ns).to(torch.float64) + 0.5) / float(ns)
-    del t
-    num, den = dv.empty_f64(npix), dv.empty_f64(npix)
+    r = int(r)
+    dev = P._pix_dev.device
     st = dv.stream()
-    dv.call("cm2_pointing_apply_t", dv.ptr(P._pix_dev), None, None, nt, 1, dv.ptr(coord), dv.ptr(num), npix, st)
-    coord.fill_(1.0)
-    dv.call("cm2_pointing_apply_t", dv.ptr(P._pix_dev), None, None, nt, 1, dv.ptr(coord), dv.ptr(den), npix, st)
-    del coord
+    sums = torch.zeros((3, npix), dtype=torch.float64, device=dev)           # sum cos, sum sin, hits
+    part = dv.empty_f64(npix)
+    # theta depends on the position inside the detector timeline only: one timeline's worth of cos / sin
+    # / ones, scattered detector by detector (chunks must start 32-byte aligned: ns a multiple of 8)
+    chunk = ns if (ns % 8 == 0 and nt % ns == 0) else nt
+    t = torch.arange(chunk, dtype=torch.int64, device=dev)
+    theta = ((t % ns).to(torch.float64) + 0.5) * (2.0 * np.pi / float(ns))
+    del t
+    for k, src in enumerate((torch.cos(theta), torch.sin(theta), torch.ones_like(theta))):
+        for t0 in range(0, nt, chunk):
+            dv.call("cm2_pointing_apply_t", dv.ptr(P._pix_dev[t0:t0 + chunk]), None, None, chunk, 1, dv.ptr(src),
+                    dv.ptr(part), npix, st)
+            sums[k] += part
+    del theta, src
     if distributed.is_distributed(group):
-        distributed.all_reduce_sum_(num, group)
-        distributed.all_reduce_sum_(den, group)
-    seen = den > 0
-    band = torch.clamp((num / torch.clamp(den, min=1.0) * r).to(torch.int64), 0, r - 1)
-    Zt = torch.zeros((int(r), pol * npix), dtype=torch.float64, device=num.device)
+        distributed.all_reduce_sum_(sums, group)
+    seen = sums[2] > 0
+    den = torch.clamp(sums[2], min=1.0)
+    coord = [sums[0] / den, sums[1] / den]
+    if A is not None and Mbd is not None and pol != 2:
+        A, Mbd = _as_op(A), _as_op(Mbd)
+        w = dv.zeros_f64(pol * npix)
+        for _ in range(int(smooth)):
+            for c in coord:
+                w.zero_()
+                w[0::pol] = c
+                c -= Mbd._apply(A._apply(w))[0::pol]
+    ang = torch.remainder(torch.atan2(coord[1], coord[0]), 2.0 * np.pi) / (2.0 * np.pi)
+    band = torch.clamp((ang * r).to(torch.int64), 0, r - 1)
+    Zt = torch.zeros((r, pol * npix), dtype=torch.float64, device=dev)
     if pol != 2:                                   # the intensity component (pol = 2 maps have none)
         idx = torch.nonzero(seen).reshape(-1)
         Zt[band[idx], pol * idx] = 1.0

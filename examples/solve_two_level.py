@@ -64,7 +64,11 @@ def main():
     ap.add_argument("--nx", type=int, default=1600)
     ap.add_argument("--ny", type=int, default=800)
     ap.add_argument("--ndet", type=int, default=64)
-    ap.add_argument("--r", type=int, default=24)
+    ap.add_argument("--r", type=int, default=32)
+    ap.add_argument("--coarse", default="scan", choices=["scan", "ritz"],
+                    help="deflation space: 'scan' = a-priori subdomain space from the scan order, "
+                         "'ritz' = preconditioned Arnoldi + Ritz vectors (the reference's recipe)")
+    ap.add_argument("--smooth", type=int, default=2, help="coordinate smoothing sweeps of the scan coarse space")
     ap.add_argument("--arnoldi", type=int, default=300)
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--maxiter", type=int, default=2000)
@@ -125,14 +129,21 @@ def main():
            "nseg_per_gpu": F.nseg, "poly_order": args.poly_order, "shard_m2": bool(args.shard_m2 and world > 1)}
     x_bd, out["M_BD"] = solve(Mbd, "M_BD")
 
-    # ---- deflation space: preconditioned Arnoldi, Ritz vectors of the smallest Ritz values ----------
+    # ---- deflation space ---------------------------------------------------------------------------
     t0 = time.perf_counter()
-    V, H, m = cm.run_krypy_arnoldi(A, torch.ones(n, dtype=torch.float64, device="cuda"), Mbd, 1e-5,
-                                   maxiter=args.arnoldi, ortho="dmgs")
-    theta = np.sort(np.linalg.eigvalsh(H[:H.shape[1], :]))
-    r = min(args.r, len(theta) - 1)
-    thr = 0.5 * (theta[r - 1] + theta[r])
-    Z, r, th = cm.find_ritz_eigenvalues(H, V, threshold=thr, eigenvalues=True)
+    if args.coarse == "scan":
+        # a-priori subdomain space from the scan order (cosmomap2_b200.scan_coarse_space): no Krylov phase
+        Z = cm.scan_coarse_space(P, args.r, ns, A=A, Mbd=Mbd, smooth=args.smooth).t()
+        r, m, theta, thr = args.r, 0, np.zeros(1), 0.0
+    else:
+        # the reference's recipe: preconditioned Arnoldi, Ritz vectors of the smallest Ritz values
+        V, H, m = cm.run_krypy_arnoldi(A, torch.ones(n, dtype=torch.float64, device="cuda"), Mbd, 1e-5,
+                                       maxiter=args.arnoldi, ortho="dmgs")
+        theta = np.sort(np.linalg.eigvalsh(H[:H.shape[1], :]))
+        r = min(args.r, len(theta) - 1)
+        thr = 0.5 * (theta[r - 1] + theta[r])
+        Z, r, th = cm.find_ritz_eigenvalues(H, V, threshold=thr, eigenvalues=True)
+        del V
     Zc = Z.contiguous() if isinstance(Z, torch.Tensor) else Z
     AZ = torch.stack([A._apply(dv.to_dev_f64(Zc[:, i].contiguous())) for i in range(r)]).t()
     E = cm.CoarseLO(Zc, AZ, r, apply="eig")
@@ -142,7 +153,7 @@ def main():
     else:
         M2 = Mbd * (cm.lp.IdentityOperator(n) - AZd * E * Zd.T) + Zd * E * Zd.T  # fused at first use
     torch.cuda.synchronize()
-    out["deflation"] = dict(arnoldi_steps=int(m), r=int(r), ritz_min=float(theta[0]), ritz_cut=float(thr),
+    out["deflation"] = dict(kind=args.coarse, arnoldi_steps=int(m), r=int(r), ritz_min=float(theta[0]), ritz_cut=float(thr),
                             ritz_max=float(theta[-1]), discarded_E_modes=int(getattr(E, "ndiscarded", 0)),
                             build_seconds=time.perf_counter() - t0)
     x_m2, out["M_2lvl"] = solve(M2, "M_2lvl")
