@@ -67,6 +67,10 @@ def parse():
     ap.add_argument("--cpu-iters", type=int, default=10)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the `secondary` block (configs[2], configs[3], configs[4] on this run's GPUs)")
+    ap.add_argument("--secondary-timeout", type=float, default=420.0,
+                    help="seconds after which the line is printed without the unfinished part of `secondary`")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --nt samples per GPU (default, the contract); strong: --nt samples in total")
     return ap.parse_args()
@@ -170,6 +174,38 @@ class ClockSampler(object):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+def run_secondary(world, rank, out):
+    """configs[2], configs[3] and configs[4] on this run's GPUs (cosmomap2_b200/workloads.py, the functions behind
+    examples/solve_correlated.py and examples/solve_two_level.py): per-GPU shares of the named sizes, so that
+    N = 8 runs them at exactly 1e9, 4e9 and 8e9 samples.  Results go into ``out`` as they complete."""
+    import gc
+    import torch
+    from cosmomap2_b200 import workloads
+
+    def run(key, fn, **kw):
+        t0 = time.time()
+        try:
+            res = fn(**kw)
+            res["wall_seconds_incl_setup"] = time.time() - t0
+            out[key] = res
+        except Exception as e:                      # noqa: BLE001 -- the headline line must still be printed
+            out[key] = {"error": "%s: %s" % (type(e).__name__, e)}
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    # configs[2]: 1e9 samples / 64 detectors over 8 GPUs = 1.25e8 samples, 8 detectors per GPU
+    run("configs[2]", workloads.correlated, nt=1.25e8, ndet=8, nband=4096, nside=512, nx=1000, ny=500, rtol=1e-6,
+        maxiter=300, time_iters=10, symmetry=False)
+    # configs[3]: 4e9 samples over 8 GPUs = 5e8 per GPU, nside 1024, r = 32
+    run("configs[3]", workloads.two_level, nt=5e8, nside=1024, nx=1600, ny=800, ndet=64, r=32, coarse="scan", smooth=2,
+        rtol=1e-8, maxiter=2000)
+    # configs[4]: 8e9 samples in total when they fit (N >= 4: strong scaling), else 1e9 per GPU; nside 2048
+    nt4 = 8e9 / world if world >= 4 else 1e9
+    run("configs[4]", workloads.white, nt=nt4, nside=2048, nx=3200, ny=1600, ndet=64, steps=20)
+    if "error" not in out["configs[4]"]:
+        out["configs[4]"]["scaling"] = "strong (8e9 samples in total)" if world >= 4 else "1e9 samples per GPU (8e9 do not fit %d GPU)" % world
 
 
 def main():
@@ -388,6 +424,8 @@ def main():
                        "check": check},
             "roofline": {"bound": "hbm", "kernel": "k_amatvec_white<3> (cm2_amatvec_white)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one committed `ncu --set full` capture of "
+                                           "this kernel on this workload (profiles/amatvec_white_traffic.json), not measured in this run",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": t_a_ms, "frac_of_8TBs_spec": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": UNIT,
@@ -412,6 +450,28 @@ def main():
                 "sample": "oracle port (C twin of the reference's weave loops, gcc -O3, + scipy cg) on %d samples of the "
                           "same workload generator, %d iterations, %.2f s/iteration" % (nt_cpu, args.cpu_iters, t_iter),
                 "host_cores_available": os.cpu_count()}
+    else:
+        line = None
+    failed_primary = world > 1 and ((sharded and solver.failed()) or (getattr(A, "_p2p", None) is not None and A._p2p.error() != 0))
+    if not args.no_secondary and not failed_primary:
+        # the other configurations, on the same GPUs, after the headline measurement.  A watchdog prints the line
+        # with whatever has completed if a part hangs (every rank exits then).
+        secondary = {"note": "per-GPU shares of configs[2] (1e9 samples / 8), configs[3] (4e9 / 8) and configs[4]; device-generated "
+                             "synthetic scans; solve times are wall clock around cosmomap2_b200.cg, kernel times CUDA events, max over ranks"}
+        if line is not None:
+            line["secondary"] = secondary
+
+        def watchdog():
+            if line is not None:
+                secondary["error"] = "timeout after %.0f s: unfinished parts are missing" % args.secondary_timeout
+                emit(line)
+            os._exit(0)
+        timer = threading.Timer(args.secondary_timeout, watchdog)
+        timer.daemon = True
+        timer.start()
+        run_secondary(world, rank, secondary)
+        timer.cancel()
+    if line is not None:
         emit(line)
     if world > 1:
         if sharded and solver.failed():

@@ -46,17 +46,17 @@ SIGNATURES = {
     "cm2_toeplitz_fft_scratch_bytes": (_i64, [_i64]),
     "cm2_noise_toeplitz_fft_apply": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _int, _vp]),
     "cm2_filter_offset_apply": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
-    "cm2_amatvec_white": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "cm2_amatvec_white": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp]),
     "cm2_amatvec_filter": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "cm2_filter_runs_mark": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "cm2_filter_runs_fill": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cm2_filter_seg_mean": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
-    "cm2_amatvec_filter_mu": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "cm2_amatvec_filter_mu": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
     "cm2_filter_poly_gram": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
     "cm2_filter_poly_runs_fill": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cm2_filter_poly_seg_coef": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp]),
     "cm2_amatvec_filter_poly_mu": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp,
-                                          _i64, _int, _vp]),
+                                          _i64, _int, _i64, _vp]),
     "cm2_pointing_filter_mu": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "cm2_amatvec_toeplitz_max_band": (_int, []),
     "cm2_amatvec_toeplitz": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _int, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),

@@ -79,6 +79,41 @@ __device__ __forceinline__ void chunk_weights(const BlockW &bw, int64_t t0, int6
     }
 }
 
+// Order in which the persistent warps walk the tiles.  S = 1: time order.  S > 1: the tile sequence is cut into
+// S streams of T tiles (S = number of detector timelines) and walked round-robin over the streams, so that all
+// detectors are processed at the same scan time: they sweep the same sky rows then, and the part of x / y the
+// kernel touches stays in L2 when the map itself (24 B/pixel each) is larger than L2.  In time order every
+// detector timeline is one pass over the WHOLE map.
+struct TileOrder {
+    unsigned S, T;
+    __device__ __forceinline__ int64_t count() const { return (int64_t)S * T; }
+    __device__ __forceinline__ int64_t tile(int64_t v) const {
+        if (S == 1) return v;
+        const unsigned q = (unsigned)v / S, r = (unsigned)v - q * S;
+        return (int64_t)r * T + q;
+    }
+    // first v' in {v, v + step, ...} below count() whose tile exists; sets tile = -1 at the end
+    __device__ __forceinline__ int64_t next(int64_t v, int64_t step, int64_t ntiles, int64_t &t) const {
+        const int64_t nv = count();
+        for (; v < nv; v += step) {
+            t = tile(v);
+            if (t < ntiles) return v;
+        }
+        t = -1;
+        return v;
+    }
+};
+
+static TileOrder make_order(int64_t nt, int64_t nstreams) {
+    const int64_t ntiles = (nt + TILE - 1) / TILE;
+    TileOrder o{1u, (unsigned)ntiles};
+    if (nstreams > 1 && nstreams <= 65536 && ntiles >= 4 * nstreams && ntiles < ((int64_t)1 << 31)) {
+        o.S = (unsigned)nstreams;
+        o.T = (unsigned)((ntiles + nstreams - 1) / nstreams);
+    }
+    return o;
+}
+
 __device__ __forceinline__ void load_pix(const int32_t *__restrict__ pix, int64_t t0, int64_t nt, int (&p)[K]) {
     if (t0 + K <= nt) {
         I8 v = ld_stream_i8(pix + t0);
@@ -290,7 +325,7 @@ __global__ void __launch_bounds__(BLOCK) k_pointing_apply_t(const int32_t *__res
 // and the merge phase of the current tile, so their DRAM latency overlaps the shuffles and REDs.
 template <int POL>
 __global__ void __launch_bounds__(BLOCK) k_amatvec_white(const int32_t *__restrict__ pix, const double *__restrict__ cs,
-                                                         const double *__restrict__ sn, int64_t nt, BlockW bw,
+                                                         const double *__restrict__ sn, int64_t nt, BlockW bw, TileOrder ord,
                                                          const double *__restrict__ x, double *__restrict__ y) {
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
@@ -304,7 +339,10 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_white(const int32_t *__restri
     rs.single = true;
 #pragma unroll
     for (int k = 0; k < POL; ++k) rs.acc[k] = rs.head[k] = 0.0;
-    for (int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
+    const int64_t nv = ord.count();
+    for (int64_t vt = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); vt < nv; vt += nwarps) {
+        const int64_t tile = ord.tile(vt);
+        if (tile >= ntiles) continue;           // the last stream may be short
         const int64_t t0 = tile * TILE + (int64_t)lane * K;
         int p[K];
         double c[K], s[K];
@@ -460,13 +498,14 @@ struct SegInfo {
 
 template <int POL>
 __global__ void __launch_bounds__(BLOCK) k_amatvec_filter_mu(const int32_t *__restrict__ pix, const double *__restrict__ cs,
-                                                             const double *__restrict__ sn, int64_t nt, SegInfo sg,
+                                                             const double *__restrict__ sn, int64_t nt, SegInfo sg, TileOrder ord,
                                                              const double *__restrict__ x, double *__restrict__ y) {
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
     const int64_t ntiles = (nt + TILE - 1) / TILE;
-    int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
-    if (tile >= ntiles) return;
+    int64_t tile;
+    int64_t v = ord.next((int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5), nwarps, ntiles, tile);
+    if (tile < 0) return;
     int p[K];
     double c[K], s[K];
     int flag, k0;
@@ -479,7 +518,7 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter_mu(const int32_t *__re
         k0 = __ldg(sg.tile_seg + tile);
         m0 = flag == 1 ? __ldg(sg.mu + k0) : 0.0;
     }
-    for (; tile < ntiles; tile += nwarps) {
+    while (tile >= 0) {
         const int64_t t0 = tile * TILE + (int64_t)lane * K;
         double mu[K];
         if (flag == 1) {                       // the whole tile lies inside subscan k0 (the common case)
@@ -526,8 +565,9 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter_mu(const int32_t *__re
                 else { o[0] = v[j]; o[1] = v[j] * c[j]; o[2] = v[j] * s[j]; }
             }, rs);
         }
-        const int64_t nxt = tile + nwarps;
-        if (nxt < ntiles) {   // warp-uniform: next tile's TOD loads and subscan info overlap the merge
+        int64_t nxt;
+        v = ord.next(v + nwarps, nwarps, ntiles, nxt);
+        if (nxt >= 0) {       // warp-uniform: next tile's TOD loads and subscan info overlap the merge
             const int64_t t1 = nxt * TILE + (int64_t)lane * K;
             load_pix(pix, t1, nt, p);
             if (POL > 1) { load_f64(cs, t1, nt, c); load_f64(sn, t1, nt, s); }
@@ -536,6 +576,7 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter_mu(const int32_t *__re
             m0 = flag == 1 ? __ldg(sg.mu + k0) : 0.0;
         }
         run_merge<POL, POL>(y, rs);
+        tile = nxt;
     }
 }
 
@@ -562,7 +603,7 @@ __device__ __forceinline__ double poly_eval(const double (&cf)[NK], double xt) {
 
 template <int POL, int NK>
 __global__ void __launch_bounds__(BLOCK) k_amatvec_filter_poly_mu(const int32_t *__restrict__ pix, const double *__restrict__ cs,
-                                                                  const double *__restrict__ sn, int64_t nt, SegPoly sg,
+                                                                  const double *__restrict__ sn, int64_t nt, SegPoly sg, TileOrder ord,
                                                                   const double *__restrict__ x, double *__restrict__ y) {
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
@@ -572,7 +613,10 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter_poly_mu(const int32_t 
     rs.single = true;
 #pragma unroll
     for (int k = 0; k < POL; ++k) rs.acc[k] = rs.head[k] = 0.0;
-    for (int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
+    const int64_t nv = ord.count();
+    for (int64_t vt = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); vt < nv; vt += nwarps) {
+        const int64_t tile = ord.tile(vt);
+        if (tile >= ntiles) continue;          // the last stream may be short
         const int64_t t0 = tile * TILE + (int64_t)lane * K;
         int p[K];
         double c[K], s[K];
@@ -1145,7 +1189,7 @@ static int check_blocks(const double *wblk, int64_t nblocks, int64_t blocksize, 
 
 extern "C" int cm2_amatvec_white(const int32_t *pix, const double *c, const double *s, int64_t nt, int pol,
                                  const double *wblk, int64_t nblocks, int64_t blocksize, const int64_t *blk_start,
-                                 const double *x, double *y, int64_t npix, cm2_stream_t stream) {
+                                 const double *x, double *y, int64_t npix, int64_t nstreams, cm2_stream_t stream) {
     int rc = check_tod(pix, c, s, nt, pol);
     if (rc) return rc;
     rc = check_blocks(wblk, nblocks, blocksize, blk_start);
@@ -1155,9 +1199,10 @@ extern "C" int cm2_amatvec_white(const int32_t *pix, const double *c, const doub
     if (npix > 0) CM2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)npix * pol, st));
     if (nt == 0 || npix == 0) return CM2_OK;
     const BlockW bw = make_blockw(wblk, nblocks, blocksize, blk_start);
-    if (pol == 1) k_amatvec_white<1><<<tod_grid(k_amatvec_white<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, x, y);
-    else if (pol == 2) k_amatvec_white<2><<<tod_grid(k_amatvec_white<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, x, y);
-    else k_amatvec_white<3><<<tod_grid(k_amatvec_white<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, x, y);
+    const TileOrder ord = make_order(nt, nstreams);
+    if (pol == 1) k_amatvec_white<1><<<tod_grid(k_amatvec_white<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, ord, x, y);
+    else if (pol == 2) k_amatvec_white<2><<<tod_grid(k_amatvec_white<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, ord, x, y);
+    else k_amatvec_white<3><<<tod_grid(k_amatvec_white<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, ord, x, y);
     CM2_LAUNCHED();
     return CM2_OK;
 }
@@ -1265,7 +1310,7 @@ extern "C" int cm2_amatvec_filter(const int32_t *pix, const double *c, const dou
 extern "C" int cm2_amatvec_filter_mu(const int32_t *pix, const double *c, const double *s, int64_t nt, int pol,
                                      const int64_t *seg_start, const int64_t *seg_end, const double *seg_mu,
                                      const int32_t *tile_seg, const uint8_t *tile_flag, int64_t nseg, const double *x,
-                                     double *y, int64_t npix, cm2_stream_t stream) {
+                                     double *y, int64_t npix, int64_t nstreams, cm2_stream_t stream) {
     int rc = check_tod(pix, c, s, nt, pol);
     if (rc) return rc;
     CM2_REQUIRE(npix >= 0 && nseg >= 0, "negative size");
@@ -1273,9 +1318,10 @@ extern "C" int cm2_amatvec_filter_mu(const int32_t *pix, const double *c, const 
     if (npix > 0) CM2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)npix * pol, st));
     if (nt == 0 || npix == 0 || nseg == 0) return CM2_OK;
     SegInfo sg{seg_start, seg_end, seg_mu, tile_seg, tile_flag, nseg};
-    if (pol == 1) k_amatvec_filter_mu<1><<<tod_grid(k_amatvec_filter_mu<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, y);
-    else if (pol == 2) k_amatvec_filter_mu<2><<<tod_grid(k_amatvec_filter_mu<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, y);
-    else k_amatvec_filter_mu<3><<<tod_grid(k_amatvec_filter_mu<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, y);
+    const TileOrder ord = make_order(nt, nstreams);
+    if (pol == 1) k_amatvec_filter_mu<1><<<tod_grid(k_amatvec_filter_mu<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, ord, x, y);
+    else if (pol == 2) k_amatvec_filter_mu<2><<<tod_grid(k_amatvec_filter_mu<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, ord, x, y);
+    else k_amatvec_filter_mu<3><<<tod_grid(k_amatvec_filter_mu<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, ord, x, y);
     CM2_LAUNCHED();
     return CM2_OK;
 }
@@ -1304,8 +1350,8 @@ extern "C" int cm2_pointing_filter_mu(const int32_t *pix, const double *c, const
 
 template <int POL>
 static int dispatch_amatvec_filter_poly_mu(int nk, const int32_t *pix, const double *c, const double *s, int64_t nt,
-                                           const SegPoly &sg, const double *x, double *y, cudaStream_t st) {
-#define CM2_POLY_MU(NK) k_amatvec_filter_poly_mu<POL, NK><<<tod_grid(k_amatvec_filter_poly_mu<POL, NK>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, y)
+                                           const SegPoly &sg, const TileOrder &ord, const double *x, double *y, cudaStream_t st) {
+#define CM2_POLY_MU(NK) k_amatvec_filter_poly_mu<POL, NK><<<tod_grid(k_amatvec_filter_poly_mu<POL, NK>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, ord, x, y)
     switch (nk) {
         case 2: CM2_POLY_MU(2); break;
         case 3: CM2_POLY_MU(3); break;
@@ -1322,7 +1368,8 @@ static int dispatch_amatvec_filter_poly_mu(int nk, const int32_t *pix, const dou
 extern "C" int cm2_amatvec_filter_poly_mu(const int32_t *pix, const double *c, const double *s, int64_t nt, int pol,
                                           const int64_t *seg_start, const int64_t *seg_end, const double *seg_coef,
                                           const int32_t *tile_seg, const uint8_t *tile_flag, int64_t nseg, int poly_order,
-                                          const double *x, double *y, int64_t npix, int accumulate, cm2_stream_t stream) {
+                                          const double *x, double *y, int64_t npix, int accumulate, int64_t nstreams,
+                                          cm2_stream_t stream) {
     int rc = check_tod(pix, c, s, nt, pol);
     if (rc) return rc;
     CM2_REQUIRE(npix >= 0 && nseg >= 0, "negative size");
@@ -1333,9 +1380,10 @@ extern "C" int cm2_amatvec_filter_poly_mu(const int32_t *pix, const double *c, c
     if (nt == 0 || npix == 0 || nseg == 0) return CM2_OK;
     SegPoly sg{seg_start, seg_end, seg_coef, tile_seg, tile_flag, nseg};
     const int nk = poly_order + 1;
-    if (pol == 1) return dispatch_amatvec_filter_poly_mu<1>(nk, pix, c, s, nt, sg, x, y, st);
-    if (pol == 2) return dispatch_amatvec_filter_poly_mu<2>(nk, pix, c, s, nt, sg, x, y, st);
-    return dispatch_amatvec_filter_poly_mu<3>(nk, pix, c, s, nt, sg, x, y, st);
+    const TileOrder ord = make_order(nt, nstreams);
+    if (pol == 1) return dispatch_amatvec_filter_poly_mu<1>(nk, pix, c, s, nt, sg, ord, x, y, st);
+    if (pol == 2) return dispatch_amatvec_filter_poly_mu<2>(nk, pix, c, s, nt, sg, ord, x, y, st);
+    return dispatch_amatvec_filter_poly_mu<3>(nk, pix, c, s, nt, sg, ord, x, y, st);
 }
 
 /* fused P^T F_K P, Legendre subscan filter of order 1..4 */

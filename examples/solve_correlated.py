@@ -14,23 +14,18 @@ ProcessTimeSamples, src/test_BD_precond_onto_real_data.py:78-80).
 
 The pointing is generated on the device (inputs only).  Under torchrun the TOD is sharded by detector:
 noise blocks and subscans never straddle detectors, so the time domain needs no exchange and every
-A apply ends in one sum of the map-domain vector (cosmomap2_b200.distributed.AllReduceLO).
-The A apply runs as: subscan means from the run table + one gather pass (F P fused), the Toeplitz
-kernel, the subscan filter, the scatter -- see `plan` in the output.
+A apply ends in one sum of the map-domain vector.  The work itself lives in cosmomap2_b200/workloads.py
+(bench.py runs the same function for its `secondary` block); see `plan` in the output for the kernels
+the A apply runs as.
 """
 import argparse
 import json
 import os
 import sys
-import time
 
-import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-
-from solve_two_level import make_scan  # noqa: E402
 
 
 def main():
@@ -53,84 +48,12 @@ def main():
     torch.cuda.set_device(lr)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    import cosmomap2_b200 as cm
-    from cosmomap2_b200 import distributed, synthetic
-
-    pol = 3
-    nt, ns, pix, phi, sub_len, sub_start, g = make_scan(int(args.nt), args.nside, args.nx, args.ny, args.ndet, 8.0,
-                                                        seed=rank)
-    npix_full = 12 * args.nside ** 2
-    bands = synthetic.toeplitz_bands(args.ndet, args.nband, seed=100 + rank)
-    N = cm.BlockLO(ns, bands, offdiag=True)
-    Nw = cm.BlockLO(ns, [a[0] for a in bands])             # the diagonal of N^-1: the weights of M_BD
-    pts = cm.ProcessTimeSamples(pix, npix_full, obspix=np.arange(npix_full), pol=pol, phi=phi, w=Nw.diag,
-                                comm=(True if world > 1 else None))
-    del phi
-    npix = pts.get_new_pixel[0]
-    n = pol * npix
-    P = cm.SparseLO(npix, nt, pts._pix_dev, pol=pol, angle_processed=pts)
-    F = cm.FilterLO(nt, [sub_len, sub_start], ns, args.ndet, pts._pix_dev)
-    Mbd = cm.BlockDiagonalPreconditionerLO(pts, npix, pol=pol)
-    A_local = P.T * F * N * F * P
-    A = distributed.AllReduceLO(A_local) if world > 1 else A_local
-    sky = torch.randn(n, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(99))
-    d = P._apply(sky)
-    d += 0.5 * torch.randn(nt, dtype=torch.float64, device="cuda", generator=g)
-    b = P.T._apply(F._apply(N._apply(F._apply(d))))
-    if world > 1:
-        distributed.all_reduce_sum_(b)
-    del d
-    torch.cuda.synchronize()
-
-    res = []
-    t0 = time.perf_counter()
-    x, info = cm.cg(A, b, M=Mbd, rtol=args.rtol, maxiter=args.maxiter, residuals=res)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    its = len(res) - 1 if info == 0 else len(res)
-    rel = float(torch.linalg.norm(b - A._apply(x)) / torch.linalg.norm(b))
-    # symmetry of the composed operator (F and N symmetric): <u, A v> = <v, A u>
-    u = torch.randn(n, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7))
-    v = torch.randn(n, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(8))
-    Av, Au = A._apply(v), A._apply(u)
-    uav, vau = float(torch.dot(u, Av)), float(torch.dot(v, Au))
-    sym_scale = float(torch.linalg.norm(u) * torch.linalg.norm(Av))
-
-    # device time of the A apply alone (CUDA events; the TOD streams are far larger than L2)
-    for _ in range(3):
-        A._apply(x)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.time_iters):
-        A._apply(x)
-    e1.record()
-    torch.cuda.synchronize()
-    a_ms = torch.tensor([e0.elapsed_time(e1) / args.time_iters], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(a_ms, op=dist.ReduceOp.MAX)
-    a_ms = float(a_ms.item())
-
-    out = {"config": "configs[2]: Toeplitz noise (%d coefficients) + subscan offset filter, M_BD PCG" % args.nband,
-           "world": world, "nt_total": nt * world, "nt_per_gpu": nt, "ndet_per_gpu": args.ndet, "npix": int(npix),
-           "nside": args.nside, "nseg_per_gpu": F.nseg, "nband": args.nband,
-           "plan": [type(f).__name__ for f in A_local.planned()],
-           "cg": dict(info=int(info), iterations=its, seconds=dt, ms_per_iteration=1e3 * dt / max(its, 1),
-                      true_relres=rel, rtol=args.rtol,
-                      residual_first_last=[float(res[0]), float(res[-1])] if len(res) else None),
-           "samples_per_s_per_pcg_iter": nt * world / (dt / max(its, 1)),
-           "A_apply_ms": a_ms, "A_apply_samples_per_s": nt * world / (a_ms * 1e-3),
-           "symmetry": {"u_Av": uav, "v_Au": vau, "rel": abs(uav - vau) / max(abs(uav), 1e-300),
-                        "rel_to_norms": abs(uav - vau) / max(sym_scale, 1e-300),
-                        "u_minus_v_norm": float(torch.linalg.norm(u - v))},
-           "hbm_GB": torch.cuda.max_memory_allocated() / 1e9}
+    from cosmomap2_b200 import workloads
+    out = workloads.correlated(nt=args.nt, ndet=args.ndet, nband=args.nband, nside=args.nside, nx=args.nx, ny=args.ny,
+                               rtol=args.rtol, maxiter=args.maxiter, time_iters=args.time_iters)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
-        if hasattr(A, "close"):
-            A.close()
         dist.barrier()
         dist.destroy_process_group()
 

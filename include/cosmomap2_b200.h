@@ -137,11 +137,17 @@ int cm2_filter_offset_apply(const int32_t *pix, const int64_t *seg_start, const 
                             cm2_stream_t stream);
 
 /* ---- fused A-matvecs (no TOD temporary) ---------------------------------------------------- */
-/* y = P^T diag(w) P x   (the composition P.T*N*P at tests/test_toeplitz_vector_multiplication.py:28) */
+/* y = P^T diag(w) P x   (the composition P.T*N*P at tests/test_toeplitz_vector_multiplication.py:28)
+ * nstreams (here and in the other single-pass A-matvecs): order in which the TOD is walked.  <= 1: time
+ * order.  S > 1: the TOD is treated as S equally long timelines (detectors; the reference's layout is
+ * detector-major, interfaces/linearoperators.py:134-140) that are walked round-robin, tile by tile, so that
+ * all detectors are processed at the same scan time and the map rows they share stay in L2 -- for maps larger
+ * than L2 (nside >= 1024 patches), where time order makes every detector timeline a pass over the whole map.
+ * The result is the same sum in a different order of the atomic adds. */
 int cm2_amatvec_white(const int32_t *pix, const double *cos2phi, const double *sin2phi,
                       int64_t nt, int pol, const double *wblk, int64_t nblocks,
                       int64_t blocksize, const int64_t *blk_start, const double *x, double *y,
-                      int64_t npix, cm2_stream_t stream);
+                      int64_t npix, int64_t nstreams, cm2_stream_t stream);
 /* y = P^T F P x with the offset filter (src/test_M2_precond_onto_real_data.py:86) */
 int cm2_amatvec_filter(const int32_t *pix, const double *cos2phi, const double *sin2phi,
                        int64_t nt, int pol, const int64_t *seg_start, const int64_t *seg_end,
@@ -169,7 +175,7 @@ int cm2_filter_seg_mean(const int32_t *run_pix, const double *run_mom, const int
 int cm2_amatvec_filter_mu(const int32_t *pix, const double *cos2phi, const double *sin2phi,
                           int64_t nt, int pol, const int64_t *seg_start, const int64_t *seg_end,
                           const double *seg_mu, const int32_t *tile_seg, const uint8_t *tile_flag,
-                          int64_t nseg, const double *x, double *y, int64_t npix,
+                          int64_t nseg, const double *x, double *y, int64_t npix, int64_t nstreams,
                           cm2_stream_t stream);
 
 /* Single-TOD-pass P^T F_K P x for the Legendre filter, poly_order 1..4 (FilterLO.polyfilter
@@ -195,7 +201,7 @@ int cm2_amatvec_filter_poly_mu(const int32_t *pix, const double *cos2phi, const 
                                int64_t nt, int pol, const int64_t *seg_start, const int64_t *seg_end,
                                const double *seg_coef, const int32_t *tile_seg, const uint8_t *tile_flag,
                                int64_t nseg, int poly_order, const double *x, double *y, int64_t npix,
-                               int accumulate, cm2_stream_t stream);
+                               int accumulate, int64_t nstreams, cm2_stream_t stream);
 
 /* d = F P x for the offset filter in one TOD pass (the first two factors of a chain such as
  * P.T*F*N*F*P): d_t = (P x)_t - mu_seg(t) inside subscans -- flagged samples included, as

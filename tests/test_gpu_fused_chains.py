@@ -242,3 +242,40 @@ def test_poly_run_table_path(cm, pol, order):
             lo.FILTER_POLY_RUN_TABLE = old
     gc.close(res["subscan"], res["oracle"], what="per-subscan kernel")
     gc.close(res["table"], res["oracle"], what="run-table path")
+
+
+@pytest.mark.parametrize("pol", [1, 3])
+@pytest.mark.parametrize("kind", ["white", "offset", "legendre"])
+def test_stream_interleaved_tile_order_equals_time_order(cm, pol, kind):
+    """The single-pass A-matvecs walk the TOD detector-interleaved when the map is larger than L2
+    (``nstreams`` in include/cosmomap2_b200.h): the same sum in another order of the atomic adds.  Forced here
+    on a small scan -- detector timelines that are not a multiple of the 256-sample tile, a last stream that is
+    short -- against the time-ordered kernel and the oracle."""
+    import oracle
+    from cosmomap2_b200 import linearoperators as lo
+    sc = _raster(nt=7 * 43211, ndet=7, seed=5, flag_turnarounds=True)
+    sc.pix[np.random.default_rng(3).random(sc.nt) < 0.01] = -1
+    res = {}
+    for label, impl in (("oracle", oracle), ("time", cm), ("streams", cm)):
+        pix = sc.pix.astype(np.int64)
+        pts = impl.ProcessTimeSamples(pix, sc.npix_full, pol=pol, phi=sc.phi)
+        npix = pts.get_new_pixel[0]
+        P = impl.SparseLO(npix, sc.nt, pix, pol=pol, angle_processed=pts)
+        if kind == "white":
+            A = P.T * impl.BlockLO(sc.ns, sc.weights) * P
+        else:
+            F = impl.FilterLO(sc.nt, [sc.sub_len, sc.sub_start], sc.ns, sc.ndet, pix, poly_order=0 if kind == "offset" else 2)
+            A = P.T * F * P
+        x = np.random.default_rng(4).standard_normal(pol * npix)
+        old = lo.TOD_INTERLEAVE_MIN_MAP_BYTES
+        lo.TOD_INTERLEAVE_MIN_MAP_BYTES = 0 if label == "streams" else 1e30
+        try:
+            res[label] = A * x
+            if impl is cm:
+                fused = [f for f in A.planned() if isinstance(f, (lo._FusedWhiteA, lo._FusedFilterA, lo._FusedPolyFilterA))]
+                assert len(fused) == 1
+                assert lo._tod_streams(P, sc.ns) == (sc.ndet if label == "streams" else 1)
+        finally:
+            lo.TOD_INTERLEAVE_MIN_MAP_BYTES = old
+    gc.close(res["streams"], res["time"], rtol=1e-13, what="interleaved vs time order")
+    gc.close(res["streams"], res["oracle"], rtol=1e-10, what="interleaved vs oracle")

@@ -20,5 +20,5 @@ t1 = timeit(lambda: dv.call("cm2_filter_seg_mean", dv.ptr(rt["run_pix"]), dv.ptr
                             dv.ptr(rt["seg_nruns"]), F.nseg, 3, dv.ptr(x), dv.ptr(rt["mu"]), st()))
 t2 = timeit(lambda: dv.call("cm2_amatvec_filter_mu", dv.ptr(P._pix_dev), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.nrows, 3,
                             dv.ptr(F._seg_start), dv.ptr(F._seg_end), dv.ptr(rt["mu"]), dv.ptr(rt["tile_seg"]), dv.ptr(rt["tile_flag"]), F.nseg,
-                            dv.ptr(x), dv.ptr(y), P.ncols, st()))
+                            dv.ptr(x), dv.ptr(y), P.ncols, 1, st()))
 print(json.dumps({"nseg": F.nseg, "nruns": rt["nruns"], "seg_mean_ms": t1, "amatvec_filter_mu_ms": t2}))

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "examples"))
 import cosmomap2_b200 as cm  # noqa: E402
 from cosmomap2_b200 import synthetic, linearoperators as lo  # noqa: E402
-from solve_two_level import make_scan  # noqa: E402
+from cosmomap2_b200.workloads import make_scan  # noqa: E402
 
 
 def timeit(fn, reps=10, warm=3):
