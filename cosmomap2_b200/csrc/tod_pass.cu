@@ -363,6 +363,105 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_white(const int32_t *__restri
     run_merge<POL, POL>(y, rs);
 }
 
+// Variant of k_amatvec_white with the scatter STAGED through shared memory: when the pixels of a warp tile span
+// fewer than `wpix` pixels (a raster sweep along a pixel row: 256 / samples-per-pixel consecutive pixels), the
+// lanes add their runs into a per-warp shared-memory window (fp64 CAS adds; collisions only where a run crosses a
+// lane boundary or the scan turns around inside the tile) and the warp then flushes the window with REDs to
+// CONSECUTIVE doubles: a warp-wide RED covers 8 sectors of y instead of up to 32, and a pixel crossed in fewer
+// than 8 samples costs POL doubles of one coalesced RED instead of POL REDs of its own.  Tiles that span more
+// (row changes, tilted or random pointing) take the register path of k_amatvec_white.  The window is zero
+// outside [sink, flush]: the flush clears what it reads.
+template <int POL>
+__device__ __forceinline__ void stage_flush(double *__restrict__ sm, double *__restrict__ y, int64_t base, int len) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    for (int i = lane; i < len; i += 32) {
+        const double v = sm[i];
+        if (v != 0.0) {
+            sm[i] = 0.0;
+            atomicAdd(y + base + i, v);
+        }
+    }
+    __syncwarp();
+}
+
+template <int POL>
+__global__ void __launch_bounds__(BLOCK) k_amatvec_white_staged(const int32_t *__restrict__ pix, const double *__restrict__ cs,
+                                                                const double *__restrict__ sn, int64_t nt, BlockW bw, TileOrder ord,
+                                                                const double *__restrict__ x, double *__restrict__ y, int wpix) {
+    extern __shared__ double stage_sm[];
+    const int lane = threadIdx.x & 31;
+    double *sm = stage_sm + (size_t)(threadIdx.x >> 5) * POL * wpix;
+    for (int i = lane; i < POL * wpix; i += 32) sm[i] = 0.0;
+    __syncwarp();
+    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
+    const int64_t ntiles = (nt + TILE - 1) / TILE;
+    const int64_t nv = ord.count();
+    int64_t base_prev = 0;
+    int len_prev = 0;
+    for (int64_t vt = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); vt < nv; vt += nwarps) {
+        const int64_t tile = ord.tile(vt);
+        if (tile >= ntiles) continue;
+        const int64_t t0 = tile * TILE + (int64_t)lane * K;
+        int p[K];
+        double c[K], s[K];
+        load_pix(pix, t0, nt, p);
+        if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
+        if (len_prev) stage_flush<POL>(sm, y, base_prev, len_prev);   // previous tile, after this tile's loads were issued
+        len_prev = 0;
+        double w[K], xv[K][POL], v[K];
+        gather_x<POL>(x, p, xv);
+        chunk_weights(bw, t0 < nt ? t0 : nt - 1, nt, w);
+#pragma unroll
+        for (int j = 0; j < K; ++j) v[j] = w[j] * project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0);
+        int lo = INT32_MAX, hi = INT32_MIN;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (p[j] >= 0) { lo = min(lo, p[j]); hi = max(hi, p[j]); }
+        }
+        lo = __reduce_min_sync(FULL, lo);
+        hi = __reduce_max_sync(FULL, hi);
+        if (hi < lo) continue;                                    // every sample of the tile is flagged
+        auto contrib = [&](int j, double (&o)[POL]) {
+            if constexpr (POL == 1) { o[0] = v[j]; }
+            else if constexpr (POL == 2) { o[0] = v[j] * c[j]; o[1] = v[j] * s[j]; }
+            else { o[0] = v[j]; o[1] = v[j] * c[j]; o[2] = v[j] * s[j]; }
+        };
+        if ((int64_t)hi - lo < wpix) {                            // warp-uniform
+            double acc[POL];
+            int cur = p[0];
+            contrib(0, acc);
+#pragma unroll
+            for (int j = 1; j <= K; ++j) {
+                double o[POL];
+                if (j < K) contrib(j, o);
+                if (j == K || p[j] != cur) {
+                    if (cur >= 0) {
+                        double *dst = sm + (cur - lo) * POL;
+#pragma unroll
+                        for (int k = 0; k < POL; ++k) atomicAdd(dst + k, acc[k]);
+                    }
+                    if (j < K) {
+                        cur = p[j];
+#pragma unroll
+                        for (int k = 0; k < POL; ++k) acc[k] = o[k];
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < POL; ++k) acc[k] += o[k];
+                }
+            }
+            base_prev = (int64_t)POL * lo;
+            len_prev = POL * (hi - lo + 1);
+        } else {
+            RunState<POL> rs;
+            run_compress<POL, POL>(y, p, contrib, rs);
+            run_merge<POL, POL>(y, rs);
+        }
+    }
+    if (len_prev) stage_flush<POL>(sm, y, base_prev, len_prev);
+}
+
 // Fused y = P^T T P x for a short symmetric band (T = the banded Toeplitz blocks of
 // BlockLO(offdiag=True), linearoperators.py:582-595, 672-674; the composition P.T*N*P of
 // tests/test_2level_preconditioner.py:16-29), NLAG = nband-1 <= 8 lags: one pass over the TOD, no
@@ -1187,6 +1286,16 @@ static int check_blocks(const double *wblk, int64_t nblocks, int64_t blocksize, 
     return CM2_OK;
 }
 
+static int g_white_stage_wpix = 0;
+
+/* experimental: > 0 selects the shared-memory-staged scatter of the fused white A-matvec with a window of that
+ * many pixels per warp tile (tools/pattern_probe.py) */
+extern "C" int cm2_amatvec_white_set_stage(int wpix) {
+    CM2_REQUIRE(wpix >= 0 && wpix <= 1024, "stage window must be 0..1024 pixels");
+    g_white_stage_wpix = wpix;
+    return CM2_OK;
+}
+
 extern "C" int cm2_amatvec_white(const int32_t *pix, const double *c, const double *s, int64_t nt, int pol,
                                  const double *wblk, int64_t nblocks, int64_t blocksize, const int64_t *blk_start,
                                  const double *x, double *y, int64_t npix, int64_t nstreams, cm2_stream_t stream) {
@@ -1200,6 +1309,18 @@ extern "C" int cm2_amatvec_white(const int32_t *pix, const double *c, const doub
     if (nt == 0 || npix == 0) return CM2_OK;
     const BlockW bw = make_blockw(wblk, nblocks, blocksize, blk_start);
     const TileOrder ord = make_order(nt, nstreams);
+    if (g_white_stage_wpix > 0) {
+        const int wpix = g_white_stage_wpix;
+        const size_t smem = sizeof(double) * (size_t)(BLOCK / 32) * pol * wpix;
+#define CM2_STAGED(POL) do { \
+        CM2_CUDA(cudaFuncSetAttribute(k_amatvec_white_staged<POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        int64_t ntiles_ = (nt + TILE - 1) / TILE, blocks_ = (ntiles_ + (BLOCK / 32) - 1) / (BLOCK / 32); \
+        k_amatvec_white_staged<POL><<<persistent_grid(k_amatvec_white_staged<POL>, BLOCK, smem, blocks_), BLOCK, smem, st>>>(pix, c, s, nt, bw, ord, x, y, wpix); } while (0)
+        if (pol == 1) CM2_STAGED(1); else if (pol == 2) CM2_STAGED(2); else CM2_STAGED(3);
+#undef CM2_STAGED
+        CM2_LAUNCHED();
+        return CM2_OK;
+    }
     if (pol == 1) k_amatvec_white<1><<<tod_grid(k_amatvec_white<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, ord, x, y);
     else if (pol == 2) k_amatvec_white<2><<<tod_grid(k_amatvec_white<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, ord, x, y);
     else k_amatvec_white<3><<<tod_grid(k_amatvec_white<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, ord, x, y);

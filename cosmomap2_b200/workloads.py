@@ -54,12 +54,13 @@ def time_device(fn, iters, warmup=3):
     return _max_over_ranks(e0.elapsed_time(e1) / iters)
 
 
-def make_scan(nt, nside, nx, ny, ndet, spp, seed, turnaround=0.05):
+def make_scan(nt, nside, nx, ny, ndet, spp, seed, turnaround=0.05, tilt_deg=0.0):
     """Raster scan of ``ndet`` detectors over an nx x ny patch of a RING-ordered HEALPix map, generated on the
     device: constant-speed sweeps (``spp`` samples per pixel crossing) with flagged turnarounds (-1), a slow
     cross-scan drift over the detector timeline, per-detector focal-plane offsets, the reference's HWP ramp
     (utilities/utilities_functions.py:99-107) plus encoder jitter.  Returns
-    (nt, ns, pix int32, phi fp64, sub_len, sub_start, generator)."""
+    (nt, ns, pix int32, phi fp64, sub_len, sub_start, generator).  ``tilt_deg`` turns the sweep direction against
+    the pixel rows (iso-latitude rings) by that angle: the sweep then changes row every 1 / tan(tilt) pixels."""
     dev = torch.device("cuda")
     ns = nt // ndet
     nt = ns * ndet
@@ -79,7 +80,10 @@ def make_scan(nt, nside, nx, ny, ndet, spp, seed, turnaround=0.05):
         dx = (torch.rand(1, generator=g, device=dev).item() - 0.5) * 0.04 * nx
         dy = (torch.rand(1, generator=g, device=dev).item() - 0.5) * 0.1 * ny
         ix = torch.remainder(torch.floor(xpos + dx).to(torch.int64), nx)
-        iy = torch.remainder(torch.floor(t.to(torch.float64) / ns * ny + dy).to(torch.int64), ny)
+        ypos = t.to(torch.float64) / ns * ny + dy
+        if tilt_deg:
+            ypos = ypos + float(np.tan(np.radians(tilt_deg))) * xpos
+        iy = torch.remainder(torch.floor(ypos).to(torch.int64), ny)
         p = ((2 * nside - ny // 2 + iy) * ring + (ring // 2 - nx // 2 + ix)).to(torch.int32)
         pix[b * ns:(b + 1) * ns] = torch.where(inside, p, torch.full_like(p, -1))
         phi[b * ns:(b + 1) * ns] = 3.0 * torch.rand(1, generator=g, device=dev).item() + \
@@ -90,6 +94,19 @@ def make_scan(nt, nside, nx, ny, ndet, spp, seed, turnaround=0.05):
     sub_start = np.arange(nsweeps, dtype=np.int64) * sweep + s0
     sub_len = np.full(nsweeps, s1 - s0, dtype=np.int64)
     return nt, ns, pix, phi, sub_len, sub_start, g
+
+
+def random_pointing(nt, nside, nx, ny, seed):
+    """The reference tests' pointing (utilities/utilities_functions.py:111-122 ``pairs_gen``: every sample an
+    independent uniform pixel), over the same nx x ny patch, on the device."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    ring = 4 * nside
+    ix = torch.randint(0, nx, (nt,), generator=g, device="cuda")
+    iy = torch.randint(0, ny, (nt,), generator=g, device="cuda")
+    pix = ((2 * nside - ny // 2 + iy) * ring + (ring // 2 - nx // 2 + ix)).to(torch.int32)
+    phi = 3.0 * torch.rand(nt, generator=g, device="cuda", dtype=torch.float64)
+    return pix, phi, g
 
 
 def _peak():
@@ -164,7 +181,12 @@ def correlated(nt=1.25e8, ndet=8, nband=4096, nside=512, nx=1000, ny=500, rtol=1
         distributed.all_reduce_sum_(b)
     torch.cuda.synchronize()
 
+    t0 = time.perf_counter()
+    A._apply(b)                        # first use: run table of F P, plan, work buffers (set-up, not the solve)
+    torch.cuda.synchronize()
+    first_apply = time.perf_counter() - t0
     x, res, cg = _solve(cm, A, b, Mbd, rtol, maxiter)
+    cg["first_A_apply_seconds_not_in_solve"] = first_apply
     cg["residual_first_last"] = [float(res[0]), float(res[-1])] if len(res) else None
     out = {"config": "configs[2]: Toeplitz noise (%d coefficients) + subscan offset filter, M_BD PCG" % nband,
            "world": world, "nt_total": nt * world, "nt_per_gpu": nt, "ndet_per_gpu": ndet, "npix": int(npix),
@@ -234,6 +256,10 @@ def two_level(nt=5e8, nside=1024, nx=1600, ny=800, ndet=64, r=32, coarse="scan",
                      % (poly_order, r, coarse),
            "world": world, "nt_total": nt * world, "nt_per_gpu": nt, "npix": int(npix), "nside": nside,
            "nseg_per_gpu": F.nseg, "poly_order": poly_order, "shard_m2": bool(shard_m2 and world > 1)}
+    t0 = time.perf_counter()
+    A._apply(b)                        # first use: run table of P^T F P, plan, work buffers (set-up, not the solve)
+    torch.cuda.synchronize()
+    out["first_A_apply_seconds_not_in_solve"] = time.perf_counter() - t0
     x_bd, _res, out["M_BD"] = _solve(cm, A, b, Mbd, rtol, maxiter)
 
     # ---- deflation space ---------------------------------------------------------------------------

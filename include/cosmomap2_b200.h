@@ -148,6 +148,10 @@ int cm2_amatvec_white(const int32_t *pix, const double *cos2phi, const double *s
                       int64_t nt, int pol, const double *wblk, int64_t nblocks,
                       int64_t blocksize, const int64_t *blk_start, const double *x, double *y,
                       int64_t npix, int64_t nstreams, cm2_stream_t stream);
+/* Scatter variant of cm2_amatvec_white: wpix > 0 stages the scatter of every warp tile whose pixels span fewer
+ * than wpix pixels through a shared-memory window and flushes it with coalesced REDs (pixels crossed in few
+ * samples: 1-4 samples per pixel crossing); 0 = run compression in registers + warp merge (the default). */
+int cm2_amatvec_white_set_stage(int wpix);
 /* y = P^T F P x with the offset filter (src/test_M2_precond_onto_real_data.py:86) */
 int cm2_amatvec_filter(const int32_t *pix, const double *cos2phi, const double *sin2phi,
                        int64_t nt, int pol, const int64_t *seg_start, const int64_t *seg_end,
