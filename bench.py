@@ -176,6 +176,49 @@ class ClockSampler(object):
                 "samples": len(sm)}
 
 
+def run_sensitivity(nt=50000000):
+    """Pointing-pattern sensitivity of the dominant kernel (the fused white A-matvec through the drop-in operators,
+    which choose the scatter from the pointing): samples per pixel crossing 1..32, a scan tilted 30 degrees against
+    the pixel rows, and the random pointing of the reference's tests (utilities/utilities_functions.py:111-122);
+    IQU nside 512, 64 white-noise blocks, device-generated, CUDA events, inputs far larger than L2."""
+    import gc
+    import torch
+    import cosmomap2_b200 as cm
+    from cosmomap2_b200 import workloads, linearoperators as lo
+    peak, _src = workloads._peak()
+    nside, nx, ny, ndet, pol = 512, 1000, 500, 64, 3
+    rows = []
+    cases = [("spp=%g" % s, dict(spp=s)) for s in (1.0, 2.0, 4.0, 8.0, 32.0)]
+    cases += [("tilt30 spp=8", dict(spp=8.0, tilt_deg=30.0)), ("random (pairs_gen)", None)]
+    for name, kw in cases:
+        if kw is None:
+            pix, phi, g = workloads.random_pointing(nt, nside, nx, ny, seed=0)
+            ntt, ns = nt, nt // ndet
+        else:
+            ntt, ns, pix, phi, _a, _b, g = workloads.make_scan(nt, nside, nx, ny, ndet, kw["spp"], seed=0, turnaround=0.0,
+                                                               tilt_deg=kw.get("tilt_deg", 0.0))
+        N = cm.BlockLO(ns, 0.5 + np.random.default_rng(0).random(ndet))
+        pts = cm.ProcessTimeSamples(pix, 12 * nside ** 2, obspix=np.arange(12 * nside ** 2), pol=pol, phi=phi, w=N.diag)
+        del phi
+        npix = pts.get_new_pixel[0]
+        P = cm.SparseLO(npix, ntt, pts._pix_dev, pol=pol, angle_processed=pts)
+        A = P.T * N * P
+        x = torch.randn(pol * npix, dtype=torch.float64, device="cuda", generator=g)
+        A._apply(x)
+        ms = workloads.time_device(lambda: A._apply(x), 20, warmup=3)
+        fused = [f for f in A.planned() if isinstance(f, lo._FusedWhiteA)]
+        alg = 20.0 * ntt + 48.0 * npix
+        rows.append({"pattern": name, "nt": int(ntt), "mean_run_length": P.mean_run_length(),
+                     "scatter": fused[0]._mode if fused else None, "kernel_ms": ms, "GBs": alg / ms / 1e6,
+                     "frac": alg / ms / 1e6 / peak})
+        del P, A, N, pts, pix, x
+        gc.collect()
+        torch.cuda.empty_cache()
+    return {"kernel": "cm2_amatvec_white through P.T*N*P (scatter chosen from SparseLO.mean_run_length)",
+            "algorithmic_bytes": "20 B/sample + 48 B/pixel for every pattern (the pixel-sorted path really reads 28 B/sample)",
+            "patterns": rows}
+
+
 def run_secondary(world, rank, out):
     """configs[2], configs[3] and configs[4] on this run's GPUs (cosmomap2_b200/workloads.py, the functions behind
     examples/solve_correlated.py and examples/solve_two_level.py): per-GPU shares of the named sizes, so that
@@ -469,6 +512,11 @@ def main():
         timer = threading.Timer(args.secondary_timeout, watchdog)
         timer.daemon = True
         timer.start()
+        if world == 1:
+            try:
+                secondary["sensitivity"] = run_sensitivity()
+            except Exception as e:                      # noqa: BLE001
+                secondary["sensitivity"] = {"error": "%s: %s" % (type(e).__name__, e)}
         run_secondary(world, rank, secondary)
         timer.cancel()
     if line is not None:

@@ -54,6 +54,8 @@ __device__ __forceinline__ int64_t block_of(const BlockW &bw, int64_t t) {
     return lo;
 }
 
+__device__ __forceinline__ void load_f64(const double *__restrict__ a, int64_t t0, int64_t nt, double (&c)[K]);
+
 // weights of the K samples starting at t0 (one lookup when the chunk sits inside one block)
 __device__ __forceinline__ void chunk_weights(const BlockW &bw, int64_t t0, int64_t nt, double (&w)[K]) {
     if (bw.w == nullptr) {
@@ -323,7 +325,8 @@ __global__ void __launch_bounds__(BLOCK) k_pointing_apply_t(const int32_t *__res
 
 // Fused y = P^T diag(w) P x.  The next tile's pix/cos/sin loads are issued between the compress
 // and the merge phase of the current tile, so their DRAM latency overlaps the shuffles and REDs.
-template <int POL>
+// WS = true: per-sample weights bw.w[t] (blocks of one sample: the pixel-sorted pointing copy), read as a stream.
+template <int POL, bool ILV, bool WS = false>
 __global__ void __launch_bounds__(BLOCK) k_amatvec_white(const int32_t *__restrict__ pix, const double *__restrict__ cs,
                                                          const double *__restrict__ sn, int64_t nt, BlockW bw, TileOrder ord,
                                                          const double *__restrict__ x, double *__restrict__ y) {
@@ -334,15 +337,19 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_white(const int32_t *__restri
     // issued, so DRAM latency overlaps the shuffles and REDs of the merge.  One load site per loop trip
     // (the loop-carried state is rs, 15 registers, not the 40 registers of p/c/s: the first version
     // carried p/c/s across the back edge and spent 79 register moves per tile on it).
+    // ILV = false: time order (the instantiation measured on configs[1]); true: detector-interleaved (TileOrder).
     RunState<POL> rs;
     rs.ph = rs.pt = -1;
     rs.single = true;
 #pragma unroll
     for (int k = 0; k < POL; ++k) rs.acc[k] = rs.head[k] = 0.0;
-    const int64_t nv = ord.count();
+    const int64_t nv = ILV ? ord.count() : ntiles;
     for (int64_t vt = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); vt < nv; vt += nwarps) {
-        const int64_t tile = ord.tile(vt);
-        if (tile >= ntiles) continue;           // the last stream may be short
+        int64_t tile = vt;
+        if constexpr (ILV) {
+            tile = ord.tile(vt);
+            if (tile >= ntiles) continue;       // the last stream may be short
+        }
         const int64_t t0 = tile * TILE + (int64_t)lane * K;
         int p[K];
         double c[K], s[K];
@@ -350,8 +357,9 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_white(const int32_t *__restri
         if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
         run_merge<POL, POL>(y, rs);             // previous tile (the empty state on the first trip emits nothing)
         double w[K], xv[K][POL], v[K];
+        if constexpr (WS) load_f64(bw.w, t0, nt, w);
         gather_x<POL>(x, p, xv);
-        chunk_weights(bw, t0 < nt ? t0 : nt - 1, nt, w);
+        if constexpr (!WS) chunk_weights(bw, t0 < nt ? t0 : nt - 1, nt, w);
 #pragma unroll
         for (int j = 0; j < K; ++j) v[j] = w[j] * project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0);
         run_compress<POL, POL>(y, p, [&](int j, double (&o)[POL]) {
@@ -1288,8 +1296,8 @@ static int check_blocks(const double *wblk, int64_t nblocks, int64_t blocksize, 
 
 static int g_white_stage_wpix = 0;
 
-/* experimental: > 0 selects the shared-memory-staged scatter of the fused white A-matvec with a window of that
- * many pixels per warp tile (tools/pattern_probe.py) */
+/* > 0 selects the shared-memory-staged scatter of the fused white A-matvec with a window of that many pixels
+ * per warp tile (pixels crossed in 2..6 samples; tools/pattern_probe.py) */
 extern "C" int cm2_amatvec_white_set_stage(int wpix) {
     CM2_REQUIRE(wpix >= 0 && wpix <= 1024, "stage window must be 0..1024 pixels");
     g_white_stage_wpix = wpix;
@@ -1321,9 +1329,18 @@ extern "C" int cm2_amatvec_white(const int32_t *pix, const double *c, const doub
         CM2_LAUNCHED();
         return CM2_OK;
     }
-    if (pol == 1) k_amatvec_white<1><<<tod_grid(k_amatvec_white<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, ord, x, y);
-    else if (pol == 2) k_amatvec_white<2><<<tod_grid(k_amatvec_white<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, ord, x, y);
-    else k_amatvec_white<3><<<tod_grid(k_amatvec_white<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, ord, x, y);
+#define CM2_WHITE(POL, ILV) k_amatvec_white<POL, ILV><<<tod_grid(k_amatvec_white<POL, ILV>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, ord, x, y)
+    if (wblk != nullptr && blk_start == nullptr && blocksize == 1) {      // one weight per sample, streamed
+        CM2_REQUIRE(nblocks >= nt && aligned(wblk, 32), "per-sample weights: nt values, 32-byte aligned");
+        if (pol == 1) k_amatvec_white<1, false, true><<<tod_grid(k_amatvec_white<1, false, true>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, ord, x, y);
+        else if (pol == 2) k_amatvec_white<2, false, true><<<tod_grid(k_amatvec_white<2, false, true>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, ord, x, y);
+        else k_amatvec_white<3, false, true><<<tod_grid(k_amatvec_white<3, false, true>, nt), BLOCK, 0, st>>>(pix, c, s, nt, bw, ord, x, y);
+    } else if (ord.S > 1) {
+        if (pol == 1) CM2_WHITE(1, true); else if (pol == 2) CM2_WHITE(2, true); else CM2_WHITE(3, true);
+    } else {
+        if (pol == 1) CM2_WHITE(1, false); else if (pol == 2) CM2_WHITE(2, false); else CM2_WHITE(3, false);
+    }
+#undef CM2_WHITE
     CM2_LAUNCHED();
     return CM2_OK;
 }

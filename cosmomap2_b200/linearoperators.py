@@ -106,6 +106,24 @@ class SparseLO(lp.LinearOperator):
                 dv.ptr(self._sin_dev), self.pol, dv.ptr(v), dv.ptr(y), self.ncols, _stream())
         return y
 
+    def mean_run_length(self):
+        """Mean number of consecutive samples on the same pixel (flagged samples excluded): the statistic the
+        fused A-matvecs use to choose their scatter (registers / staged through shared memory / pixel-sorted
+        pointing).  One chunked pass over the pixels at first use."""
+        if getattr(self, "_mean_run", None) is None:
+            pix, nt = self._pix_dev, self.nrows
+            starts = good = 0
+            step = 1 << 27
+            for a in range(0, nt, step):
+                b = min(a + step, nt)
+                cur = pix[a:b]
+                prev = pix[max(a - 1, 0):b - 1] if a > 0 else torch.cat([cur[:1] - 1, cur[:-1]])
+                ok = cur >= 0
+                starts += int(((cur != prev) & ok).sum().item())
+                good += int(ok.sum().item())
+            self._mean_run = good / max(starts, 1)
+        return self._mean_run
+
     def hits(self):
         out = torch.empty(max(self.ncols, 1), dtype=torch.int64, device=self._pix_dev.device)
         dv.call("cm2_hits_i64", dv.ptr(self._pix_dev), self.nrows, self.ncols, dv.ptr(out), _stream())
@@ -518,24 +536,89 @@ def _filter_timeline(F):
     return int(ns[0]) if ns.size and np.all(ns == ns[0]) else 0
 
 
+WHITE_STAGE_RUN_RANGE = (1.5, 6.0)   # mean run length for which the staged scatter wins (measured, tools/pattern_probe.py)
+WHITE_STAGE_WINDOW = 288             # pixels per warp tile
+WHITE_SORT_BELOW_RUN = 1.5           # below: the white A-matvec runs over a pixel-sorted copy of the pointing
+
+
 class _FusedWhiteA(lp.LinearOperator):
+    """``P^T diag(w) P`` in one pass over the TOD (cm2_amatvec_white).  The scatter is chosen from the pointing
+    (SparseLO.mean_run_length, at first use):
+
+    * runs of >= 6 samples (a raster scan at the usual sampling): run compression in registers + warp merge;
+    * runs of 1.5-6 samples: the same pass with the scatter staged through a shared-memory window and flushed
+      with coalesced REDs (cm2_amatvec_white_set_stage; 0.55 -> 0.46 ms per 1e8 samples at 4 samples per pixel);
+    * shorter (1 sample per pixel crossing, or the random pointing of the reference's tests,
+      utilities/utilities_functions.py:111-122): one atomic and one gather per sample and component would bound
+      the pass (2.2 ms per 1e8 samples); white noise has no time-domain structure, so the pass runs over a copy
+      of the pointing SORTED BY PIXEL with per-sample weights (28 B/sample, every pixel one run) instead.
+      Set-up: one stable sort; memory: a second copy of the pointing."""
+
     def __init__(self, P, N):
         self.P, self.N = P, N
         n = P.pol * P.ncols
         bs = N._blk.blocksize if N is not None else 0
         self._streams = _tod_streams(P, bs)
+        self._mode = None
+        self._sorted = None
         super(_FusedWhiteA, self).__init__(n, n, matvec=self._run, symmetric=True, device=True)
+
+    def _choose(self):
+        run = self.P.mean_run_length()
+        if run < WHITE_SORT_BELOW_RUN and self.P.nrows > 0:
+            self._mode = "sorted"
+            self._build_sorted()
+        elif WHITE_STAGE_RUN_RANGE[0] <= run < WHITE_STAGE_RUN_RANGE[1]:
+            self._mode = "staged"
+        else:
+            self._mode = "registers"
+
+    def _build_sorted(self):
+        P, N = self.P, self.N
+        order = torch.sort(P._pix_dev, stable=True).indices                  # one-off set-up (flagged first)
+        nflag = int((P._pix_dev < 0).sum().item())
+        order = order[nflag:]
+        nts = int(order.numel())
+        pad = (-nts) % 8                                                      # keep 32-byte alignment rules simple
+        pix = torch.full((nts + pad,), -1, dtype=torch.int32, device=order.device)
+        pix[:nts] = P._pix_dev[order]
+        cs = sn = None
+        if P.pol > 1:
+            cs, sn = dv.zeros_f64(nts + pad), dv.zeros_f64(nts + pad)
+            cs[:nts] = P._cos_dev[order]
+            sn[:nts] = P._sin_dev[order]
+        w = None
+        if N is not None:
+            starts = dv.to_dev(N._blk.starts, torch.int64)
+            blk = torch.bucketize(order, starts[1:], right=True)
+            w = dv.zeros_f64(nts + pad)
+            w[:nts] = N.weights_dev()[blk]
+        self._sorted = (pix, cs, sn, w, nts + pad)
 
     def _run(self, x):
         P = self.P
+        if self._mode is None:
+            self._choose()
         y = dv.out_f64(P.ncols * P.pol)
+        if self._mode == "sorted":
+            pix, cs, sn, w, nts = self._sorted
+            dv.call("cm2_amatvec_white", dv.ptr(pix), dv.ptr(cs), dv.ptr(sn), nts, P.pol,
+                    dv.ptr(w) if w is not None else None, nts if w is not None else 0, 1, None, dv.ptr(x), dv.ptr(y),
+                    P.ncols, 1, _stream())
+            return y
         if self.N is None:
             w, nb, bs, startp = None, 0, 0, None
         else:
             w = dv.ptr(self.N.weights_dev())
             nb, bs, startp = self.N._blk.args()
-        dv.call("cm2_amatvec_white", dv.ptr(P._pix_dev), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.nrows, P.pol,
-                w, nb, bs, startp, dv.ptr(x), dv.ptr(y), P.ncols, self._streams, _stream())
+        if self._mode == "staged":
+            dv.call("cm2_amatvec_white_set_stage", WHITE_STAGE_WINDOW)
+        try:
+            dv.call("cm2_amatvec_white", dv.ptr(P._pix_dev), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.nrows, P.pol,
+                    w, nb, bs, startp, dv.ptr(x), dv.ptr(y), P.ncols, self._streams, _stream())
+        finally:
+            if self._mode == "staged":
+                dv.call("cm2_amatvec_white_set_stage", 0)
         return y
 
 

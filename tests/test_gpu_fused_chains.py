@@ -279,3 +279,51 @@ def test_stream_interleaved_tile_order_equals_time_order(cm, pol, kind):
             lo.TOD_INTERLEAVE_MIN_MAP_BYTES = old
     gc.close(res["streams"], res["time"], rtol=1e-13, what="interleaved vs time order")
     gc.close(res["streams"], res["oracle"], rtol=1e-10, what="interleaved vs oracle")
+
+
+@pytest.mark.parametrize("pol", [1, 2, 3])
+@pytest.mark.parametrize("pattern", ["spp3", "spp1", "random"])
+def test_white_amatvec_scatter_modes(cm, pol, pattern):
+    """The fused white A-matvec chooses its scatter from the pointing (linearoperators._FusedWhiteA): staged
+    through shared memory for short runs, a pixel-sorted copy of the pointing for run-free pointing (the
+    reference tests' random pointing, utilities/utilities_functions.py:111-122).  Every mode against the oracle
+    and against the register path, with flagged samples and unequal block weights."""
+    import oracle
+    from cosmomap2_b200 import synthetic, linearoperators as lo
+    rng = np.random.default_rng(11)
+    if pattern == "random":
+        ndet, ns, nside = 5, 30011, 16
+        nt = ndet * ns
+        pix0 = rng.integers(0, 12 * nside * nside, nt).astype(np.int32)
+        phi = rng.uniform(0, np.pi, nt)
+        weights = rng.uniform(0.5, 1.5, ndet)
+        npix_full = 12 * nside * nside
+    else:
+        sc = synthetic.raster_scan(6 * 40003, nside=64, ndet=6, nx=90, ny=50,
+                                   samples_per_pixel=3.0 if pattern == "spp3" else 1.0, seed=7, flag_turnarounds=True)
+        pix0, phi, weights, ns, nt, npix_full = sc.pix.copy(), sc.phi, sc.weights, sc.ns, sc.nt, sc.npix_full
+    pix0[rng.random(nt) < 0.02] = -1
+    res, modes = {}, {}
+    for label, impl in (("oracle", oracle), ("auto", cm), ("registers", cm)):
+        pix = pix0.astype(np.int64)
+        N = impl.BlockLO(ns, weights)
+        pts = impl.ProcessTimeSamples(pix, npix_full, pol=pol, phi=phi, w=N.diag)
+        npix = pts.get_new_pixel[0]
+        P = impl.SparseLO(npix, nt, pix, pol=pol, angle_processed=pts)
+        A = P.T * N * P
+        x = np.random.default_rng(4).standard_normal(pol * npix)
+        old = lo.WHITE_SORT_BELOW_RUN, lo.WHITE_STAGE_RUN_RANGE
+        if label == "registers":
+            lo.WHITE_SORT_BELOW_RUN, lo.WHITE_STAGE_RUN_RANGE = 0.0, (0.0, 0.0)
+        try:
+            res[label] = A * x
+            if impl is cm:
+                fused = [f for f in A.planned() if isinstance(f, lo._FusedWhiteA)]
+                assert len(fused) == 1
+                modes[label] = fused[0]._mode
+        finally:
+            lo.WHITE_SORT_BELOW_RUN, lo.WHITE_STAGE_RUN_RANGE = old
+    assert modes["registers"] == "registers"
+    assert modes["auto"] == {"spp3": "staged", "spp1": "sorted", "random": "sorted"}[pattern]
+    gc.close(res["auto"], res["registers"], rtol=1e-13, what="%s vs register path" % modes["auto"])
+    gc.close(res["auto"], res["oracle"], rtol=1e-10, what="%s vs oracle" % modes["auto"])
