@@ -106,23 +106,29 @@ class SparseLO(lp.LinearOperator):
                 dv.ptr(self._sin_dev), self.pol, dv.ptr(v), dv.ptr(y), self.ncols, _stream())
         return y
 
-    def mean_run_length(self):
-        """Mean number of consecutive samples on the same pixel (flagged samples excluded): the statistic the
-        fused A-matvecs use to choose their scatter (registers / staged through shared memory / pixel-sorted
-        pointing).  One chunked pass over the pixels at first use."""
-        if getattr(self, "_mean_run", None) is None:
+    def run_statistics(self):
+        """(mean run length, contiguity): the mean number of consecutive samples on the same pixel (flagged
+        samples excluded) and the fraction of pixel changes that go to the neighbouring pixel index (a sweep along
+        a pixel row) -- what the fused A-matvecs use to choose their scatter (registers / staged through shared
+        memory / pixel-sorted pointing).  One chunked pass over the pixels at first use."""
+        if getattr(self, "_run_stats", None) is None:
             pix, nt = self._pix_dev, self.nrows
-            starts = good = 0
+            starts = good = near = 0
             step = 1 << 27
             for a in range(0, nt, step):
                 b = min(a + step, nt)
                 cur = pix[a:b]
-                prev = pix[max(a - 1, 0):b - 1] if a > 0 else torch.cat([cur[:1] - 1, cur[:-1]])
+                prev = pix[a - 1:b - 1] if a > 0 else torch.cat([cur[:1] - 2, cur[:-1]])
                 ok = cur >= 0
-                starts += int(((cur != prev) & ok).sum().item())
+                change = (cur != prev) & ok
+                starts += int(change.sum().item())
+                near += int((change & ((cur - prev).abs() == 1)).sum().item())
                 good += int(ok.sum().item())
-            self._mean_run = good / max(starts, 1)
-        return self._mean_run
+            self._run_stats = (good / max(starts, 1), near / max(starts, 1))
+        return self._run_stats
+
+    def mean_run_length(self):
+        return self.run_statistics()[0]
 
     def hits(self):
         out = torch.empty(max(self.ncols, 1), dtype=torch.int64, device=self._pix_dev.device)
@@ -536,23 +542,27 @@ def _filter_timeline(F):
     return int(ns[0]) if ns.size and np.all(ns == ns[0]) else 0
 
 
-WHITE_STAGE_RUN_RANGE = (1.5, 6.0)   # mean run length for which the staged scatter wins (measured, tools/pattern_probe.py)
+WHITE_STAGE_RUN_RANGE = (3.0, 6.0)   # mean run length for which the staged scatter wins (measured, tools/pattern_probe.py)
+WHITE_STAGE_MIN_CONTIGUITY = 0.9     # ... on sweeps along pixel rows only (a tilted scan changes row at most pixel changes)
 WHITE_STAGE_WINDOW = 288             # pixels per warp tile
-WHITE_SORT_BELOW_RUN = 1.5           # below: the white A-matvec runs over a pixel-sorted copy of the pointing
+WHITE_SORT_BELOW_RUN = 3.0           # below: the white A-matvec runs over a pixel-sorted copy of the pointing
 
 
 class _FusedWhiteA(lp.LinearOperator):
     """``P^T diag(w) P`` in one pass over the TOD (cm2_amatvec_white).  The scatter is chosen from the pointing
     (SparseLO.mean_run_length, at first use):
 
-    * runs of >= 6 samples (a raster scan at the usual sampling): run compression in registers + warp merge;
-    * runs of 1.5-6 samples: the same pass with the scatter staged through a shared-memory window and flushed
-      with coalesced REDs (cm2_amatvec_white_set_stage; 0.55 -> 0.46 ms per 1e8 samples at 4 samples per pixel);
-    * shorter (1 sample per pixel crossing, or the random pointing of the reference's tests,
+    * runs of >= 6 samples (a raster scan at the usual sampling), or sweeps that do not follow pixel rows: run
+      compression in registers + warp merge;
+    * runs of 3-6 samples along pixel rows: the same pass with the scatter staged through a shared-memory window
+      and flushed with coalesced REDs (cm2_amatvec_white_set_stage; 0.55 -> 0.46 ms per 1e8 samples at 4 samples
+      per pixel);
+    * shorter (1-2 samples per pixel crossing, or the random pointing of the reference's tests,
       utilities/utilities_functions.py:111-122): one atomic and one gather per sample and component would bound
-      the pass (2.2 ms per 1e8 samples); white noise has no time-domain structure, so the pass runs over a copy
-      of the pointing SORTED BY PIXEL with per-sample weights (28 B/sample, every pixel one run) instead.
-      Set-up: one stable sort; memory: a second copy of the pointing."""
+      the pass (0.96 / 1.83 / 2.2 ms per 1e8 samples at 2 / 1 samples per pixel / random); white noise has no
+      time-domain structure, so the pass runs over a copy of the pointing SORTED BY PIXEL with per-sample
+      weights instead (28 B/sample, every pixel one run: 0.45 ms).  Set-up: one stable sort; memory: a second
+      copy of the pointing."""
 
     def __init__(self, P, N):
         self.P, self.N = P, N
@@ -564,11 +574,11 @@ class _FusedWhiteA(lp.LinearOperator):
         super(_FusedWhiteA, self).__init__(n, n, matvec=self._run, symmetric=True, device=True)
 
     def _choose(self):
-        run = self.P.mean_run_length()
+        run, contig = self.P.run_statistics()
         if run < WHITE_SORT_BELOW_RUN and self.P.nrows > 0:
             self._mode = "sorted"
             self._build_sorted()
-        elif WHITE_STAGE_RUN_RANGE[0] <= run < WHITE_STAGE_RUN_RANGE[1]:
+        elif WHITE_STAGE_RUN_RANGE[0] <= run < WHITE_STAGE_RUN_RANGE[1] and contig >= WHITE_STAGE_MIN_CONTIGUITY:
             self._mode = "staged"
         else:
             self._mode = "registers"
