@@ -119,13 +119,48 @@ __device__ __forceinline__ void butterfly16(double2 (&v)[16], double2 w16) {
 }
 
 
+// Fused input d = F P x (offset filter, linearoperators.py:129-168 applied to P x, :463-497): the window is
+// computed on the fly from the pointing, x and the subscan means mu (cm2_filter_seg_mean) instead of being read
+// from a TOD temporary: d_t = (pix_t >= 0 ? P x : 0) - mu_seg(t) inside subscans (flagged samples included, as
+// FilterLO.mult leaves them, :165), 0 in the gaps.  Tile tables as for cm2_pointing_filter_mu.
+struct FftFusedIn {
+    const int32_t *pix;
+    const double *cs, *sn, *x;
+    const int64_t *seg_start, *seg_end;
+    const double *mu;
+    const int32_t *tile_seg;
+    const uint8_t *tile_flag;
+    int64_t nseg;
+    int pol;
+};
+
+template <int POL>
+__device__ __forceinline__ double fused_in_sample(const FftFusedIn &f, int64_t t) {
+    const int64_t tile = t >> 8;
+    const int flag = __ldg(f.tile_flag + tile);
+    if (flag == 0) return 0.0;
+    int64_t k = __ldg(f.tile_seg + tile);
+    if (flag != 1) {
+        while (k < f.nseg && __ldg(f.seg_end + k) <= t) ++k;
+        if (k >= f.nseg || t < __ldg(f.seg_start + k)) return 0.0;
+    }
+    const double m = __ldg(f.mu + k);
+    const int p = __ldg(f.pix + t);
+    if (p < 0) return -m;
+    const double *xp = f.x + (int64_t)POL * p;
+    if constexpr (POL == 1) return __ldg(xp) - m;
+    else if constexpr (POL == 2) return fma(__ldg(xp + 1), __ldg(f.sn + t), __ldg(xp) * __ldg(f.cs + t)) - m;
+    else return fma(__ldg(xp + 2), __ldg(f.sn + t), fma(__ldg(xp + 1), __ldg(f.cs + t), __ldg(xp))) - m;
+}
+
 // one CTA per window.  win_first[b] = first window index of noise block b (prefix, nblocks+1).
-template <int FFT_THREADS>
+// FIN = 0: the window is read from d; 1 / 2 / 3: computed from the pointing with pol = FIN (FftFusedIn).
+template <int FFT_THREADS, int FIN = 0>
 __global__ void __launch_bounds__(FFT_THREADS, 1)
     k_toeplitz_fft(const double2 *__restrict__ coef,   // [nblocks][2][M]: C1 then C2, indexed by PHYSICAL (bit-reversed) position
                    const double2 *__restrict__ tw, int L, int64_t nblocks, int64_t blocksize,
                    const int64_t *__restrict__ start, const int64_t *__restrict__ win_first,
-                   const double *__restrict__ d, double *__restrict__ out, int64_t nt) {
+                   const double *__restrict__ d, double *__restrict__ out, int64_t nt, FftFusedIn fin) {
     extern __shared__ double2 zs[];   // M complex points, one pad element per 8 (bank-conflict relief)
 #define z(i) zs[(i) + ((i) >> 3)]
     const int S = FFT_NF - 2 * (L - 1);   // alias-free outputs per window
@@ -151,8 +186,13 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
         auto winload = [&](int i) {
             const int64_t t = w0 + 2 * (int64_t)i;
             double2 v;
-            v.x = (t >= bs && t < be) ? d[t] : 0.0;
-            v.y = (t + 1 >= bs && t + 1 < be) ? d[t + 1] : 0.0;
+            if constexpr (FIN == 0) {
+                v.x = (t >= bs && t < be) ? d[t] : 0.0;
+                v.y = (t + 1 >= bs && t + 1 < be) ? d[t + 1] : 0.0;
+            } else {
+                v.x = (t >= bs && t < be) ? fused_in_sample<FIN>(fin, t) : 0.0;
+                v.y = (t + 1 >= bs && t + 1 < be) ? fused_in_sample<FIN>(fin, t + 1) : 0.0;
+            }
             return v;
         };
         {   // first pass: radix-16 (half-sizes M/2 .. M/16), inputs from global memory
@@ -171,29 +211,42 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
         }
         for (int lq = FFT_LOG2M - 7; lq >= 0; lq -= 3) {
             const int q = 1 << lq;
-            for (int j = threadIdx.x; j < FFT_M / 8; j += FFT_THREADS) {
-                const int pos = j & (q - 1);
-                const int i0 = ((j >> lq) << (lq + 3)) + pos;
-                double2 v[8];
+            // NB butterflies per thread and loop trip, every input loaded before the first output is stored:
+            // the loads of the second butterfly overlap the arithmetic of the first (the compiler cannot move
+            // them above the stores itself: same shared-memory array)
+            constexpr int NB = (FFT_M / 8) % (2 * FFT_THREADS) == 0 ? 2 : 1;
+            for (int j = threadIdx.x; j < FFT_M / 8; j += NB * FFT_THREADS) {
+                double2 v[NB][8];
+                int i0[NB];
+                double2 w8[NB];
 #pragma unroll
-                for (int m = 0; m < 8; ++m) v[m] = z(i0 + m * q);
-                const double2 w8 = __ldg(tw + q + pos);
-                const double2 w4 = cmul(w8, w8), w2 = cmul(w4, w4);
-                dif(v[0], v[4], w8);                       // half-size 4q
-                dif(v[1], v[5], rot1(w8));
-                dif(v[2], v[6], rot2(w8));
-                dif(v[3], v[7], rot3(w8));
-                const double2 w4r = rot2(w4);
-                dif(v[0], v[2], w4);                       // half-size 2q
-                dif(v[1], v[3], w4r);
-                dif(v[4], v[6], w4);
-                dif(v[5], v[7], w4r);
-                dif(v[0], v[1], w2);                       // half-size q
-                dif(v[2], v[3], w2);
-                dif(v[4], v[5], w2);
-                dif(v[6], v[7], w2);
+                for (int b = 0; b < NB; ++b) {
+                    const int jb = j + b * FFT_THREADS;
+                    const int pos = jb & (q - 1);
+                    i0[b] = ((jb >> lq) << (lq + 3)) + pos;
 #pragma unroll
-                for (int m = 0; m < 8; ++m) z(i0 + m * q) = v[m];
+                    for (int m = 0; m < 8; ++m) v[b][m] = z(i0[b] + m * q);
+                    w8[b] = __ldg(tw + q + pos);
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const double2 w4 = cmul(w8[b], w8[b]), w2 = cmul(w4, w4);
+                    dif(v[b][0], v[b][4], w8[b]);                       // half-size 4q
+                    dif(v[b][1], v[b][5], rot1(w8[b]));
+                    dif(v[b][2], v[b][6], rot2(w8[b]));
+                    dif(v[b][3], v[b][7], rot3(w8[b]));
+                    const double2 w4r = rot2(w4);
+                    dif(v[b][0], v[b][2], w4);                          // half-size 2q
+                    dif(v[b][1], v[b][3], w4r);
+                    dif(v[b][4], v[b][6], w4);
+                    dif(v[b][5], v[b][7], w4r);
+                    dif(v[b][0], v[b][1], w2);                          // half-size q
+                    dif(v[b][2], v[b][3], w2);
+                    dif(v[b][4], v[b][5], w2);
+                    dif(v[b][6], v[b][7], w2);
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) z(i0[b] + m * q) = v[b][m];
+                }
             }
             __syncthreads();
         }
@@ -229,30 +282,40 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
         // natural order -- go straight to global memory
         for (int lq = 0; lq + 4 < FFT_LOG2M; lq += 3) {
             const int q = 1 << lq;
-            for (int j = threadIdx.x; j < FFT_M / 8; j += FFT_THREADS) {
-                const int pos = j & (q - 1);
-                const int i0 = ((j >> lq) << (lq + 3)) + pos;
-                double2 v[8];
+            constexpr int NB = (FFT_M / 8) % (2 * FFT_THREADS) == 0 ? 2 : 1;
+            for (int j = threadIdx.x; j < FFT_M / 8; j += NB * FFT_THREADS) {
+                double2 v[NB][8];
+                int i0[NB];
+                double2 w8[NB];
 #pragma unroll
-                for (int m = 0; m < 8; ++m) v[m] = z(i0 + m * q);
-                double2 w8 = __ldg(tw + q + pos);
-                w8.y = -w8.y;                                               // inverse transform: conjugates
-                const double2 w4 = cmul(w8, w8), w2 = cmul(w4, w4);
-                dit(v[0], v[1], w2);                       // half-size q
-                dit(v[2], v[3], w2);
-                dit(v[4], v[5], w2);
-                dit(v[6], v[7], w2);
-                const double2 w4r = rot2c(w4);
-                dit(v[0], v[2], w4);                       // half-size 2q
-                dit(v[1], v[3], w4r);
-                dit(v[4], v[6], w4);
-                dit(v[5], v[7], w4r);
-                dit(v[0], v[4], w8);                       // half-size 4q
-                dit(v[1], v[5], rot1c(w8));
-                dit(v[2], v[6], rot2c(w8));
-                dit(v[3], v[7], rot3c(w8));
+                for (int b = 0; b < NB; ++b) {
+                    const int jb = j + b * FFT_THREADS;
+                    const int pos = jb & (q - 1);
+                    i0[b] = ((jb >> lq) << (lq + 3)) + pos;
 #pragma unroll
-                for (int m = 0; m < 8; ++m) z(i0 + m * q) = v[m];
+                    for (int m = 0; m < 8; ++m) v[b][m] = z(i0[b] + m * q);
+                    w8[b] = __ldg(tw + q + pos);
+                    w8[b].y = -w8[b].y;                                     // inverse transform: conjugates
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const double2 w4 = cmul(w8[b], w8[b]), w2 = cmul(w4, w4);
+                    dit(v[b][0], v[b][1], w2);                          // half-size q
+                    dit(v[b][2], v[b][3], w2);
+                    dit(v[b][4], v[b][5], w2);
+                    dit(v[b][6], v[b][7], w2);
+                    const double2 w4r = rot2c(w4);
+                    dit(v[b][0], v[b][2], w4);                          // half-size 2q
+                    dit(v[b][1], v[b][3], w4r);
+                    dit(v[b][4], v[b][6], w4);
+                    dit(v[b][5], v[b][7], w4r);
+                    dit(v[b][0], v[b][4], w8[b]);                       // half-size 4q
+                    dit(v[b][1], v[b][5], rot1c(w8[b]));
+                    dit(v[b][2], v[b][6], rot2c(w8[b]));
+                    dit(v[b][3], v[b][7], rot3c(w8[b]));
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) z(i0[b] + m * q) = v[b][m];
+                }
             }
             __syncthreads();
         }
@@ -305,18 +368,15 @@ extern "C" int64_t cm2_toeplitz_fft_scratch_bytes(int64_t nblocks) {
     return (nblocks + 1) * (int64_t)sizeof(int64_t) + (int64_t)FFT_M * (int64_t)sizeof(double2) + 64;
 }
 
-// coef: device, [nblocks][2][M] complex (C1, C2 stored at the bit-reversed position of their frequency, 1/M folded in);
-// scratch: cm2_toeplitz_fft_scratch_bytes(nblocks) bytes, `init` != 0 builds the twiddle table in it
-extern "C" int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
-                                            const int64_t *blk_start, const double *d, double *out, int64_t nt,
-                                            void *scratch, int init, cm2_stream_t stream) {
+static int fft_launch(const double *coef, int nband, int64_t nblocks, int64_t blocksize, const int64_t *blk_start,
+                      const double *d, double *out, int64_t nt, void *scratch, int init, const FftFusedIn *fin,
+                      cudaStream_t st) {
     CM2_REQUIRE(nt >= 0 && nblocks > 0 && nband >= 1, "bad sizes");
     CM2_REQUIRE(blk_start != nullptr || blocksize > 0, "blocksize must be > 0");
     CM2_REQUIRE(2 * (nband - 1) < FFT_NF / 2, "band too wide for the 16384-point overlap-save window");
     CM2_REQUIRE(scratch != nullptr && aligned(scratch, 16) && aligned(coef, 16), "scratch/coef must be 16-byte aligned");
     CM2_REQUIRE(d != out, "in-place Toeplitz apply is not supported");
     if (nt == 0) return CM2_OK;
-    cudaStream_t st = as_stream(stream);
     double2 *tw = reinterpret_cast<double2 *>(scratch);
     int64_t *win_first = reinterpret_cast<int64_t *>(reinterpret_cast<char *>(scratch) + FFT_M * sizeof(double2));
     if (init) {
@@ -329,6 +389,18 @@ extern "C" int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64
     const size_t smem = sizeof(double2) * (FFT_M + FFT_M / 8);
     int64_t nwin_ub = nt / S + nblocks + 1;
     int grid = (int)(nwin_ub < sm_count() ? nwin_ub : sm_count());
+    const double2 *cf = reinterpret_cast<const double2 *>(coef);
+    FftFusedIn none{};
+#define CM2_FFT_LAUNCH(THR, FIN, F) do { \
+        CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft<THR, FIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_toeplitz_fft<THR, FIN><<<grid, THR, smem, st>>>(cf, tw, nband, nblocks, blocksize, blk_start, win_first, d, out, nt, F); } while (0)
+    if (fin != nullptr) {
+        if (fin->pol == 1) CM2_FFT_LAUNCH(512, 1, *fin);
+        else if (fin->pol == 2) CM2_FFT_LAUNCH(512, 2, *fin);
+        else CM2_FFT_LAUNCH(512, 3, *fin);
+        CM2_LAUNCHED();
+        return CM2_OK;
+    }
     // threads per CTA (one CTA per SM): 512 by default -- the 16-point butterflies of the first / last pass
     // need the 128 registers per thread that 512 threads leave (measured at L = 4096: 1.81 ms vs 2.12 ms
     // with 1024 threads, which spill); CM2_FFT_THREADS=1024 selects the other instantiation
@@ -336,15 +408,34 @@ extern "C" int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64
         const char *e = getenv("CM2_FFT_THREADS");
         return (e && atoi(e) == 1024) ? 1024 : 512;
     }();
-    if (threads == 512) {
-        CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_toeplitz_fft<512><<<grid, 512, smem, st>>>(reinterpret_cast<const double2 *>(coef), tw, nband, nblocks, blocksize,
-                                                    blk_start, win_first, d, out, nt);
-    } else {
-        CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_toeplitz_fft<1024><<<grid, 1024, smem, st>>>(reinterpret_cast<const double2 *>(coef), tw, nband, nblocks, blocksize,
-                                                      blk_start, win_first, d, out, nt);
-    }
+    if (threads == 512) CM2_FFT_LAUNCH(512, 0, none);
+    else CM2_FFT_LAUNCH(1024, 0, none);
+#undef CM2_FFT_LAUNCH
     CM2_LAUNCHED();
     return CM2_OK;
+}
+
+// coef: device, [nblocks][2][M] complex (C1, C2 stored at the bit-reversed position of their frequency, 1/M folded in);
+// scratch: cm2_toeplitz_fft_scratch_bytes(nblocks) bytes, `init` != 0 builds the twiddle table in it
+extern "C" int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
+                                            const int64_t *blk_start, const double *d, double *out, int64_t nt,
+                                            void *scratch, int init, cm2_stream_t stream) {
+    return fft_launch(coef, nband, nblocks, blocksize, blk_start, d, out, nt, scratch, init, nullptr, as_stream(stream));
+}
+
+// out = T (F P x): the Toeplitz blocks applied to the offset-filtered P x WITHOUT the TOD temporary of F P x -- the
+// factors N*F*P of the composition P.T*F*N*F*P (configs[2]; linearoperators.py:582-595 over :129-168 over :463-497).
+// seg_mu from cm2_filter_seg_mean, tile tables as for cm2_pointing_filter_mu.
+extern "C" int cm2_noise_toeplitz_fft_apply_fp(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
+                                               const int64_t *blk_start, const int32_t *pix, const double *cos2phi,
+                                               const double *sin2phi, int pol, const int64_t *seg_start,
+                                               const int64_t *seg_end, const double *seg_mu, const int32_t *tile_seg,
+                                               const uint8_t *tile_flag, int64_t nseg, const double *x, double *out,
+                                               int64_t nt, void *scratch, int init, cm2_stream_t stream) {
+    CM2_REQUIRE(pol >= 1 && pol <= 3, "bad pol");
+    CM2_REQUIRE(pix != nullptr && x != nullptr && (pol == 1 || (cos2phi != nullptr && sin2phi != nullptr)), "pointing is NULL");
+    CM2_REQUIRE(nseg >= 0 && (nseg == 0 || (seg_start && seg_end && seg_mu)) && tile_seg && tile_flag, "subscan tables are NULL");
+    FftFusedIn fin{pix, cos2phi, sin2phi, x, seg_start, seg_end, seg_mu, tile_seg, tile_flag, nseg, pol};
+    return fft_launch(coef, nband, nblocks, blocksize, blk_start, reinterpret_cast<const double *>(pix), out, nt, scratch,
+                      init, &fin, as_stream(stream));
 }

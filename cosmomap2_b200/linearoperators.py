@@ -383,15 +383,20 @@ class BlockLO(BlockDiagonalLinearOperator):
             self._w_dev = dv.to_dev_f64(self._w_host)
         return self._w_dev
 
+    def _toeplitz_state(self):
+        """Device band and (for wide bands) the overlap-save FFT tables, built at first use."""
+        if self._band_dev is None:
+            self._band_dev = dv.to_dev_f64(self._band_host.reshape(-1))
+            self._fft = (_ToeplitzFFT(self._band_host, self._nband)
+                         if self._nband >= TOEPLITZ_FFT_MIN_BAND else None)
+        return self._fft
+
     def _apply_all(self, x):
         if x.numel() != self._blk.nt:
             raise lp.ShapeError("Multiplying with vector of wrong shape.")
         nb, bs, startp = self._blk.args()
         if self.isoffdiag:
-            if self._band_dev is None:
-                self._band_dev = dv.to_dev_f64(self._band_host.reshape(-1))
-                self._fft = (_ToeplitzFFT(self._band_host, self._nband)
-                             if self._nband >= TOEPLITZ_FFT_MIN_BAND else None)
+            self._toeplitz_state()
             return _toeplitz_apply(self._band_dev, self._nband, self._blk, x, self._fft)
         out = torch.empty_like(x)
         dv.call("cm2_noise_white_apply", dv.ptr(self.weights_dev()), nb, bs, startp, dv.ptr(x), dv.ptr(out),
@@ -864,6 +869,53 @@ class _FusedFilterP(lp.LinearOperator):
                 dv.ptr(F._seg_start), dv.ptr(F._seg_end), dv.ptr(rt["mu"]), dv.ptr(rt["tile_seg"]),
                 dv.ptr(rt["tile_flag"]), F.nseg, dv.ptr(x), dv.ptr(d), _stream())
         return d
+
+
+FUSE_TOEPLITZ_FILTER_P = True   # N F P (FFT Toeplitz over the offset-filtered pointing) without the TOD temporary of F P x
+
+
+class _FusedToeplitzFilterP(lp.LinearOperator):
+    """``N F P`` for a wide-band Toeplitz ``N = BlockLO(offdiag=True)`` (overlap-save FFT kernel) and the offset
+    filter: the FFT windows are computed from the pointing, x and the run-table subscan means
+    (cm2_noise_toeplitz_fft_apply_fp), so ``F P x`` never exists in HBM -- the noise operator fused with the
+    subscan filter, three of the five factors of configs[2]'s ``P.T*F*N*F*P``."""
+
+    def __init__(self, N, FP):
+        self.N, self.FP = N, FP
+        super(_FusedToeplitzFilterP, self).__init__(FP.nargin, N.nargout, matvec=self._run, symmetric=False, device=True)
+
+    def _run(self, x):
+        N, FP = self.N, self.FP
+        P, F = FP.P, FP.F
+        fft = N._toeplitz_state()
+        if FP._runs is None:
+            FP._runs = _filter_runs(P, F)
+        rt = FP._runs
+        if not rt or fft is None or not fft.ok:
+            return N._apply(FP._apply(x))
+        out = dv.empty_f64(P.nrows)
+        nb, bs, startp = N._blk.args()
+        dv.call("cm2_filter_seg_mean", dv.ptr(rt["run_pix"]), dv.ptr(rt["run_mom"]), dv.ptr(rt["seg_first"]),
+                dv.ptr(rt["seg_nruns"]), F.nseg, P.pol, dv.ptr(x), dv.ptr(rt["mu"]), _stream())
+        dv.call("cm2_noise_toeplitz_fft_apply_fp", dv.ptr(fft.coef), fft.nband, nb, bs, startp, dv.ptr(P._pix_dev),
+                dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.pol, dv.ptr(F._seg_start), dv.ptr(F._seg_end), dv.ptr(rt["mu"]),
+                dv.ptr(rt["tile_seg"]), dv.ptr(rt["tile_flag"]), F.nseg, dv.ptr(x), dv.ptr(out), P.nrows,
+                dv.ptr(fft.scratch), fft.init, _stream())
+        fft.init = 0
+        return out
+
+
+@lp.register_fuser
+def _fuse_toeplitz_filter_pointing(factors):
+    """[..., N, (F P fused)] with N a wide-band Toeplitz BlockLO: N F P becomes seg_mean + ONE FFT kernel."""
+    if not (fusion_enabled and FUSE_TOEPLITZ_FILTER_P):
+        return None
+    for i in range(len(factors) - 1):
+        N, FP = factors[i], factors[i + 1]
+        if (isinstance(N, BlockLO) and N.isoffdiag and N._nband >= TOEPLITZ_FFT_MIN_BAND and isinstance(FP, _FusedFilterP)
+                and N.shape[1] == FP.nargout):
+            return factors[:i] + [_FusedToeplitzFilterP(N, FP)] + factors[i + 2:]
+    return None
 
 
 class _FusedToeplitzA(lp.LinearOperator):

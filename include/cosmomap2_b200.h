@@ -130,6 +130,16 @@ int64_t cm2_toeplitz_fft_scratch_bytes(int64_t nblocks);
 int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
                                  const int64_t *blk_start, const double *d, double *out,
                                  int64_t nt, void *scratch, int init, cm2_stream_t stream);
+/* out = T (F P x) in one kernel: the window of the overlap-save FFT is computed from the pointing, x and the
+ * subscan means (cm2_filter_seg_mean; tile tables as for cm2_pointing_filter_mu) instead of being read from a
+ * TOD temporary -- the factors N*F*P of P.T*F*N*F*P (interfaces/linearoperators.py:582-595 over :129-168 over
+ * :463-497; the noise operator fused with the subscan filter and the pointing). */
+int cm2_noise_toeplitz_fft_apply_fp(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
+                                    const int64_t *blk_start, const int32_t *pix, const double *cos2phi,
+                                    const double *sin2phi, int pol, const int64_t *seg_start,
+                                    const int64_t *seg_end, const double *seg_mu, const int32_t *tile_seg,
+                                    const uint8_t *tile_flag, int64_t nseg, const double *x, double *out,
+                                    int64_t nt, void *scratch, int init, cm2_stream_t stream);
 /* subscan offset filter (FilterLO.mult :129-168): out = 0; for each segment [seg_start[k],
  * seg_end[k]): mu = mean of d over unflagged samples; skipped if none; out = d - mu */
 int cm2_filter_offset_apply(const int32_t *pix, const int64_t *seg_start, const int64_t *seg_end,
