@@ -20,6 +20,8 @@
 // form at L = 4096.
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "cm2_common.cuh"
 
 namespace cm2 {
@@ -51,6 +53,16 @@ __global__ void k_fft_twiddles(double2 *__restrict__ tw) {
         double sn, cs;
         sincospi(-2.0 * (double)i / (double)FFT_M, &sn, &cs);
         tw[FFT_M / 4 + i] = make_double2(cs, sn);
+    }
+}
+
+// pair mode: W^n = exp(-2 pi i n / (2 M)), n < M -- the twiddles of the radix-2 stage that joins two CTAs
+__global__ void k_fft_twiddles_pair(double2 *__restrict__ tw2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < FFT_M) {
+        double sn, cs;
+        sincospi(-(double)i / (double)FFT_M, &sn, &cs);
+        tw2[i] = make_double2(cs, sn);
     }
 }
 
@@ -119,53 +131,31 @@ __device__ __forceinline__ void butterfly16(double2 (&v)[16], double2 w16) {
 }
 
 
-// Fused input d = F P x (offset filter, linearoperators.py:129-168 applied to P x, :463-497): the window is
-// computed on the fly from the pointing, x and the subscan means mu (cm2_filter_seg_mean) instead of being read
-// from a TOD temporary: d_t = (pix_t >= 0 ? P x : 0) - mu_seg(t) inside subscans (flagged samples included, as
-// FilterLO.mult leaves them, :165), 0 in the gaps.  Tile tables as for cm2_pointing_filter_mu.
-struct FftFusedIn {
-    const int32_t *pix;
-    const double *cs, *sn, *x;
-    const int64_t *seg_start, *seg_end;
-    const double *mu;
-    const int32_t *tile_seg;
-    const uint8_t *tile_flag;
-    int64_t nseg;
-    int pol;
-};
-
-template <int POL>
-__device__ __forceinline__ double fused_in_sample(const FftFusedIn &f, int64_t t) {
-    const int64_t tile = t >> 8;
-    const int flag = __ldg(f.tile_flag + tile);
-    if (flag == 0) return 0.0;
-    int64_t k = __ldg(f.tile_seg + tile);
-    if (flag != 1) {
-        while (k < f.nseg && __ldg(f.seg_end + k) <= t) ++k;
-        if (k >= f.nseg || t < __ldg(f.seg_start + k)) return 0.0;
-    }
-    const double m = __ldg(f.mu + k);
-    const int p = __ldg(f.pix + t);
-    if (p < 0) return -m;
-    const double *xp = f.x + (int64_t)POL * p;
-    if constexpr (POL == 1) return __ldg(xp) - m;
-    else if constexpr (POL == 2) return fma(__ldg(xp + 1), __ldg(f.sn + t), __ldg(xp) * __ldg(f.cs + t)) - m;
-    else return fma(__ldg(xp + 2), __ldg(f.sn + t), fma(__ldg(xp + 1), __ldg(f.cs + t), __ldg(xp))) - m;
-}
-
 // one CTA per window.  win_first[b] = first window index of noise block b (prefix, nblocks+1).
-// FIN = 0: the window is read from d; 1 / 2 / 3: computed from the pointing with pol = FIN (FftFusedIn).
-template <int FFT_THREADS, int FIN = 0>
+// PAIR: a window of 2 NF = 32768 samples on a CLUSTER of two CTAs (one 16384-point complex transform split by one
+// radix-2 stage).  With z the packed window, W = exp(-2 pi i / 2M): CTA 0 transforms u[n] = z[n] + z[n+M] (the even
+// frequencies), CTA 1 v[n] = (z[n] - z[n+M]) W^n (the odd ones) -- both read both halves of the window from global
+// memory / L2, so the forward stage needs no exchange.  The packed-real partner of frequency k is 2M - k, which has
+// the parity of k: the transfer step stays inside a CTA (partner position M - k' for the even half, M - 1 - k', i.e.
+// the complemented physical position, for the odd half).  The inverse transforms give U (CTA 0) and V (CTA 1);
+// the window is U[n] + conj(W^n) V[n] (first half, written by CTA 0) and U[n] - conj(W^n) V[n] (second half,
+// CTA 1): each CTA reads the other's result over distributed shared memory.  At 4096 coefficients 75 % of a window
+// is alias-free instead of 50 %.
+template <int FFT_THREADS, bool PAIR = false>
 __global__ void __launch_bounds__(FFT_THREADS, 1)
     k_toeplitz_fft(const double2 *__restrict__ coef,   // [nblocks][2][M]: C1 then C2, indexed by PHYSICAL (bit-reversed) position
                    const double2 *__restrict__ tw, int L, int64_t nblocks, int64_t blocksize,
                    const int64_t *__restrict__ start, const int64_t *__restrict__ win_first,
-                   const double *__restrict__ d, double *__restrict__ out, int64_t nt, FftFusedIn fin) {
+                   const double *__restrict__ d, double *__restrict__ out, int64_t nt,
+                   const double2 *__restrict__ tw2) {
     extern __shared__ double2 zs[];   // M complex points, one pad element per 8 (bank-conflict relief)
 #define z(i) zs[(i) + ((i) >> 3)]
-    const int S = FFT_NF - 2 * (L - 1);   // alias-free outputs per window
+    const int S = (PAIR ? 2 * FFT_NF : FFT_NF) - 2 * (L - 1);   // alias-free outputs per window
     const int64_t nwin = win_first[nblocks];
-    for (int64_t win = blockIdx.x; win < nwin; win += gridDim.x) {
+    unsigned crank = 0;
+    if constexpr (PAIR) asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int64_t win0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x, winstep = PAIR ? (gridDim.x >> 1) : gridDim.x;
+    for (int64_t win = win0; win < nwin; win += winstep) {
         int64_t lo = 0, hi = nblocks;
         while (hi - lo > 1) {
             int64_t mid = (lo + hi) >> 1;
@@ -183,17 +173,21 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
         // The FIRST pass takes its inputs straight from global memory (zero outside the noise block:
         // the non-circulant boundary), so the window never makes a separate trip through shared memory.
         static_assert(FFT_LOG2M % 3 == 1 && FFT_LOG2M >= 4, "one radix-16 pass + radix-8 passes");
-        auto winload = [&](int i) {
+        auto winload1 = [&](int i) {
             const int64_t t = w0 + 2 * (int64_t)i;
             double2 v;
-            if constexpr (FIN == 0) {
-                v.x = (t >= bs && t < be) ? d[t] : 0.0;
-                v.y = (t + 1 >= bs && t + 1 < be) ? d[t + 1] : 0.0;
-            } else {
-                v.x = (t >= bs && t < be) ? fused_in_sample<FIN>(fin, t) : 0.0;
-                v.y = (t + 1 >= bs && t + 1 < be) ? fused_in_sample<FIN>(fin, t + 1) : 0.0;
-            }
+            v.x = (t >= bs && t < be) ? d[t] : 0.0;
+            v.y = (t + 1 >= bs && t + 1 < be) ? d[t + 1] : 0.0;
             return v;
+        };
+        auto winload = [&](int i) {
+            if constexpr (!PAIR) {
+                return winload1(i);
+            } else {
+                const double2 a = winload1(i), b = winload1(i + FFT_M);
+                if (crank == 0) return make_double2(a.x + b.x, a.y + b.y);
+                return cmul(make_double2(a.x - b.x, a.y - b.y), __ldg(tw2 + i));
+            }
         };
         {   // first pass: radix-16 (half-sizes M/2 .. M/16), inputs from global memory
             constexpr int lq = FFT_LOG2M - 4, q = 1 << lq;
@@ -256,7 +250,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
         // partner Z[M-k] but not the partner's coefficients (the first version handled the pair
         // (k, M-k) in one thread and paid two scattered 16-byte global loads per pair for them).
         // All reads, a barrier, then all writes: the update is in place.
-        const double2 *c1 = coef + (int64_t)b * 2 * FFT_M;
+        const double2 *c1 = coef + (PAIR ? (int64_t)(2 * b + crank) : (int64_t)b) * 2 * FFT_M;
         const double2 *c2 = c1 + FFT_M;
         constexpr int NPOS = FFT_M / FFT_THREADS;
         double2 res[NPOS];
@@ -265,7 +259,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             const int pk = threadIdx.x + i * FFT_THREADS;
             const int k = __brev((unsigned)pk) >> (32 - FFT_LOG2M);
             const int km = (FFT_M - k) & (FFT_M - 1);
-            const int pm = __brev((unsigned)km) >> (32 - FFT_LOG2M);
+            const int pm = (PAIR && crank == 1) ? (FFT_M - 1 - pk) : (int)(__brev((unsigned)km) >> (32 - FFT_LOG2M));
             const double2 zk = z(pk), zm = z(pm);
             // E[k] = (Z[k] + conj Z[M-k])/2 ; O[k] = (Z[k] - conj Z[M-k])/(2i)
             const double2 Ek = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
@@ -330,14 +324,39 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                 double2 w16 = __ldg(tw + FFT_M / 4 + pos);
                 w16.y = -w16.y;
                 butterfly16<true>(v, w16);
-                // the alias-free samples, window positions [L-1, L-1+S)
+                if constexpr (PAIR) {
 #pragma unroll
-                for (int m = 0; m < 16; ++m) {
-                    const int r0 = 2 * (i0 + m * q) - (L - 1);        // output index of v.x within the window's S outputs
-                    if (r0 >= 0 && r0 < S && j0 + r0 < be) out[j0 + r0] = v[m].x;
-                    if (r0 + 1 >= 0 && r0 + 1 < S && j0 + r0 + 1 < be) out[j0 + r0 + 1] = v[m].y;
+                    for (int m = 0; m < 16; ++m) z(i0 + m * q) = v[m];      // U (CTA 0) / V (CTA 1), natural order
+                } else {
+                    // the alias-free samples, window positions [L-1, L-1+S)
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) {
+                        const int r0 = 2 * (i0 + m * q) - (L - 1);        // output index of v.x within the window's S outputs
+                        if (r0 >= 0 && r0 < S && j0 + r0 < be) out[j0 + r0] = v[m].x;
+                        if (r0 + 1 >= 0 && r0 + 1 < S && j0 + r0 + 1 < be) out[j0 + r0 + 1] = v[m].y;
+                    }
                 }
             }
+        }
+        if constexpr (PAIR) {
+            // the radix-2 stage that joins the two CTAs: this CTA's half of the window from U and V
+            namespace cg = cooperative_groups;
+            cg::cluster_group cl = cg::this_cluster();
+            cl.sync();                                                  // both inverse transforms are complete
+            const double2 *rz = cl.map_shared_rank(zs, crank ^ 1u);
+            for (int n = threadIdx.x; n < FFT_M; n += FFT_THREADS) {
+                const int r0 = 2 * (n + (crank ? FFT_M : 0)) - (L - 1);
+                if (r0 + 1 < 0 || r0 >= S) continue;                    // aliased head / tail of the window
+                const double2 own = z(n), oth = rz[n + (n >> 3)];
+                double2 w = __ldg(tw2 + n);
+                w.y = -w.y;
+                const double2 U = crank ? oth : own, V = crank ? own : oth;
+                const double2 t = cmul(w, V);
+                const double2 r = crank ? make_double2(U.x - t.x, U.y - t.y) : make_double2(U.x + t.x, U.y + t.y);
+                if (r0 >= 0 && j0 + r0 < be) out[j0 + r0] = r.x;
+                if (r0 + 1 < S && j0 + r0 + 1 < be) out[j0 + r0 + 1] = r.y;
+            }
+            cl.sync();                                                  // the partner has read my half: the next window may overwrite it
         }
     }
 }
@@ -365,42 +384,55 @@ using namespace cm2;
 extern "C" int cm2_toeplitz_fft_points(void) { return FFT_M; }
 
 extern "C" int64_t cm2_toeplitz_fft_scratch_bytes(int64_t nblocks) {
-    return (nblocks + 1) * (int64_t)sizeof(int64_t) + (int64_t)FFT_M * (int64_t)sizeof(double2) + 64;
+    return (nblocks + 1) * (int64_t)sizeof(int64_t) + 2 * (int64_t)FFT_M * (int64_t)sizeof(double2) + 64;
 }
 
 static int fft_launch(const double *coef, int nband, int64_t nblocks, int64_t blocksize, const int64_t *blk_start,
-                      const double *d, double *out, int64_t nt, void *scratch, int init, const FftFusedIn *fin,
-                      cudaStream_t st) {
+                      const double *d, double *out, int64_t nt, void *scratch, int init, int pair, cudaStream_t st) {
     CM2_REQUIRE(nt >= 0 && nblocks > 0 && nband >= 1, "bad sizes");
     CM2_REQUIRE(blk_start != nullptr || blocksize > 0, "blocksize must be > 0");
     CM2_REQUIRE(2 * (nband - 1) < FFT_NF / 2, "band too wide for the 16384-point overlap-save window");
     CM2_REQUIRE(scratch != nullptr && aligned(scratch, 16) && aligned(coef, 16), "scratch/coef must be 16-byte aligned");
     CM2_REQUIRE(d != out, "in-place Toeplitz apply is not supported");
+    CM2_REQUIRE(pair == 0 || pair == 1, "pair must be 0 or 1");
     if (nt == 0) return CM2_OK;
     double2 *tw = reinterpret_cast<double2 *>(scratch);
-    int64_t *win_first = reinterpret_cast<int64_t *>(reinterpret_cast<char *>(scratch) + FFT_M * sizeof(double2));
+    double2 *tw2 = tw + FFT_M;
+    int64_t *win_first = reinterpret_cast<int64_t *>(reinterpret_cast<char *>(scratch) + 2 * FFT_M * sizeof(double2));
     if (init) {
         k_fft_twiddles<<<(FFT_M / 4 + 255) / 256, 256, 0, st>>>(tw);
+        k_fft_twiddles_pair<<<(FFT_M + 255) / 256, 256, 0, st>>>(tw2);
         CM2_LAUNCHED();
     }
-    const int S = FFT_NF - 2 * (nband - 1);
+    const int S = (pair ? 2 * FFT_NF : FFT_NF) - 2 * (nband - 1);
     k_win_first<<<1, 1, 0, st>>>(nblocks, blocksize, blk_start, nt, S, win_first);
     CM2_LAUNCHED();
     const size_t smem = sizeof(double2) * (FFT_M + FFT_M / 8);
     int64_t nwin_ub = nt / S + nblocks + 1;
-    int grid = (int)(nwin_ub < sm_count() ? nwin_ub : sm_count());
     const double2 *cf = reinterpret_cast<const double2 *>(coef);
-    FftFusedIn none{};
-#define CM2_FFT_LAUNCH(THR, FIN, F) do { \
-        CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft<THR, FIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_toeplitz_fft<THR, FIN><<<grid, THR, smem, st>>>(cf, tw, nband, nblocks, blocksize, blk_start, win_first, d, out, nt, F); } while (0)
-    if (fin != nullptr) {
-        if (fin->pol == 1) CM2_FFT_LAUNCH(512, 1, *fin);
-        else if (fin->pol == 2) CM2_FFT_LAUNCH(512, 2, *fin);
-        else CM2_FFT_LAUNCH(512, 3, *fin);
-        CM2_LAUNCHED();
+    if (pair) {
+        // one window per 2-CTA cluster (distributed shared memory for the joining stage)
+        int64_t ncl = sm_count() / 2;
+        if (nwin_ub < ncl) ncl = nwin_ub;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * ncl));
+        cfg.blockDim = dim3(512);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CM2_CUDA(cudaLaunchKernelEx(&cfg, k_toeplitz_fft<512, true>, cf, (const double2 *)tw, nband, nblocks, blocksize,
+                                    blk_start, (const int64_t *)win_first, d, out, nt, (const double2 *)tw2));
+        count_launch();
         return CM2_OK;
     }
+    int grid = (int)(nwin_ub < sm_count() ? nwin_ub : sm_count());
     // threads per CTA (one CTA per SM): 512 by default -- the 16-point butterflies of the first / last pass
     // need the 128 registers per thread that 512 threads leave (measured at L = 4096: 1.81 ms vs 2.12 ms
     // with 1024 threads, which spill); CM2_FFT_THREADS=1024 selects the other instantiation
@@ -408,34 +440,23 @@ static int fft_launch(const double *coef, int nband, int64_t nblocks, int64_t bl
         const char *e = getenv("CM2_FFT_THREADS");
         return (e && atoi(e) == 1024) ? 1024 : 512;
     }();
-    if (threads == 512) CM2_FFT_LAUNCH(512, 0, none);
-    else CM2_FFT_LAUNCH(1024, 0, none);
-#undef CM2_FFT_LAUNCH
+    if (threads == 512) {
+        CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_toeplitz_fft<512><<<grid, 512, smem, st>>>(cf, tw, nband, nblocks, blocksize, blk_start, win_first, d, out, nt, tw2);
+    } else {
+        CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_toeplitz_fft<1024><<<grid, 1024, smem, st>>>(cf, tw, nband, nblocks, blocksize, blk_start, win_first, d, out, nt, tw2);
+    }
     CM2_LAUNCHED();
     return CM2_OK;
 }
 
 // coef: device, [nblocks][2][M] complex (C1, C2 stored at the bit-reversed position of their frequency, 1/M folded in);
-// scratch: cm2_toeplitz_fft_scratch_bytes(nblocks) bytes, `init` != 0 builds the twiddle table in it
+// pair = 1: 32768-sample windows on 2-CTA clusters, coef [nblocks][2 (CTA: even / odd frequencies)][2][M] of the
+// 2M-point packed transform, entry p of CTA c = C[2 brev(p) + c], 1/(2M) folded in;
+// scratch: cm2_toeplitz_fft_scratch_bytes(nblocks) bytes, `init` != 0 builds the twiddle tables in it
 extern "C" int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
                                             const int64_t *blk_start, const double *d, double *out, int64_t nt,
-                                            void *scratch, int init, cm2_stream_t stream) {
-    return fft_launch(coef, nband, nblocks, blocksize, blk_start, d, out, nt, scratch, init, nullptr, as_stream(stream));
-}
-
-// out = T (F P x): the Toeplitz blocks applied to the offset-filtered P x WITHOUT the TOD temporary of F P x -- the
-// factors N*F*P of the composition P.T*F*N*F*P (configs[2]; linearoperators.py:582-595 over :129-168 over :463-497).
-// seg_mu from cm2_filter_seg_mean, tile tables as for cm2_pointing_filter_mu.
-extern "C" int cm2_noise_toeplitz_fft_apply_fp(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
-                                               const int64_t *blk_start, const int32_t *pix, const double *cos2phi,
-                                               const double *sin2phi, int pol, const int64_t *seg_start,
-                                               const int64_t *seg_end, const double *seg_mu, const int32_t *tile_seg,
-                                               const uint8_t *tile_flag, int64_t nseg, const double *x, double *out,
-                                               int64_t nt, void *scratch, int init, cm2_stream_t stream) {
-    CM2_REQUIRE(pol >= 1 && pol <= 3, "bad pol");
-    CM2_REQUIRE(pix != nullptr && x != nullptr && (pol == 1 || (cos2phi != nullptr && sin2phi != nullptr)), "pointing is NULL");
-    CM2_REQUIRE(nseg >= 0 && (nseg == 0 || (seg_start && seg_end && seg_mu)) && tile_seg && tile_flag, "subscan tables are NULL");
-    FftFusedIn fin{pix, cos2phi, sin2phi, x, seg_start, seg_end, seg_mu, tile_seg, tile_flag, nseg, pol};
-    return fft_launch(coef, nband, nblocks, blocksize, blk_start, reinterpret_cast<const double *>(pix), out, nt, scratch,
-                      init, &fin, as_stream(stream));
+                                            void *scratch, int init, int pair, cm2_stream_t stream) {
+    return fft_launch(coef, nband, nblocks, blocksize, blk_start, d, out, nt, scratch, init, pair, as_stream(stream));
 }

@@ -189,30 +189,53 @@ TOEPLITZ_FFT_MIN_BAND = 48     # bands at least this wide go through the overlap
                                # crossover at 1e8 samples: direct 64 lags 2.29 ms, FFT 1.5 ms for any band <= 256)
 
 
-def toeplitz_fft_tables(band_host, nband, M):
-    """Packed transfer functions C1, C2 of cm2_noise_toeplitz_fft_apply for every noise block
-    (host, NumPy): [nblocks][2][M] complex, stored at the bit-reversed position of each frequency,
-    1/M folded in.  See csrc/toeplitz_fft.cu for the derivation."""
-    NF = 2 * M
-    band_host = np.asarray(band_host, dtype=np.float64).reshape(-1, nband)
-    nb = band_host.shape[0]
+TOEPLITZ_FFT_PAIR_MIN_BAND = 2000   # from here on a 32768-sample window on a 2-CTA cluster beats two 16384-sample windows
+
+
+def _bit_reverse(M):
     k = np.arange(M)
-    w = np.exp(-2j * np.pi * k / NF)
     bits = int(np.log2(M))
-    brev = np.zeros(M, dtype=np.int64)              # the kernel keeps spectra bit-reversed in place
+    brev = np.zeros(M, dtype=np.int64)
     for bit in range(bits):
         brev |= ((k >> bit) & 1) << (bits - 1 - bit)
-    coef = np.empty((nb, 2, M), dtype=np.complex128)
+    return brev
+
+
+def _packed_transfer(a, nband, M):
+    """C1, C2 (natural frequency order, 1/M folded in) of the M-point packed transform of a 2M-sample window."""
+    NF = 2 * M
+    hc = np.zeros(NF)
+    hc[:nband] = a
+    if nband > 1:
+        hc[NF - nband + 1:] = a[1:][::-1]
+    H = np.fft.fft(hc).real                      # real and even: the band is symmetric
+    w = np.exp(-2j * np.pi * np.arange(M) / NF)
+    Hs, Hd = 0.5 * (H[:M] + H[M:]), 0.5 * (H[:M] - H[M:])
+    return (Hs + 1j * Hd * np.conj(w)) / M, (Hd * w + 1j * Hs) / M
+
+
+def toeplitz_fft_tables(band_host, nband, M, pair=False):
+    """Packed transfer functions C1, C2 of cm2_noise_toeplitz_fft_apply for every noise block (host, NumPy), 1/M
+    folded in, stored at the position the kernel keeps each frequency at (spectra stay bit-reversed in place).
+    ``pair=False``: [nblocks][2][M] for windows of 2M samples, table[p] = C[brev(p)].
+    ``pair=True``: [nblocks][2 (CTA)][2][M] for windows of 4M samples on a 2-CTA cluster: CTA c holds the
+    frequencies 2k' + c of the 2M-point transform at position brev(k').  See csrc/toeplitz_fft.cu."""
+    band_host = np.asarray(band_host, dtype=np.float64).reshape(-1, nband)
+    nb = band_host.shape[0]
+    brev = _bit_reverse(M)
+    if not pair:
+        coef = np.empty((nb, 2, M), dtype=np.complex128)
+        for b in range(nb):
+            C1, C2 = _packed_transfer(band_host[b], nband, M)
+            coef[b, 0] = C1[brev]                    # table[position] = C[brev(position)]
+            coef[b, 1] = C2[brev]
+        return coef
+    coef = np.empty((nb, 2, 2, M), dtype=np.complex128)
     for b in range(nb):
-        a = band_host[b]
-        hc = np.zeros(NF)
-        hc[:nband] = a
-        if nband > 1:
-            hc[NF - nband + 1:] = a[1:][::-1]
-        H = np.fft.fft(hc).real                      # real and even: the band is symmetric
-        Hs, Hd = 0.5 * (H[:M] + H[M:]), 0.5 * (H[:M] - H[M:])
-        coef[b, 0] = ((Hs + 1j * Hd * np.conj(w)) / M)[brev]     # table[position] = C[brev(position)]
-        coef[b, 1] = ((Hd * w + 1j * Hs) / M)[brev]
+        C1, C2 = _packed_transfer(band_host[b], nband, 2 * M)
+        for c in range(2):
+            coef[b, c, 0] = C1[2 * brev + c]
+            coef[b, c, 1] = C2[2 * brev + c]
     return coef
 
 
@@ -221,11 +244,11 @@ class _ToeplitzFFT(object):
 
     def __init__(self, band_host, nband):
         M = int(dv.call("cm2_toeplitz_fft_points"))
-        NF = 2 * M
         self.ok = 2 * (nband - 1) < M
         if not self.ok:
             return
-        coef = toeplitz_fft_tables(band_host, nband, M)
+        self.pair = 1 if nband >= TOEPLITZ_FFT_PAIR_MIN_BAND else 0
+        coef = toeplitz_fft_tables(band_host, nband, M, pair=bool(self.pair))
         nb = coef.shape[0]
         self.coef = dv.to_dev_f64(coef.view(np.float64).reshape(-1))
         self.scratch = torch.empty(int(dv.call("cm2_toeplitz_fft_scratch_bytes", nb)) // 8 + 2, dtype=torch.float64,
@@ -237,7 +260,7 @@ class _ToeplitzFFT(object):
         out = torch.empty_like(v)
         nb, bs, startp = blocks.args()
         dv.call("cm2_noise_toeplitz_fft_apply", dv.ptr(self.coef), self.nband, nb, bs, startp, dv.ptr(v), dv.ptr(out),
-                v.numel(), dv.ptr(self.scratch), self.init, _stream())
+                v.numel(), dv.ptr(self.scratch), self.init, self.pair, _stream())
         self.init = 0
         return out
 
@@ -869,53 +892,6 @@ class _FusedFilterP(lp.LinearOperator):
                 dv.ptr(F._seg_start), dv.ptr(F._seg_end), dv.ptr(rt["mu"]), dv.ptr(rt["tile_seg"]),
                 dv.ptr(rt["tile_flag"]), F.nseg, dv.ptr(x), dv.ptr(d), _stream())
         return d
-
-
-FUSE_TOEPLITZ_FILTER_P = True   # N F P (FFT Toeplitz over the offset-filtered pointing) without the TOD temporary of F P x
-
-
-class _FusedToeplitzFilterP(lp.LinearOperator):
-    """``N F P`` for a wide-band Toeplitz ``N = BlockLO(offdiag=True)`` (overlap-save FFT kernel) and the offset
-    filter: the FFT windows are computed from the pointing, x and the run-table subscan means
-    (cm2_noise_toeplitz_fft_apply_fp), so ``F P x`` never exists in HBM -- the noise operator fused with the
-    subscan filter, three of the five factors of configs[2]'s ``P.T*F*N*F*P``."""
-
-    def __init__(self, N, FP):
-        self.N, self.FP = N, FP
-        super(_FusedToeplitzFilterP, self).__init__(FP.nargin, N.nargout, matvec=self._run, symmetric=False, device=True)
-
-    def _run(self, x):
-        N, FP = self.N, self.FP
-        P, F = FP.P, FP.F
-        fft = N._toeplitz_state()
-        if FP._runs is None:
-            FP._runs = _filter_runs(P, F)
-        rt = FP._runs
-        if not rt or fft is None or not fft.ok:
-            return N._apply(FP._apply(x))
-        out = dv.empty_f64(P.nrows)
-        nb, bs, startp = N._blk.args()
-        dv.call("cm2_filter_seg_mean", dv.ptr(rt["run_pix"]), dv.ptr(rt["run_mom"]), dv.ptr(rt["seg_first"]),
-                dv.ptr(rt["seg_nruns"]), F.nseg, P.pol, dv.ptr(x), dv.ptr(rt["mu"]), _stream())
-        dv.call("cm2_noise_toeplitz_fft_apply_fp", dv.ptr(fft.coef), fft.nband, nb, bs, startp, dv.ptr(P._pix_dev),
-                dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.pol, dv.ptr(F._seg_start), dv.ptr(F._seg_end), dv.ptr(rt["mu"]),
-                dv.ptr(rt["tile_seg"]), dv.ptr(rt["tile_flag"]), F.nseg, dv.ptr(x), dv.ptr(out), P.nrows,
-                dv.ptr(fft.scratch), fft.init, _stream())
-        fft.init = 0
-        return out
-
-
-@lp.register_fuser
-def _fuse_toeplitz_filter_pointing(factors):
-    """[..., N, (F P fused)] with N a wide-band Toeplitz BlockLO: N F P becomes seg_mean + ONE FFT kernel."""
-    if not (fusion_enabled and FUSE_TOEPLITZ_FILTER_P):
-        return None
-    for i in range(len(factors) - 1):
-        N, FP = factors[i], factors[i + 1]
-        if (isinstance(N, BlockLO) and N.isoffdiag and N._nband >= TOEPLITZ_FFT_MIN_BAND and isinstance(FP, _FusedFilterP)
-                and N.shape[1] == FP.nargout):
-            return factors[:i] + [_FusedToeplitzFilterP(N, FP)] + factors[i + 2:]
-    return None
 
 
 class _FusedToeplitzA(lp.LinearOperator):

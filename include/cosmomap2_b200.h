@@ -124,22 +124,16 @@ int cm2_noise_toeplitz_apply(const double *band, int nband, int64_t nblocks, int
  * the direct form become ~150).  coef[nblocks][2][M] complex fp64, M = cm2_toeplitz_fft_points():
  * the packed transfer function C1, C2 of each block's band, stored at the bit-reversed position of
  * each frequency (see csrc/toeplitz_fft.cu), built on the host.  Requires 2 (nband-1) < M.  scratch: cm2_toeplitz_fft_scratch_bytes(nblocks) bytes; pass
- * init != 0 on the first call with a given scratch (twiddle table). */
+ * init != 0 on the first call with a given scratch (twiddle tables).
+ * pair = 1: windows of 4M = 32768 samples on clusters of two CTAs (one 2M-point packed transform split by a
+ * radix-2 stage: even frequencies in CTA 0, odd ones in CTA 1, joined over distributed shared memory), which
+ * leaves 75 % of a window alias-free at 4096 coefficients instead of 50 %; coef is then
+ * [nblocks][2 (CTA c)][2][M] with entry p of CTA c = C[2 brev(p) + c] of the 2M-point transform. */
 int cm2_toeplitz_fft_points(void);
 int64_t cm2_toeplitz_fft_scratch_bytes(int64_t nblocks);
 int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
                                  const int64_t *blk_start, const double *d, double *out,
-                                 int64_t nt, void *scratch, int init, cm2_stream_t stream);
-/* out = T (F P x) in one kernel: the window of the overlap-save FFT is computed from the pointing, x and the
- * subscan means (cm2_filter_seg_mean; tile tables as for cm2_pointing_filter_mu) instead of being read from a
- * TOD temporary -- the factors N*F*P of P.T*F*N*F*P (interfaces/linearoperators.py:582-595 over :129-168 over
- * :463-497; the noise operator fused with the subscan filter and the pointing). */
-int cm2_noise_toeplitz_fft_apply_fp(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
-                                    const int64_t *blk_start, const int32_t *pix, const double *cos2phi,
-                                    const double *sin2phi, int pol, const int64_t *seg_start,
-                                    const int64_t *seg_end, const double *seg_mu, const int32_t *tile_seg,
-                                    const uint8_t *tile_flag, int64_t nseg, const double *x, double *out,
-                                    int64_t nt, void *scratch, int init, cm2_stream_t stream);
+                                 int64_t nt, void *scratch, int init, int pair, cm2_stream_t stream);
 /* subscan offset filter (FilterLO.mult :129-168): out = 0; for each segment [seg_start[k],
  * seg_end[k]): mu = mean of d over unflagged samples; skipped if none; out = d - mu */
 int cm2_filter_offset_apply(const int32_t *pix, const int64_t *seg_start, const int64_t *seg_end,

@@ -168,19 +168,7 @@ def test_fused_filter_pointing(cm, pol):
                 assert FP.planned()[0]._runs
                 A = P.T * F * N * F * P
                 y = A * x
-                if nband >= lo.TOEPLITZ_FFT_MIN_BAND:
-                    # N F P in ONE FFT kernel: the windows are computed from the pointing and the run-table means
-                    assert isinstance(A.planned()[-1], lo._FusedToeplitzFilterP)
-                    lo.FUSE_TOEPLITZ_FILTER_P = False
-                    try:
-                        A2 = P.T * F * N * F * P
-                        y2 = A2 * x
-                        assert isinstance(A2.planned()[-1], lo._FusedFilterP)
-                    finally:
-                        lo.FUSE_TOEPLITZ_FILTER_P = True
-                    gc.close(y, y2, rtol=1e-13, what="N F P fused into the FFT kernel vs the chain")
-                else:
-                    assert isinstance(A.planned()[-1], lo._FusedFilterP)
+                assert isinstance(A.planned()[-1], lo._FusedFilterP)
                 out[name] = (d, y)
         gc.close(out["gpu"][0], out["oracle"][0], what="F P x")
         gc.close(out["gpu"][1], out["oracle"][1], what="P^T F N F P x, nband=%d" % nband)

@@ -194,28 +194,36 @@ def test_krypy_style_arnoldi_and_two_level(cm):
     assert len(it_m2) <= len(it_bd)
 
 
-def test_toeplitz_fft_path_equals_direct_path(cm):
-    """Overlap-save FFT kernel vs the direct shared-memory kernel vs the oracle, multi-block."""
+@pytest.mark.parametrize("pair_min", [None, 2])
+def test_toeplitz_fft_path_equals_direct_path(cm, pair_min):
+    """Overlap-save FFT kernel vs the direct shared-memory kernel vs the oracle, multi-block, ragged blocks.
+    ``pair_min = 2`` forces every band through the 32768-sample windows on 2-CTA clusters (by default only bands
+    of >= 2000 coefficients take them: the L = 4096 case below)."""
     import oracle
     from cosmomap2_b200 import linearoperators as lo
     rng = np.random.default_rng(21)
-    for sizes, L in ((3 * [20000], 200), ([30000, 9000, 41000], 1000), ([50000], 4096)):
+    for sizes, L in ((3 * [20000], 200), ([30000, 9000, 41000], 1000), ([50000], 4096), ([70001, 33000, 5], 3000)):
         nt = sum(sizes)
         v = rng.standard_normal(nt)
         t = [np.concatenate([[1.0 + rng.random()], -0.3 * rng.random(L - 1) / L]) for _ in sizes]
-        old = lo.TOEPLITZ_FFT_MIN_BAND
+        old = lo.TOEPLITZ_FFT_MIN_BAND, lo.TOEPLITZ_FFT_PAIR_MIN_BAND
         try:
             lo.TOEPLITZ_FFT_MIN_BAND = 10 ** 9
             y_direct = cm.BlockLO(sizes, t, offdiag=True) * v
             lo.TOEPLITZ_FFT_MIN_BAND = 2
+            if pair_min is not None:
+                lo.TOEPLITZ_FFT_PAIR_MIN_BAND = pair_min
             N = cm.BlockLO(sizes, t, offdiag=True)
             y_fft = N * v
             assert N._fft is not None and N._fft.ok
+            assert N._fft.pair == (1 if L >= lo.TOEPLITZ_FFT_PAIR_MIN_BAND else 0)
+            y_fft2 = N * v                                         # second call: tables already built
         finally:
-            lo.TOEPLITZ_FFT_MIN_BAND = old
+            lo.TOEPLITZ_FFT_MIN_BAND, lo.TOEPLITZ_FFT_PAIR_MIN_BAND = old
         y_ref = oracle.BlockLO(sizes, t, offdiag=True) * v
         gc.close(y_direct, y_ref, what="direct Toeplitz L=%d" % L)
         gc.close(y_fft, y_ref, what="FFT Toeplitz L=%d" % L)
+        gc.exact(y_fft2, y_fft, "FFT Toeplitz is deterministic")
 
 
 def test_mask_differs_only_on_rounding_knife_edge_pixels(cm):

@@ -115,6 +115,59 @@ def test_fft_transfer_tables_reproduce_the_toeplitz_product(L):
     assert np.max(np.abs(y - ref)) <= 1e-12 * np.max(np.abs(ref))
 
 
+def _emulate_fft_pair_kernel(coef, a, v, log2m):
+    """NumPy emulation of the 2-CTA (pair) mode of csrc/toeplitz_fft.cu on one block: windows of 4M samples, one
+    2M-point packed transform split by a radix-2 stage -- CTA 0: u = z[:M] + z[M:] (even frequencies), CTA 1:
+    v = (z[:M] - z[M:]) W^n (odd); transfer step inside each CTA (partner M - k' / M - 1 - k'); the halves of the
+    window are U +- conj(W^n) V.  ``coef``: [2 (CTA)][2][M] as built by toeplitz_fft_tables(pair=True), entries at
+    the bit-reversed position of k'."""
+    M = 1 << log2m
+    NF2, L, n = 4 * M, len(a), len(v)
+    S = NF2 - 2 * (L - 1)
+    brev = lo._bit_reverse(M)
+    out = np.zeros(n)
+    nn = np.arange(M)
+    Wn = np.exp(-2j * np.pi * nn / (2 * M))
+    kp = np.arange(M)
+    for j0 in range(0, n, S):
+        w0 = j0 - (L - 1)
+        t = w0 + np.arange(NF2)
+        x = np.where((t >= 0) & (t < n), v[np.clip(t, 0, n - 1)], 0.0)
+        z = x[0::2] + 1j * x[1::2]
+        halves = (z[:M] + z[M:], (z[:M] - z[M:]) * Wn)
+        res = []
+        for c in range(2):
+            Z = np.fft.fft(halves[c])                              # natural order; the kernel keeps Z[k'] at brev(k')
+            partner = np.conj(Z[(M - kp) % M]) if c == 0 else np.conj(Z[M - 1 - kp])
+            E, O = 0.5 * (Z + partner), (Z - partner) / 2j
+            C1, C2 = np.empty(M, complex), np.empty(M, complex)
+            C1[kp] = coef[c, 0][brev[kp]]                           # table[brev(k')] holds frequency 2k' + c
+            C2[kp] = coef[c, 1][brev[kp]]
+            res.append(np.fft.ifft(C1 * E + C2 * O) * M)
+        U, V = res
+        w = np.concatenate([U + np.conj(Wn) * V, U - np.conj(Wn) * V])
+        zr = np.empty(NF2)
+        zr[0::2], zr[1::2] = w.real, w.imag
+        idx = j0 + np.arange(S)
+        keep = idx < n
+        out[idx[keep]] = zr[L - 1 + np.arange(S)][keep]
+    return out
+
+
+@pytest.mark.parametrize("L", [1, 2, 9, 40, 100])
+def test_fft_pair_tables_reproduce_the_toeplitz_product(L):
+    rng = np.random.default_rng(L)
+    log2m = 7
+    a = rng.random(L)
+    a[0] += 2.0
+    v = rng.standard_normal(1900)
+    coef = lo.toeplitz_fft_tables(a[None, :], L, 1 << log2m, pair=True)
+    assert coef.shape == (1, 2, 2, 1 << log2m)
+    y = _emulate_fft_pair_kernel(coef[0], a, v, log2m)
+    ref = oracle.ToeplitzLO(a, len(v)) * v
+    assert np.max(np.abs(y - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
 def test_synthetic_scan_properties():
     sc = synthetic.raster_scan(120000, nside=64, ndet=6, nx=50, ny=30, samples_per_pixel=7.0, seed=3,
                                flag_turnarounds=True)
