@@ -150,7 +150,10 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                    const double2 *__restrict__ tw2) {
     extern __shared__ double2 zs[];   // M complex points, one pad element per 8 (bank-conflict relief)
 #define z(i) zs[(i) + ((i) >> 3)]
-    const int S = (PAIR ? 2 * FFT_NF : FFT_NF) - 2 * (L - 1);   // alias-free outputs per window
+    // window positions [HD, HD + S) are alias-free; HD = L - 1 rounded up to even and S even, so that a window
+    // starts on an even sample whenever its noise block does and the window moves as 16-byte pairs
+    const int HD = (L - 1) + ((L - 1) & 1);
+    const int S = ((PAIR ? 2 * FFT_NF : FFT_NF) - HD - (L - 1)) & ~1;
     const int64_t nwin = win_first[nblocks];
     unsigned crank = 0;
     if constexpr (PAIR) asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
@@ -165,7 +168,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
         const int64_t bs = start ? start[b] : b * blocksize;
         const int64_t be = start ? start[b + 1] : (b + 1 == nblocks ? nt : (b + 1) * blocksize);
         const int64_t j0 = bs + (win - win_first[b]) * S;     // first output of this window
-        const int64_t w0 = j0 - (L - 1);                      // first input sample of the window
+        const int64_t w0 = j0 - HD;                           // first input sample of the window
+        const bool al = ((w0 & 1) == 0) && (((uintptr_t)d | (uintptr_t)out) & 15) == 0;
         __syncthreads();
         // ---- forward FFT, decimation in frequency, natural in -> bit-reversed out.  Radix-2 stages are
         // fused into passes whose points stay in registers: one radix-16 pass (4 stages) + radix-8 passes
@@ -176,6 +180,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
         auto winload1 = [&](int i) {
             const int64_t t = w0 + 2 * (int64_t)i;
             double2 v;
+            if (al && t >= bs && t + 1 < be) return *reinterpret_cast<const double2 *>(d + t);
             v.x = (t >= bs && t < be) ? d[t] : 0.0;
             v.y = (t + 1 >= bs && t + 1 < be) ? d[t + 1] : 0.0;
             return v;
@@ -195,8 +200,28 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                 const int pos = j & (q - 1);
                 const int i0 = ((j >> lq) << (lq + 4)) + pos;
                 double2 v[16];
+                if constexpr (!PAIR) {
 #pragma unroll
-                for (int m = 0; m < 16; ++m) v[m] = winload(i0 + m * q);
+                    for (int m = 0; m < 16; ++m) v[m] = winload(i0 + m * q);
+                } else {
+                    // both halves of the 2M-point window: explicit groups of 4 points with every load of a group
+                    // issued before its first use (a, b and the joining twiddle: 12 loads in flight per thread)
+#pragma unroll
+                    for (int g = 0; g < 16; g += 4) {
+                        double2 a[4], b[4], w[4];
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            a[m] = winload1(i0 + (g + m) * q);
+                            b[m] = winload1(i0 + (g + m) * q + FFT_M);
+                            w[m] = __ldg(tw2 + i0 + (g + m) * q);
+                        }
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            if (crank == 0) v[g + m] = make_double2(a[m].x + b[m].x, a[m].y + b[m].y);
+                            else v[g + m] = cmul(make_double2(a[m].x - b[m].x, a[m].y - b[m].y), w[m]);
+                        }
+                    }
+                }
                 butterfly16<false>(v, __ldg(tw + FFT_M / 4 + pos));
 #pragma unroll
                 for (int m = 0; m < 16; ++m) z(i0 + m * q) = v[m];
@@ -331,9 +356,11 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                     // the alias-free samples, window positions [L-1, L-1+S)
 #pragma unroll
                     for (int m = 0; m < 16; ++m) {
-                        const int r0 = 2 * (i0 + m * q) - (L - 1);        // output index of v.x within the window's S outputs
-                        if (r0 >= 0 && r0 < S && j0 + r0 < be) out[j0 + r0] = v[m].x;
-                        if (r0 + 1 >= 0 && r0 + 1 < S && j0 + r0 + 1 < be) out[j0 + r0 + 1] = v[m].y;
+                        const int r0 = 2 * (i0 + m * q) - HD;             // output index of v.x within the window's S outputs (even)
+                        if (r0 < 0 || r0 >= S) continue;
+                        if (al && j0 + r0 + 1 < be) { *reinterpret_cast<double2 *>(out + j0 + r0) = v[m]; continue; }
+                        if (j0 + r0 < be) out[j0 + r0] = v[m].x;
+                        if (j0 + r0 + 1 < be) out[j0 + r0 + 1] = v[m].y;
                     }
                 }
             }
@@ -344,17 +371,29 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
             cg::cluster_group cl = cg::this_cluster();
             cl.sync();                                                  // both inverse transforms are complete
             const double2 *rz = cl.map_shared_rank(zs, crank ^ 1u);
-            for (int n = threadIdx.x; n < FFT_M; n += FFT_THREADS) {
-                const int r0 = 2 * (n + (crank ? FFT_M : 0)) - (L - 1);
-                if (r0 + 1 < 0 || r0 >= S) continue;                    // aliased head / tail of the window
-                const double2 own = z(n), oth = rz[n + (n >> 3)];
-                double2 w = __ldg(tw2 + n);
-                w.y = -w.y;
-                const double2 U = crank ? oth : own, V = crank ? own : oth;
-                const double2 t = cmul(w, V);
-                const double2 r = crank ? make_double2(U.x - t.x, U.y - t.y) : make_double2(U.x + t.x, U.y + t.y);
-                if (r0 >= 0 && j0 + r0 < be) out[j0 + r0] = r.x;
-                if (r0 + 1 < S && j0 + r0 + 1 < be) out[j0 + r0 + 1] = r.y;
+            constexpr int NU = 8;                                        // points per thread and trip, loads first
+            for (int n0 = threadIdx.x; n0 < FFT_M; n0 += NU * FFT_THREADS) {
+                double2 own[NU], oth[NU], w[NU];
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    const int n = n0 + u * FFT_THREADS;
+                    own[u] = z(n);
+                    oth[u] = rz[n + (n >> 3)];
+                    w[u] = __ldg(tw2 + n);
+                }
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    const int n = n0 + u * FFT_THREADS;
+                    const int r0 = 2 * (n + (crank ? FFT_M : 0)) - HD;   // even
+                    if (r0 < 0 || r0 >= S) continue;                    // aliased head / tail of the window
+                    w[u].y = -w[u].y;
+                    const double2 U = crank ? oth[u] : own[u], V = crank ? own[u] : oth[u];
+                    const double2 t = cmul(w[u], V);
+                    const double2 r = crank ? make_double2(U.x - t.x, U.y - t.y) : make_double2(U.x + t.x, U.y + t.y);
+                    if (al && j0 + r0 + 1 < be) { *reinterpret_cast<double2 *>(out + j0 + r0) = r; continue; }
+                    if (j0 + r0 < be) out[j0 + r0] = r.x;
+                    if (j0 + r0 + 1 < be) out[j0 + r0 + 1] = r.y;
+                }
             }
             cl.sync();                                                  // the partner has read my half: the next window may overwrite it
         }
@@ -391,10 +430,10 @@ static int fft_launch(const double *coef, int nband, int64_t nblocks, int64_t bl
                       const double *d, double *out, int64_t nt, void *scratch, int init, int pair, cudaStream_t st) {
     CM2_REQUIRE(nt >= 0 && nblocks > 0 && nband >= 1, "bad sizes");
     CM2_REQUIRE(blk_start != nullptr || blocksize > 0, "blocksize must be > 0");
-    CM2_REQUIRE(2 * (nband - 1) < FFT_NF / 2, "band too wide for the 16384-point overlap-save window");
+    CM2_REQUIRE(pair == 0 || pair == 1, "pair must be 0 or 1");
+    CM2_REQUIRE(2 * (nband - 1) < (pair ? FFT_NF : FFT_NF / 2), "band too wide for the overlap-save window (4096 coefficients; 8192 in pair mode)");
     CM2_REQUIRE(scratch != nullptr && aligned(scratch, 16) && aligned(coef, 16), "scratch/coef must be 16-byte aligned");
     CM2_REQUIRE(d != out, "in-place Toeplitz apply is not supported");
-    CM2_REQUIRE(pair == 0 || pair == 1, "pair must be 0 or 1");
     if (nt == 0) return CM2_OK;
     double2 *tw = reinterpret_cast<double2 *>(scratch);
     double2 *tw2 = tw + FFT_M;
@@ -404,7 +443,8 @@ static int fft_launch(const double *coef, int nband, int64_t nblocks, int64_t bl
         k_fft_twiddles_pair<<<(FFT_M + 255) / 256, 256, 0, st>>>(tw2);
         CM2_LAUNCHED();
     }
-    const int S = (pair ? 2 * FFT_NF : FFT_NF) - 2 * (nband - 1);
+    const int HD = (nband - 1) + ((nband - 1) & 1);
+    const int S = ((pair ? 2 * FFT_NF : FFT_NF) - HD - (nband - 1)) & ~1;       // as in the kernel
     k_win_first<<<1, 1, 0, st>>>(nblocks, blocksize, blk_start, nt, S, win_first);
     CM2_LAUNCHED();
     const size_t smem = sizeof(double2) * (FFT_M + FFT_M / 8);

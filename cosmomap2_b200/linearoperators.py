@@ -189,7 +189,12 @@ TOEPLITZ_FFT_MIN_BAND = 48     # bands at least this wide go through the overlap
                                # crossover at 1e8 samples: direct 64 lags 2.29 ms, FFT 1.5 ms for any band <= 256)
 
 
-TOEPLITZ_FFT_PAIR_MIN_BAND = 2000   # from here on a 32768-sample window on a 2-CTA cluster beats two 16384-sample windows
+# Bands of at least this many coefficients use 32768-sample windows on 2-CTA clusters.  Measured per 1e8 samples,
+# one-CTA windows / cluster windows: 1.14 / 1.42 ms at 2048 coefficients, 1.45 / 1.51 at 3000, 1.62 / 1.63 at 4096 (the
+# 1.5x fewer window points per output are eaten by the joining stage over distributed shared memory and the second
+# read of the window), so the cluster mode is used where one CTA cannot hold the band at all: 4097..8192
+# coefficients (before: the direct kernel, ~50x slower there).
+TOEPLITZ_FFT_PAIR_MIN_BAND = 4097
 
 
 def _bit_reverse(M):
@@ -244,10 +249,10 @@ class _ToeplitzFFT(object):
 
     def __init__(self, band_host, nband):
         M = int(dv.call("cm2_toeplitz_fft_points"))
-        self.ok = 2 * (nband - 1) < M
+        self.pair = 1 if nband >= TOEPLITZ_FFT_PAIR_MIN_BAND else 0
+        self.ok = 2 * (nband - 1) < (2 * M if self.pair else M)
         if not self.ok:
             return
-        self.pair = 1 if nband >= TOEPLITZ_FFT_PAIR_MIN_BAND else 0
         coef = toeplitz_fft_tables(band_host, nband, M, pair=bool(self.pair))
         nb = coef.shape[0]
         self.coef = dv.to_dev_f64(coef.view(np.float64).reshape(-1))

@@ -127,7 +127,8 @@ int cm2_noise_toeplitz_apply(const double *band, int nband, int64_t nblocks, int
  * init != 0 on the first call with a given scratch (twiddle tables).
  * pair = 1: windows of 4M = 32768 samples on clusters of two CTAs (one 2M-point packed transform split by a
  * radix-2 stage: even frequencies in CTA 0, odd ones in CTA 1, joined over distributed shared memory), which
- * leaves 75 % of a window alias-free at 4096 coefficients instead of 50 %; coef is then
+ * leaves 75 % of a window alias-free at 4096 coefficients instead of 50 % and admits bands of up to 8192
+ * coefficients (2 (nband-1) < 2M); coef is then
  * [nblocks][2 (CTA c)][2][M] with entry p of CTA c = C[2 brev(p) + c] of the 2M-point transform. */
 int cm2_toeplitz_fft_points(void);
 int64_t cm2_toeplitz_fft_scratch_bytes(int64_t nblocks);

@@ -198,11 +198,12 @@ def test_krypy_style_arnoldi_and_two_level(cm):
 def test_toeplitz_fft_path_equals_direct_path(cm, pair_min):
     """Overlap-save FFT kernel vs the direct shared-memory kernel vs the oracle, multi-block, ragged blocks.
     ``pair_min = 2`` forces every band through the 32768-sample windows on 2-CTA clusters (by default only bands
-    of >= 2000 coefficients take them: the L = 4096 case below)."""
+    of more than 4096 coefficients take them: the L = 6000 case below)."""
     import oracle
     from cosmomap2_b200 import linearoperators as lo
     rng = np.random.default_rng(21)
-    for sizes, L in ((3 * [20000], 200), ([30000, 9000, 41000], 1000), ([50000], 4096), ([70001, 33000, 5], 3000)):
+    for sizes, L in ((3 * [20000], 200), ([30000, 9000, 41000], 1000), ([50000], 4096), ([70001, 33000, 5], 3000),
+                     ([60000, 21001], 6000)):
         nt = sum(sizes)
         v = rng.standard_normal(nt)
         t = [np.concatenate([[1.0 + rng.random()], -0.3 * rng.random(L - 1) / L]) for _ in sizes]
