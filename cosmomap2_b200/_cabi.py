@@ -82,7 +82,7 @@ SIGNATURES = {
     "cm2_pcg_reset": (_int, [_vp, _i64, _vp, _f64, _vp]),
     "cm2_pcg_update_p": (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "cm2_pcg_update_xr": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
-    "cm2_pcg_bd_reset": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _f64, _vp, _vp, _vp, _vp]),
+    "cm2_pcg_bd_reset": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _f64, _f64, _vp, _vp, _vp, _vp]),
     "cm2_pcg_bd_iter": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cm2_pcg_bd_update_p": (_int, [_vp, _vp, _i64, _vp, _vp]),
     "cm2_pcg_bd_update": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

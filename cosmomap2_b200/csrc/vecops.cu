@@ -147,10 +147,10 @@ __global__ void __launch_bounds__(VB) k_update_xr(const double *__restrict__ p, 
 // ---- M = M_BD path: the preconditioner apply is pixel-local, so z = M r and rho = r.z ride in
 // the same kernel that updates r (one pass over the pixel-domain vectors per iteration) ---------
 // start: z = M r, rho = r.z, |r|^2, flags.  With b != nullptr it also performs the x0 = 0 start of
-// the solve in the same pass: r = b, x = 0.
+// the solve in the same pass: r = b, x = 0, and folds SciPy's atol = max(atol, rtol ||b||) in (rtol > 0).
 template <int POL>
 __global__ void __launch_bounds__(VB) k_bd_reset(const double *__restrict__ inv, int64_t npix, double *__restrict__ r,
-                                                 double *__restrict__ z, double *__restrict__ scal, double atol,
+                                                 double *__restrict__ z, double *__restrict__ scal, double atol, double rtol,
                                                  const double *__restrict__ b, double *__restrict__ x,
                                                  double *__restrict__ p0) {
     __shared__ double red[32];
@@ -178,11 +178,14 @@ __global__ void __launch_bounds__(VB) k_bd_reset(const double *__restrict__ inv,
         }
     }
     if (finish_reduce<2>(s, red, tot)) {
+        const double atol_eff = (b != nullptr && rtol > 0.0) ? fmax(atol, rtol * sqrt(tot[1])) : atol;
         scal[0] = tot[0]; scal[1] = 0.0; scal[2] = 0.0; scal[4] = 0.0; scal[5] = 0.0;
         scal[3] = tot[1];
-        scal[6] = atol;
-        scal[7] = (sqrt(tot[1]) < atol) ? 1.0 : 0.0;
+        scal[6] = atol_eff;
+        scal[7] = (sqrt(tot[1]) < atol_eff || (b != nullptr && tot[1] == 0.0)) ? 1.0 : 0.0;
         scal[8] = 0.0;
+        scal[9] = 0.0;                      // the sharded solver's failure word
+        scal[10] = tot[1];                  // ||r||^2 at the start (||b||^2 for x0 = 0)
     }
 }
 
@@ -361,15 +364,15 @@ extern "C" int cm2_pcg_update_xr(const double *p, const double *q, double *x, do
 }
 
 extern "C" int cm2_pcg_bd_reset(const double *inv, int64_t npix, int pol, double *r, double *z, double *scal,
-                                double atol, const double *b, double *x, double *p0, cm2_stream_t stream) {
+                                double atol, double rtol, const double *b, double *x, double *p0, cm2_stream_t stream) {
     CM2_REQUIRE(npix >= 0 && pol >= 1 && pol <= 3, "bad npix/pol");
     CM2_REQUIRE(aligned(inv, 16), "inverse blocks must be 16-byte aligned");
     CM2_REQUIRE((b == nullptr) == (x == nullptr), "b and x go together");
     cudaStream_t st = as_stream(stream);
     const int g = vgrid(npix);
-    if (pol == 1) k_bd_reset<1><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol, b, x, p0);
-    else if (pol == 2) k_bd_reset<2><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol, b, x, p0);
-    else k_bd_reset<3><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol, b, x, p0);
+    if (pol == 1) k_bd_reset<1><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol, rtol, b, x, p0);
+    else if (pol == 2) k_bd_reset<2><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol, rtol, b, x, p0);
+    else k_bd_reset<3><<<g, VB, 0, st>>>(inv, npix, r, z, scal, atol, rtol, b, x, p0);
     CM2_LAUNCHED();
     return CM2_OK;
 }

@@ -313,7 +313,11 @@ class ShardedPCG(object):
         self.plo, self.phi = self.pix_lo[self.rank], self.pix_lo[self.rank + 1]
         self.elo, self.ehi = self.pol * self.plo, self.pol * self.phi
         nl = max(self.ehi - self.elo, 2)
-        self._xs, self._rs, self._zs, self._qs = (dv.zeros_f64(nl) for _ in range(4))
+        # x, r, z: full-length buffers of which this rank maintains its slice (elo is even: the views are 16-byte
+        # aligned); a start from a replicated right-hand side fills them locally, without any exchange
+        self._xf, self._rf, self._zf = (dv.zeros_f64(max(self.n, 2) + 2) for _ in range(3))
+        self._xs, self._rs, self._zs = (t[self.elo:self.elo + nl] for t in (self._xf, self._rf, self._zf))
+        self._qs = dv.zeros_f64(nl)
         self._inv = Mbd._inv_dev[6 * self.plo:6 * self.phi].clone() if self.phi > self.plo else dv.zeros_f64(6)
         self.scal = dv.zeros_f64(NSCAL)
         self._part = dv.empty_f64(int(dv.call("cm2_pcg_sharded_work_doubles")))
@@ -364,6 +368,16 @@ class ShardedPCG(object):
         ``b``: the full right-hand side (CUDA, replicated) or this rank's slice of it."""
         if x0 is not None:
             raise ValueError("ShardedPCG starts from x0 = 0")
+        if b.numel() == self.n and self.n != self.ehi - self.elo:
+            # replicated right-hand side: every rank computes r = b, z = M_BD b, the full first search direction
+            # p = z and the scalars by itself (same data, same kernel, same order: bit-identical on all ranks) --
+            # no all-gather, no flag round.  Safe without a barrier: the last kernel of this rank on the stream
+            # ended with the end barrier of its iteration, after which no peer writes this rank's p or reads its y.
+            self._b = b
+            dv.call("cm2_pcg_bd_reset", dv.ptr(self.bd._inv_dev), self.npix, self.pol, dv.ptr(self._rf), dv.ptr(self._zf),
+                    dv.ptr(self.scal), float(atol), float(rtol), dv.ptr(b), dv.ptr(self._xf), dv.ptr(self._p), dv.stream())
+            self._queued = 0
+            return
         bs = b if b.numel() == self.ehi - self.elo and self.world > 1 else self.slice_of(b)
         if bs.numel() == 0:
             bs = self._zs                      # an empty slice: any valid pointer

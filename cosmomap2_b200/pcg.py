@@ -97,14 +97,14 @@ class PCG(object):
         """x <- x0 (or 0), r <- b - A x0, device scalars reset.  ``b`` is a CUDA fp64 tensor.
         ``rtol`` > 0 folds SciPy's ``atol = max(atol, rtol*||b||)`` in (one synchronising norm)."""
         n, st = self.n, dv.stream
-        if rtol:
-            atol = max(float(atol), float(rtol) * self.norm(b))
         if x0 is None and self.bd is not None:
-            # x0 = 0 with M_BD: r = b, x = 0, z = M r, rho, ||r||^2 in ONE pass
+            # x0 = 0 with M_BD: r = b, x = 0, z = M r, rho, ||r||^2 and atol = max(atol, rtol ||b||) in ONE pass
             dv.call("cm2_pcg_bd_reset", dv.ptr(self.bd._inv_dev), self.bd._n, self.bd.pol, dv.ptr(self.r),
-                    dv.ptr(self.z), dv.ptr(self.scal), float(atol), dv.ptr(b), dv.ptr(self.x), dv.ptr(self.p), st())
+                    dv.ptr(self.z), dv.ptr(self.scal), float(atol), float(rtol), dv.ptr(b), dv.ptr(self.x), dv.ptr(self.p), st())
             self._queued = 0
             return
+        if rtol:
+            atol = max(float(atol), float(rtol) * self.norm(b))
         self.r.copy_(b)
         if x0 is None:
             self.x.zero_()
@@ -115,7 +115,7 @@ class PCG(object):
                 dv.call("cm2_axpby", -1.0, dv.ptr(ax), 1.0, dv.ptr(self.r), n, st())
         if self.bd is not None:
             dv.call("cm2_pcg_bd_reset", dv.ptr(self.bd._inv_dev), self.bd._n, self.bd.pol, dv.ptr(self.r),
-                    dv.ptr(self.z), dv.ptr(self.scal), float(atol), None, None, dv.ptr(self.p), st())
+                    dv.ptr(self.z), dv.ptr(self.scal), float(atol), 0.0, None, None, dv.ptr(self.p), st())
         else:
             dv.call("cm2_pcg_reset", dv.ptr(self.r), n, dv.ptr(self.scal), float(atol), st())
         self._queued = 0

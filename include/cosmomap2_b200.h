@@ -290,14 +290,15 @@ int cm2_pcg_update_xr(const double *p, const double *q, double *x, double *r, in
 /* M = M_BD fast path (the preconditioner is pixel-local, so z = M r and rho = r.z ride in the
  * kernel that updates r):
  *   bd_reset   : z = M r ; rho = r.z ; |r|^2 ; atol ; flags.  With b, x non-NULL the x0 = 0 start
- *                of the solve happens in the same pass (r = b, x = 0); pass both NULL otherwise
+ *                of the solve happens in the same pass (r = b, x = 0) and rtol > 0 folds SciPy's
+ *                atol = max(atol, rtol ||b||) in on the device; pass both NULL otherwise
  *   bd_update_p: p = z + beta p
  *   bd_update  : pq ; alpha ; x += alpha p ; r -= alpha q ; z = M r ; rho' ; beta' ; |r|^2 ; flags
  *   bd_iter    : bd_update followed by the NEXT iteration's p = z + beta' p, all in ONE cooperative
  *                launch (two grid barriers); with it an iteration is  q = A p ; bd_iter.  bd_reset's
  *                p0, when non-NULL, receives the first search direction p = z. */
 int cm2_pcg_bd_reset(const double *bd_inv, int64_t npix, int pol, double *r, double *z,
-                     double *scal, double atol, const double *b, double *x, double *p0,
+                     double *scal, double atol, double rtol, const double *b, double *x, double *p0,
                      cm2_stream_t stream);
 int cm2_pcg_bd_update_p(const double *z, double *p, int64_t n, double *scal, cm2_stream_t stream);
 int cm2_pcg_bd_update(const double *bd_inv, int64_t npix, int pol, const double *p,
