@@ -366,6 +366,7 @@ class ShardedPCG(object):
     def start(self, b, x0=None, atol=0.0, rtol=0.0):
         """x <- 0, r <- b, z = M r, p = z on every rank, rho, ||r||^2, atol_eff = max(atol, rtol ||b||).
         ``b``: the full right-hand side (CUDA, replicated) or this rank's slice of it."""
+        from . import _device as dv
         if x0 is not None:
             raise ValueError("ShardedPCG starts from x0 = 0")
         if b.numel() == self.n and self.n != self.ehi - self.elo:
