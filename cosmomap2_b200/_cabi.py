@@ -74,6 +74,7 @@ SIGNATURES = {
     "cm2_defl_z_apply": (_int, [_vp, _i64, _int, _i64, _vp, _f64, _f64, _vp, _vp, _vp]),
     "cm2_coarse_apply": (_int, [_vp, _int, _vp, _vp, _vp]),
     "cm2_m2_apply": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
+    "cm2_m2_banded_apply": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
     "cm2_dense_gram_work_doubles": (_i64, []),
     "cm2_dense_gram": (_int, [_vp, _i64, _int, _vp, _i64, _int, _i64, _vp, _i64, _vp, _vp]),
     "cm2_dense_combine": (_int, [_vp, _i64, _i64, _int, _vp, _i64, _int, _vp, _i64, _vp]),

@@ -188,6 +188,107 @@ extern "C" int cm2_coarse_apply(const double *Einv, int r, const double *v, doub
     return CM2_OK;
 }
 
+// ---- banded two-level apply ---------------------------------------------------------------------------
+// For a subdomain coarse space (deflationlib.scan_coarse_space) column k of Z is the intensity indicator of the
+// pixels of band k, so Z has ONE non-zero per pixel and A Z is banded: (A z_k) lives on band k and its two
+// neighbours.  The same y = M_BD (v - AZ c) + Z c, c = Einv Z^T v then reads band[npix] (int32) and
+// azb[npix][pol][3] (the entries of AZ in columns band-1, band, band+1, cyclic) instead of 3 r doubles per map
+// element: 172 B per IQU pixel instead of 2304 at r = 32.
+// Z^T v = per-band sums of the intensity component.  Deterministic: every warp adds into its own r accumulators in
+// program order (a warp whose 32 pixels span several bands handles them band by band), warps are added in warp
+// order, CTAs in CTA order by k_zt_final.
+constexpr int BAND_RMAX = 64;
+
+template <int POL>
+__global__ void __launch_bounds__(DB) k_band_sums(const int32_t *__restrict__ band, int64_t npix, int r,
+                                                  const double *__restrict__ v, double *__restrict__ partial) {
+    __shared__ double acc[DB / 32][BAND_RMAX];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = lane; k < r; k += 32) acc[warp][k] = 0.0;
+    __syncwarp();
+    const int64_t nchunks = (npix + 31) / 32;
+    const int64_t nwarps = (int64_t)gridDim.x * (DB / 32);
+    // a warp walks CONSECUTIVE chunks of 32 pixels (bands are contiguous ranges of the pixel order, so a whole
+    // stretch of chunks belongs to one band and is summed in registers before it touches shared memory)
+    const int64_t per = (nchunks + nwarps - 1) / nwarps;
+    const int64_t w = (int64_t)blockIdx.x * (DB / 32) + warp;
+    const int64_t c0 = w * per, c1 = c0 + per < nchunks ? c0 + per : nchunks;
+    int cur = -1;
+    double run = 0.0;
+    for (int64_t c = c0; c < c1; ++c) {
+        const int64_t p = c * 32 + lane;
+        const int b = p < npix ? __ldg(band + p) : -1;
+        const double x = (p < npix && b >= 0) ? v[(int64_t)POL * p] : 0.0;
+        const int b0 = __shfl_sync(0xffffffffu, b, 0);
+        if (__all_sync(0xffffffffu, b == b0 || b < 0) && b0 >= 0) {       // one band (the common case)
+            if (b0 != cur) {
+                if (cur >= 0) {
+                    const double t = warp_sum(run);
+                    if (lane == 0) acc[warp][cur] += t;
+                }
+                cur = b0;
+                run = 0.0;
+            }
+            run += x;
+        } else {                                                            // several bands inside these 32 pixels
+            if (cur >= 0) {
+                const double t = warp_sum(run);
+                if (lane == 0) acc[warp][cur] += t;
+                cur = -1;
+                run = 0.0;
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, b >= 0);
+            while (todo) {
+                const int leader = __ffs(todo) - 1;
+                const int bl = __shfl_sync(0xffffffffu, b, leader);
+                const double t = warp_sum(b == bl ? x : 0.0);
+                if (lane == 0) acc[warp][bl] += t;
+                todo &= ~__ballot_sync(0xffffffffu, b == bl);
+            }
+        }
+    }
+    if (cur >= 0) {
+        const double t = warp_sum(run);
+        if (lane == 0) acc[warp][cur] += t;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < r; k += DB) {
+        double t = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < DB / 32; ++ww) t += acc[ww][k];
+        partial[(int64_t)blockIdx.x * r + k] = t;
+    }
+}
+
+template <int POL>
+__global__ void __launch_bounds__(DB) k_m2_banded_finish(const int32_t *__restrict__ band, const double *__restrict__ azb, int r,
+                                                         const double *__restrict__ coef, const double *__restrict__ inv,
+                                                         int64_t npix, const double *__restrict__ v, double *__restrict__ y) {
+    extern __shared__ double sc[];
+    for (int k = threadIdx.x; k < r; k += DB) sc[k] = coef[k];
+    __syncthreads();
+    for (int64_t j = (int64_t)blockIdx.x * DB + threadIdx.x; j < npix; j += (int64_t)gridDim.x * DB) {
+        const int b = __ldg(band + j);
+        double u[POL], z[POL];
+        double c0 = 0.0;
+        if (b >= 0) {
+            const double cm = sc[b == 0 ? r - 1 : b - 1], cp = sc[b == r - 1 ? 0 : b + 1];
+            c0 = sc[b];
+            const double *a = azb + (int64_t)3 * POL * j;
+#pragma unroll
+            for (int k = 0; k < POL; ++k)
+                u[k] = v[(int64_t)POL * j + k] - (__ldcs(a + 3 * k) * cm + __ldcs(a + 3 * k + 1) * c0 + __ldcs(a + 3 * k + 2) * cp);
+        } else {
+#pragma unroll
+            for (int k = 0; k < POL; ++k) u[k] = v[(int64_t)POL * j + k];
+        }
+        bd_z<POL>(inv, j, u, z);
+        z[0] += c0;                                  // Z c: the intensity component of band b
+#pragma unroll
+        for (int k = 0; k < POL; ++k) y[(int64_t)POL * j + k] = z[k];
+    }
+}
+
 extern "C" int cm2_m2_apply(const double *Z, const double *AZ, int64_t n, int r, int64_t ld, const double *Einv,
                             const double *bd_inv, int64_t npix, int pol, const double *v, double *y, double *work,
                             cm2_stream_t stream) {
@@ -205,6 +306,32 @@ extern "C" int cm2_m2_apply(const double *Z, const double *AZ, int64_t n, int r,
     if (pol == 1) k_m2_finish<1><<<g2, DB, sm, st>>>(Z, AZ, r, ld, coef, bd_inv, npix, v, y);
     else if (pol == 2) k_m2_finish<2><<<g2, DB, sm, st>>>(Z, AZ, r, ld, coef, bd_inv, npix, v, y);
     else k_m2_finish<3><<<g2, DB, sm, st>>>(Z, AZ, r, ld, coef, bd_inv, npix, v, y);
+    CM2_LAUNCHED();
+    return CM2_OK;
+}
+
+
+// y = M_BD (v - AZ c) + Z c, c = Einv Z^T v for a subdomain coarse space given in banded form (see k_band_sums):
+// band[npix] = column of Z whose indicator contains the pixel (-1: none), azb[npix][pol][3] = AZ[pol*p + k, band-1 |
+// band | band+1 (cyclic)].  Requires pol = 1 or 3 (the indicator sits on the intensity component), 3 <= r <= 64.
+extern "C" int cm2_m2_banded_apply(const int32_t *band, const double *azb, int r, const double *Einv, const double *bd_inv,
+                                   int64_t npix, int pol, const double *v, double *y, double *work, cm2_stream_t stream) {
+    CM2_REQUIRE((pol == 1 || pol == 3) && r >= 3 && r <= BAND_RMAX && npix >= 0, "bad sizes (pol 1 or 3, 3 <= r <= 64)");
+    CM2_REQUIRE(work != nullptr && band != nullptr && azb != nullptr, "NULL argument");
+    if (npix == 0) return CM2_OK;
+    cudaStream_t st = as_stream(stream);
+    int g = dgrid(npix, 2);
+    if (g > DG_MAX) g = DG_MAX;
+    double *coef = work + (int64_t)DG_MAX * r;
+    if (pol == 1) k_band_sums<1><<<g, DB, 0, st>>>(band, npix, r, v, work);
+    else k_band_sums<3><<<g, DB, 0, st>>>(band, npix, r, v, work);
+    CM2_LAUNCHED();
+    k_zt_final<<<1, DB, sizeof(double) * r, st>>>(work, g, r, Einv, nullptr, coef);
+    CM2_LAUNCHED();
+    const int g2 = dgrid(npix, 8);
+    const size_t sm = sizeof(double) * r;
+    if (pol == 1) k_m2_banded_finish<1><<<g2, DB, sm, st>>>(band, azb, r, coef, bd_inv, npix, v, y);
+    else k_m2_banded_finish<3><<<g2, DB, sm, st>>>(band, azb, r, coef, bd_inv, npix, v, y);
     CM2_LAUNCHED();
     return CM2_OK;
 }

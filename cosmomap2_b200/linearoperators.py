@@ -1222,27 +1222,82 @@ class CoarseLO(lp.LinearOperator):
     mult_eig = mult
 
 
+M2_BANDED = True     # use the banded form of the two-level apply when Z is a subdomain (indicator) coarse space
+
+
+def _banded_coarse_space(Zd, AZd, pol):
+    """If ``Z`` is a subdomain coarse space -- every column the intensity indicator of a set of pixels, every pixel in
+    at most one column (deflationlib.scan_coarse_space) -- and ``A Z`` is confined to each column's own band and its two
+    cyclic neighbours, return ``(band, azb)``: band[npix] int32 (-1: pixel in no column) and azb[npix][pol][3], the
+    entries of AZ in columns band-1, band, band+1.  ``None`` otherwise (checked exactly, entry by entry: nothing is
+    dropped)."""
+    zt, azt = Zd._zt, AZd._zt                       # (r, n), row k = column k
+    r, n = zt.shape
+    if pol not in (1, 3) or r < 3 or r > 64 or n % pol or azt.shape != zt.shape:
+        return None
+    npix = n // pol
+    zi = zt[:, 0::pol]                               # (r, npix) intensity rows
+    ones = zi == 1.0
+    if not bool(((zi == 0.0) | ones).all().item()):
+        return None
+    cnt = ones.sum(dim=0)
+    if int(cnt.max().item()) > 1:
+        return None
+    if pol == 3 and (bool((zt[:, 1::3] != 0).any().item()) or bool((zt[:, 2::3] != 0).any().item())):
+        return None
+    band = torch.where(cnt > 0, ones.to(torch.int8).argmax(dim=0), torch.full_like(cnt, -1)).to(torch.int32)
+    del zi, ones
+    bl = band.to(torch.int64)
+    bsafe = torch.clamp(bl, min=0)
+    azb = torch.zeros((npix, pol, 3), dtype=torch.float64, device=zt.device)
+    nnz_kept = 0
+    for k in range(pol):
+        ak = azt[:, k::pol]                                                   # (r, npix)
+        for o in range(3):
+            col = torch.remainder(bsafe + (o - 1), r)
+            vals = ak.gather(0, col.unsqueeze(0)).squeeze(0)
+            vals = torch.where(bl >= 0, vals, torch.zeros_like(vals))
+            azb[:, k, o] = vals
+            nnz_kept += int((vals != 0).sum().item())
+    nnz_all = int((azt != 0).sum().item())
+    if nnz_kept != nnz_all:                          # some entry of AZ lies outside the three bands (or on an unbanded pixel)
+        return None
+    return band.contiguous(), azb.contiguous()
+
+
 class TwoLevelPreconditionerLO(lp.LinearOperator):
     """M_2lvl = M_BD (I - AZ E^-1 Z^T) + Z E^-1 Z^T as ONE fused apply.
 
     The reference composes it with operator algebra (src/test_M2_precond_onto_real_data.py:109-112),
     which evaluates ``E*Zd.T*v`` twice; the algebraic composition still works with the classes
-    above, and ``_fuse_two_level`` below rewrites it into this operator.
+    above, and ``_fuse_two_level`` below rewrites it into this operator.  When ``Z`` is a subdomain coarse space
+    (one non-zero per pixel, ``A Z`` banded: ``_banded_coarse_space``) the apply reads the band index and three
+    entries of AZ per map element instead of 3 r doubles (cm2_m2_banded_apply).
     """
 
     def __init__(self, Mbd, Zd, AZd, E):
         self.Mbd, self.Zd, self.AZd, self.E = Mbd, Zd, AZd, E
         n = Zd.nrows
         self._work = dv.empty_f64(int(dv.call("cm2_defl_work_doubles", int(Zd.ncols))))
+        self._banded = _banded_coarse_space(Zd, AZd, Mbd.pol) if (M2_BANDED and r_ok(Zd)) else None
         super(TwoLevelPreconditionerLO, self).__init__(n, n, matvec=self.mult, symmetric=True, device=True)
 
     def mult(self, v):
         Zd, M = self.Zd, self.Mbd
         y = torch.empty_like(v)
+        if self._banded is not None:
+            band, azb = self._banded
+            dv.call("cm2_m2_banded_apply", dv.ptr(band), dv.ptr(azb), Zd.ncols, dv.ptr(self.E._einv_dev), dv.ptr(M._inv_dev),
+                    M._n, M.pol, dv.ptr(v), dv.ptr(y), dv.ptr(self._work), _stream())
+            return y
         dv.call("cm2_m2_apply", dv.ptr(Zd._zt), dv.ptr(self.AZd._zt), Zd.nrows, Zd.ncols, Zd.nrows,
                 dv.ptr(self.E._einv_dev), dv.ptr(M._inv_dev), M._n, M.pol, dv.ptr(v), dv.ptr(y),
                 dv.ptr(self._work), _stream())
         return y
+
+
+def r_ok(Zd):
+    return 3 <= Zd.ncols <= 64 and Zd.nrows == Zd._zt.shape[1]
 
 
 def _is_zt(op, Zd=None):

@@ -252,6 +252,13 @@ int cm2_coarse_apply(const double *Einv, int r, const double *v, double *c,
 int cm2_m2_apply(const double *Z, const double *AZ, int64_t n, int r, int64_t ld,
                  const double *Einv, const double *bd_inv, int64_t npix, int pol,
                  const double *v, double *y, double *work, cm2_stream_t stream);
+/* The same apply for a SUBDOMAIN coarse space (column k of Z = intensity indicator of the pixels of band k, as built
+ * by cosmomap2_b200.scan_coarse_space): band[npix] = the pixel's column (-1: none), azb[npix][pol][3] = the entries of
+ * A Z in columns band-1, band, band+1 (cyclic) -- A z_k lives on band k and its neighbours.  172 B per IQU pixel
+ * instead of 3 r doubles per map element; pol = 1 or 3, 3 <= r <= 64; work as for cm2_m2_apply. */
+int cm2_m2_banded_apply(const int32_t *band, const double *azb, int r, const double *Einv,
+                        const double *bd_inv, int64_t npix, int pol, const double *v, double *y,
+                        double *work, cm2_stream_t stream);
 
 /* ---- a11 / a12: the dense tall-skinny contractions on the fp64 tensor cores (DMMA m8n8k4) ----------
  * Tall matrices are column-major with a leading dimension (every column contiguous).

@@ -114,3 +114,50 @@ def test_scan_coarse_space_deflates_the_offset_filter_modes(dense):
     (gb, gm, _, xg), (ob, om, Axo, xo) = out["gpu"], out["oracle"]
     assert abs(gb - ob) <= 1 and abs(gm - om) <= 1
     assert gm <= 0.4 * gb, "the scan-aligned coarse space must cut the iteration count (%d vs %d)" % (gm, gb)
+
+
+@pytest.mark.parametrize("pol", [1, 3])
+def test_banded_two_level_apply_equals_dense(dense, pol):
+    """The two-level apply in banded form (cm2_m2_banded_apply: band index + three entries of AZ per map element)
+    for the scan coarse space against the dense apply (cm2_m2_apply) on the same Z, AZ, E; a generic (dense) Z and
+    an A Z that leaves the three bands are refused by the exact check and keep the dense apply."""
+    import torch
+    import cosmomap2_b200 as cm
+    from cosmomap2_b200 import synthetic, linearoperators as lo, _device as dv
+    sc = synthetic.raster_scan(8 * 45000, nside=64, ndet=8, nx=60, ny=96, samples_per_pixel=8.0, seed=2, flag_turnarounds=True)
+    r = 12
+    pix = sc.pix.astype(np.int64)
+    pts = cm.ProcessTimeSamples(pix, sc.npix_full, obspix=np.arange(sc.npix_full), pol=pol, phi=sc.phi)
+    npix = pts.get_new_pixel[0]
+    n = pol * npix
+    P = cm.SparseLO(npix, sc.nt, pix, pol=pol, angle_processed=pts)
+    F = cm.FilterLO(sc.nt, [sc.sub_len, sc.sub_start], sc.ns, sc.ndet, pix)
+    Mbd = cm.BlockDiagonalPreconditionerLO(pts, npix, pol=pol)
+    A = P.T * F * P
+    Zt = cm.scan_coarse_space(P, r, sc.ns, A=A, Mbd=Mbd, smooth=2)
+    AZt = torch.stack([A._apply(Zt[i]) for i in range(r)])
+    E = cm.CoarseLO(Zt.t(), AZt.t(), r, apply="eig")
+    Zd, AZd = cm.DeflationLO(Zt.t()), cm.DeflationLO(AZt.t())
+    v = dv.to_dev_f64(np.random.default_rng(3).standard_normal(n))
+    out = {}
+    for banded in (True, False):
+        lo.M2_BANDED = banded
+        try:
+            M2 = Mbd * (cm.lp.IdentityOperator(n) - AZd * E * Zd.T) + Zd * E * Zd.T
+            out[banded] = M2._apply(v).clone()
+        finally:
+            lo.M2_BANDED = True
+    T = lo.TwoLevelPreconditionerLO(Mbd, Zd, AZd, E)
+    assert T._banded is not None, "the scan coarse space must be recognised as banded"
+    band = dv.to_host(T._banded[0])
+    assert band.min() >= 0 and band.max() == r - 1
+    err = float((out[True] - out[False]).abs().max() / out[False].abs().max())
+    assert err < 1e-13, "banded vs dense two-level apply: %.2e" % err
+    assert torch.equal(T._apply(v), T._apply(v)), "the banded apply is deterministic"
+    # refused: a dense Z; an AZ with an entry outside the three bands
+    Zr = cm.DeflationLO(torch.randn((r, n), dtype=torch.float64, device="cuda").t())
+    assert lo.TwoLevelPreconditionerLO(Mbd, Zr, AZd, E)._banded is None
+    AZbad = AZt.clone()
+    far = int(np.nonzero(band == 0)[0][0])
+    AZbad[r // 2, pol * far] = 1.0
+    assert lo.TwoLevelPreconditionerLO(Mbd, Zd, cm.DeflationLO(AZbad.t()), E)._banded is None
