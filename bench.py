@@ -240,7 +240,7 @@ def run_secondary(world, rank, out):
 
     # configs[2]: 1e9 samples / 64 detectors over 8 GPUs = 1.25e8 samples, 8 detectors per GPU
     run("configs[2]", workloads.correlated, nt=1.25e8, ndet=8, nband=4096, nside=512, nx=1000, ny=500, rtol=1e-6,
-        maxiter=300, time_iters=10, symmetry=False)
+        maxiter=300, time_iters=10, symmetry=False, two_level_r=32)
     # configs[3]: 4e9 samples over 8 GPUs = 5e8 per GPU, nside 1024, r = 32
     run("configs[3]", workloads.two_level, nt=5e8, nside=1024, nx=1600, ny=800, ndet=64, r=32, coarse="scan", smooth=2,
         rtol=1e-8, maxiter=2000)

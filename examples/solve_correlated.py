@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--rtol", type=float, default=1e-6)
     ap.add_argument("--maxiter", type=int, default=300)
     ap.add_argument("--time-iters", type=int, default=20, help="A applies timed with CUDA events after the solve")
+    ap.add_argument("--two-level", type=int, default=0, metavar="R",
+                    help="also solve with M_2lvl on an R-dimensional scan coarse space (cosmomap2_b200.scan_coarse_space)")
     args = ap.parse_args()
 
     import torch.distributed as dist
@@ -50,7 +52,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     from cosmomap2_b200 import workloads
     out = workloads.correlated(nt=args.nt, ndet=args.ndet, nband=args.nband, nside=args.nside, nx=args.nx, ny=args.ny,
-                               rtol=args.rtol, maxiter=args.maxiter, time_iters=args.time_iters)
+                               rtol=args.rtol, maxiter=args.maxiter, time_iters=args.time_iters, two_level_r=args.two_level)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

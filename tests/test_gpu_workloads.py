@@ -22,8 +22,11 @@ def _roofline_ok(r):
 
 
 def test_correlated_workload(wl):
-    out = wl.correlated(nt=4e5, ndet=4, nband=300, nside=128, nx=100, ny=60, rtol=1e-6, maxiter=400, time_iters=2)
+    out = wl.correlated(nt=4e5, ndet=4, nband=300, nside=128, nx=100, ny=60, rtol=1e-6, maxiter=400, time_iters=2,
+                        two_level_r=8)
     assert out["cg"]["info"] == 0 and out["cg"]["true_relres"] < 5e-6
+    m2 = out["M_2lvl_scan_space"]
+    assert m2["info"] == 0 and m2["iterations"] <= out["cg"]["iterations"] and m2["Ax_agreement"] < 1e-4
     assert out["plan"][-1] == "_FusedFilterP" and out["nband"] == 300
     assert out["symmetry"]["rel_to_norms"] < 1e-12
     _roofline_ok(out["roofline"])

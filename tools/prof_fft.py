@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Two launches of the FFT Toeplitz kernel with 1000 (16384-sample windows) and 4096 coefficients (32768-sample
-windows on 2-CTA clusters), 8 detectors x 2.5e6 samples (ncu target; development tool)."""
+"""Two launches of the FFT Toeplitz kernel at 4096 coefficients with 16384-sample windows and with 32768-sample
+windows on 2-CTA clusters, 8 detectors x 2.5e6 samples (ncu target; development tool)."""
 import os
 import sys
 
