@@ -1233,7 +1233,7 @@ def _banded_coarse_space(Zd, AZd, pol):
     dropped)."""
     zt, azt = Zd._zt, AZd._zt                       # (r, n), row k = column k
     r, n = zt.shape
-    if pol not in (1, 3) or r < 3 or r > 64 or n % pol or azt.shape != zt.shape:
+    if pol not in (1, 3) or r < 3 or r > 64 or n % pol or azt.shape != zt.shape or Zd.nrows != n:
         return None
     npix = n // pol
     zi = zt[:, 0::pol]                               # (r, npix) intensity rows
@@ -1279,7 +1279,7 @@ class TwoLevelPreconditionerLO(lp.LinearOperator):
         self.Mbd, self.Zd, self.AZd, self.E = Mbd, Zd, AZd, E
         n = Zd.nrows
         self._work = dv.empty_f64(int(dv.call("cm2_defl_work_doubles", int(Zd.ncols))))
-        self._banded = _banded_coarse_space(Zd, AZd, Mbd.pol) if (M2_BANDED and r_ok(Zd)) else None
+        self._banded = _banded_coarse_space(Zd, AZd, Mbd.pol) if M2_BANDED else None
         super(TwoLevelPreconditionerLO, self).__init__(n, n, matvec=self.mult, symmetric=True, device=True)
 
     def mult(self, v):
@@ -1294,10 +1294,6 @@ class TwoLevelPreconditionerLO(lp.LinearOperator):
                 dv.ptr(self.E._einv_dev), dv.ptr(M._inv_dev), M._n, M.pol, dv.ptr(v), dv.ptr(y),
                 dv.ptr(self._work), _stream())
         return y
-
-
-def r_ok(Zd):
-    return 3 <= Zd.ncols <= 64 and Zd.nrows == Zd._zt.shape[1]
 
 
 def _is_zt(op, Zd=None):
