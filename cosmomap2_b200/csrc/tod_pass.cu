@@ -610,12 +610,17 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter_mu(const int32_t *__re
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
     const int64_t ntiles = (nt + TILE - 1) / TILE;
-    int64_t tile;
+    // Three tiles are in flight per warp: the current one (registers), the next one (its TOD loads and its subscan
+    // mean are issued before the merge of the current tile) and the one after (only its subscan lookup: flag and
+    // segment index), so that mu[k0] of the next tile never waits for the load of k0 -- the lookups are a chain
+    // tile -> segment -> mean of dependent L2 accesses otherwise.
+    int64_t tile, tile2;
     int64_t v = ord.next((int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5), nwarps, ntiles, tile);
     if (tile < 0) return;
+    int64_t v2 = ord.next(v + nwarps, nwarps, ntiles, tile2);
     int p[K];
     double c[K], s[K];
-    int flag, k0;
+    int flag, k0, flag2 = 0, k02 = 0;
     double m0;
     {
         const int64_t t0 = tile * TILE + (int64_t)lane * K;
@@ -623,6 +628,7 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter_mu(const int32_t *__re
         if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
         flag = __ldg(sg.tile_flag + tile);
         k0 = __ldg(sg.tile_seg + tile);
+        if (tile2 >= 0) { flag2 = __ldg(sg.tile_flag + tile2); k02 = __ldg(sg.tile_seg + tile2); }
         m0 = flag == 1 ? __ldg(sg.mu + k0) : 0.0;
     }
     while (tile >= 0) {
@@ -662,28 +668,29 @@ __global__ void __launch_bounds__(BLOCK) k_amatvec_filter_mu(const int32_t *__re
         }
         RunState<POL> rs;
         {
-            double xv[K][POL], v[K];
+            double xv[K][POL], vv[K];
             gather_x<POL>(x, p, xv);
 #pragma unroll
-            for (int j = 0; j < K; ++j) v[j] = project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0) - mu[j];
+            for (int j = 0; j < K; ++j) vv[j] = project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0) - mu[j];
             run_compress<POL, POL>(y, p, [&](int j, double (&o)[POL]) {
-                if constexpr (POL == 1) { o[0] = v[j]; }
-                else if constexpr (POL == 2) { o[0] = v[j] * c[j]; o[1] = v[j] * s[j]; }
-                else { o[0] = v[j]; o[1] = v[j] * c[j]; o[2] = v[j] * s[j]; }
+                if constexpr (POL == 1) { o[0] = vv[j]; }
+                else if constexpr (POL == 2) { o[0] = vv[j] * c[j]; o[1] = vv[j] * s[j]; }
+                else { o[0] = vv[j]; o[1] = vv[j] * c[j]; o[2] = vv[j] * s[j]; }
             }, rs);
         }
-        int64_t nxt;
-        v = ord.next(v + nwarps, nwarps, ntiles, nxt);
-        if (nxt >= 0) {       // warp-uniform: next tile's TOD loads and subscan info overlap the merge
-            const int64_t t1 = nxt * TILE + (int64_t)lane * K;
+        int64_t tile3 = -1, v3 = v2;
+        int flag3 = 0, k03 = 0;
+        if (tile2 >= 0) {     // warp-uniform: the next tile's TOD loads and mean, the lookup of the tile after it
+            const int64_t t1 = tile2 * TILE + (int64_t)lane * K;
             load_pix(pix, t1, nt, p);
             if (POL > 1) { load_f64(cs, t1, nt, c); load_f64(sn, t1, nt, s); }
-            flag = __ldg(sg.tile_flag + nxt);
-            k0 = __ldg(sg.tile_seg + nxt);
-            m0 = flag == 1 ? __ldg(sg.mu + k0) : 0.0;
+            m0 = flag2 == 1 ? __ldg(sg.mu + k02) : 0.0;
+            v3 = ord.next(v2 + nwarps, nwarps, ntiles, tile3);
+            if (tile3 >= 0) { flag3 = __ldg(sg.tile_flag + tile3); k03 = __ldg(sg.tile_seg + tile3); }
         }
         run_merge<POL, POL>(y, rs);
-        tile = nxt;
+        tile = tile2; flag = flag2; k0 = k02;
+        tile2 = tile3; flag2 = flag3; k02 = k03; v2 = v3;
     }
 }
 
