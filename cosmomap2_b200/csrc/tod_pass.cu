@@ -857,59 +857,6 @@ __global__ void __launch_bounds__(BLOCK) k_pointing_filter_mu(const int32_t *__r
     }
 }
 
-// y = P^T F d for the offset filter given the subscan means of d (mu[k] = mean of d over the unflagged samples of
-// subscan k): y += P^T (d - mu_seg) over the unflagged samples inside subscans, nothing elsewhere -- the last two
-// factors of P.T*F*N*F*P in one pass over (d, pix, cos, sin), 28 B/sample instead of the 20 + 28 of F then P^T.
-// The means come from the Toeplitz kernel, which sums its own output per subscan (cm2_noise_toeplitz_fft_apply_segsum).
-template <int POL>
-__global__ void __launch_bounds__(BLOCK) k_pointing_t_filter_mu(const int32_t *__restrict__ pix, const double *__restrict__ cs,
-                                                                const double *__restrict__ sn, int64_t nt, SegInfo sg,
-                                                                const double *__restrict__ d, double *__restrict__ y) {
-    const int lane = threadIdx.x & 31;
-    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
-    const int64_t ntiles = (nt + TILE - 1) / TILE;
-    for (int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
-        const int flag = __ldg(sg.tile_flag + tile);
-        if (flag == 0) continue;               // warp-uniform: the whole tile lies in a gap
-        const int64_t t0 = tile * TILE + (int64_t)lane * K;
-        int p[K];
-        double c[K], s[K], v[K], mu[K];
-        load_pix(pix, t0, nt, p);
-        load_f64(d, t0, nt, v);
-        if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
-        const int k0 = __ldg(sg.tile_seg + tile);
-        if (flag == 1) {
-            const double m0 = __ldg(sg.mu + k0);
-#pragma unroll
-            for (int j = 0; j < K; ++j) mu[j] = m0;
-        } else {
-            int64_t k = k0;
-            while (k < sg.nseg && __ldg(sg.end + k) <= t0) ++k;
-            int64_t a = k < sg.nseg ? __ldg(sg.start + k) : INT64_MAX, b = k < sg.nseg ? __ldg(sg.end + k) : INT64_MAX;
-            double m = k < sg.nseg ? __ldg(sg.mu + k) : 0.0;
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-                const int64_t t = t0 + j;
-                while (k < sg.nseg && t >= b) {
-                    ++k;
-                    a = k < sg.nseg ? __ldg(sg.start + k) : INT64_MAX;
-                    b = k < sg.nseg ? __ldg(sg.end + k) : INT64_MAX;
-                    m = k < sg.nseg ? __ldg(sg.mu + k) : 0.0;
-                }
-                if (t < a || k >= sg.nseg) p[j] = -1;
-                mu[j] = m;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < K; ++j) v[j] -= mu[j];
-        run_scatter<POL, POL>(y, p, [&](int j, double (&o)[POL]) {
-            if constexpr (POL == 1) { o[0] = v[j]; }
-            else if constexpr (POL == 2) { o[0] = v[j] * c[j]; o[1] = v[j] * s[j]; }
-            else { o[0] = v[j]; o[1] = v[j] * c[j]; o[2] = v[j] * s[j]; }
-        });
-    }
-}
-
 // moments layout: mom[npix][6] = {h, c, s, c2, cs, s2}; pol=1 fills {h}, pol=2 {c2,cs,s2}, pol=3 all
 template <int POL>
 __global__ void __launch_bounds__(BLOCK) k_moments(const int32_t *__restrict__ pix, const double *__restrict__ cs,
@@ -1542,26 +1489,6 @@ extern "C" int cm2_pointing_filter_mu(const int32_t *pix, const double *c, const
     if (pol == 1) k_pointing_filter_mu<1><<<tod_grid(k_pointing_filter_mu<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, d);
     else if (pol == 2) k_pointing_filter_mu<2><<<tod_grid(k_pointing_filter_mu<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, d);
     else k_pointing_filter_mu<3><<<tod_grid(k_pointing_filter_mu<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, x, d);
-    CM2_LAUNCHED();
-    return CM2_OK;
-}
-
-/* y = P^T F d given the subscan means seg_mu of d (offset filter): one pass over d and the pointing */
-extern "C" int cm2_pointing_t_filter_mu(const int32_t *pix, const double *c, const double *s, int64_t nt, int pol,
-                                        const int64_t *seg_start, const int64_t *seg_end, const double *seg_mu,
-                                        const int32_t *tile_seg, const uint8_t *tile_flag, int64_t nseg, const double *d,
-                                        double *y, int64_t npix, cm2_stream_t stream) {
-    int rc = check_tod(pix, c, s, nt, pol);
-    if (rc) return rc;
-    CM2_REQUIRE(npix >= 0 && nseg >= 0, "negative size");
-    CM2_REQUIRE(aligned(d, 32), "d must be 32-byte aligned");
-    cudaStream_t st = as_stream(stream);
-    if (npix > 0) CM2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)npix * pol, st));
-    if (nt == 0 || npix == 0 || nseg == 0) return CM2_OK;
-    SegInfo sg{seg_start, seg_end, seg_mu, tile_seg, tile_flag, nseg};
-    if (pol == 1) k_pointing_t_filter_mu<1><<<tod_grid(k_pointing_t_filter_mu<1>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, d, y);
-    else if (pol == 2) k_pointing_t_filter_mu<2><<<tod_grid(k_pointing_t_filter_mu<2>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, d, y);
-    else k_pointing_t_filter_mu<3><<<tod_grid(k_pointing_t_filter_mu<3>, nt), BLOCK, 0, st>>>(pix, c, s, nt, sg, d, y);
     CM2_LAUNCHED();
     return CM2_OK;
 }

@@ -131,29 +131,6 @@ __device__ __forceinline__ void butterfly16(double2 (&v)[16], double2 w16) {
 }
 
 
-// Optional by-product of the last pass (SEG): seg_sum[k] += sum of the OUTPUT over the unflagged samples (pix >= 0) of
-// subscan k -- what the offset filter that follows the noise operator in P.T*F*N*F*P needs (FilterLO.mult
-// linearoperators.py:129-168: mean over the unflagged samples), so that F never makes its own pass over the TOD: the
-// noise operator fused with the subscan filter.  Tile tables as for cm2_pointing_filter_mu.
-struct FftSegOut {
-    const int32_t *pix;
-    const int64_t *seg_start, *seg_end;
-    const int32_t *tile_seg;
-    const uint8_t *tile_flag;
-    int64_t nseg;
-    double *seg_sum;
-};
-
-__device__ __forceinline__ int64_t fft_seg_of(const FftSegOut &so, int64_t t) {
-    const int64_t tile = t >> 8;
-    const int flag = __ldg(so.tile_flag + tile);
-    if (flag == 0) return -1;
-    int64_t k = __ldg(so.tile_seg + tile);
-    if (flag == 1) return k;
-    while (k < so.nseg && __ldg(so.seg_end + k) <= t) ++k;
-    return (k < so.nseg && t >= __ldg(so.seg_start + k)) ? k : -1;
-}
-
 // one CTA per window.  win_first[b] = first window index of noise block b (prefix, nblocks+1).
 // PAIR: a window of 2 NF = 32768 samples on a CLUSTER of two CTAs (one 16384-point complex transform split by one
 // radix-2 stage).  With z the packed window, W = exp(-2 pi i / 2M): CTA 0 transforms u[n] = z[n] + z[n+M] (the even
@@ -164,13 +141,13 @@ __device__ __forceinline__ int64_t fft_seg_of(const FftSegOut &so, int64_t t) {
 // the window is U[n] + conj(W^n) V[n] (first half, written by CTA 0) and U[n] - conj(W^n) V[n] (second half,
 // CTA 1): each CTA reads the other's result over distributed shared memory.  At 4096 coefficients 75 % of a window
 // is alias-free instead of 50 %.
-template <int FFT_THREADS, bool PAIR = false, bool SEG = false>
+template <int FFT_THREADS, bool PAIR = false>
 __global__ void __launch_bounds__(FFT_THREADS, 1)
     k_toeplitz_fft(const double2 *__restrict__ coef,   // [nblocks][2][M]: C1 then C2, indexed by PHYSICAL (bit-reversed) position
                    const double2 *__restrict__ tw, int L, int64_t nblocks, int64_t blocksize,
                    const int64_t *__restrict__ start, const int64_t *__restrict__ win_first,
                    const double *__restrict__ d, double *__restrict__ out, int64_t nt,
-                   const double2 *__restrict__ tw2, FftSegOut so) {
+                   const double2 *__restrict__ tw2) {
     extern __shared__ double2 zs[];   // M complex points, one pad element per 8 (bank-conflict relief)
 #define z(i) zs[(i) + ((i) >> 3)]
     // window positions [HD, HD + S) are alias-free; HD = L - 1 rounded up to even and S even, so that a window
@@ -385,44 +362,6 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                         if (j0 + r0 < be) out[j0 + r0] = v[m].x;
                         if (j0 + r0 + 1 < be) out[j0 + r0 + 1] = v[m].y;
                     }
-                    if constexpr (SEG) {
-                        // per-subscan sums of what was just written.  For a fixed m a warp holds 64 consecutive
-                        // samples, almost always of ONE subscan, and consecutive m (1024 samples apart) mostly stay
-                        // in it: the warp keeps a running per-lane sum while the subscan is the same for all its
-                        // lanes and issues one warp reduction + one atomic add when it changes.
-                        double run = 0.0;
-                        int64_t cur = -1;
-                        auto flush = [&]() {
-                            if (cur >= 0) {
-                                const double t = warp_sum(run);
-                                if ((threadIdx.x & 31) == 0) atomicAdd(so.seg_sum + cur, t);
-                            }
-                            cur = -1;
-                            run = 0.0;
-                        };
-#pragma unroll
-                        for (int m = 0; m < 16; ++m) {
-                            const int r0 = 2 * (i0 + m * q) - HD;
-                            const int64_t t = j0 + r0;
-                            const bool ok0 = r0 >= 0 && r0 < S && t < be, ok1 = r0 >= 0 && r0 < S && t + 1 < be;
-                            const int64_t ka = ok0 ? fft_seg_of(so, t) : -1, kb = ok1 ? fft_seg_of(so, t + 1) : -1;
-                            const double ca = (ka >= 0 && __ldg(so.pix + t) >= 0) ? v[m].x : 0.0;
-                            const double cb = (kb >= 0 && __ldg(so.pix + t + 1) >= 0) ? v[m].y : 0.0;
-                            const int64_t kw = __shfl_sync(0xffffffffu, ka, 0);
-                            if (__all_sync(0xffffffffu, ka == kw && kb == kw)) {
-                                if (kw != cur) {
-                                    flush();
-                                    cur = kw;
-                                }
-                                run += ca + cb;
-                            } else {
-                                flush();
-                                if (ka >= 0 && ca != 0.0) atomicAdd(so.seg_sum + ka, ca);
-                                if (kb >= 0 && cb != 0.0) atomicAdd(so.seg_sum + kb, cb);
-                            }
-                        }
-                        flush();
-                    }
                 }
             }
         }
@@ -488,8 +427,7 @@ extern "C" int64_t cm2_toeplitz_fft_scratch_bytes(int64_t nblocks) {
 }
 
 static int fft_launch(const double *coef, int nband, int64_t nblocks, int64_t blocksize, const int64_t *blk_start,
-                      const double *d, double *out, int64_t nt, void *scratch, int init, int pair, const FftSegOut *seg,
-                      cudaStream_t st) {
+                      const double *d, double *out, int64_t nt, void *scratch, int init, int pair, cudaStream_t st) {
     CM2_REQUIRE(nt >= 0 && nblocks > 0 && nband >= 1, "bad sizes");
     CM2_REQUIRE(blk_start != nullptr || blocksize > 0, "blocksize must be > 0");
     CM2_REQUIRE(pair == 0 || pair == 1, "pair must be 0 or 1");
@@ -529,20 +467,12 @@ static int fft_launch(const double *coef, int nband, int64_t nblocks, int64_t bl
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CM2_REQUIRE(seg == nullptr, "per-subscan sums are not available in pair mode");
         CM2_CUDA(cudaLaunchKernelEx(&cfg, k_toeplitz_fft<512, true>, cf, (const double2 *)tw, nband, nblocks, blocksize,
-                                    blk_start, (const int64_t *)win_first, d, out, nt, (const double2 *)tw2, FftSegOut{}));
+                                    blk_start, (const int64_t *)win_first, d, out, nt, (const double2 *)tw2));
         count_launch();
         return CM2_OK;
     }
     int grid = (int)(nwin_ub < sm_count() ? nwin_ub : sm_count());
-    if (seg != nullptr) {
-        CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft<512, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_toeplitz_fft<512, false, true><<<grid, 512, smem, st>>>(cf, tw, nband, nblocks, blocksize, blk_start, win_first, d, out,
-                                                                  nt, tw2, *seg);
-        CM2_LAUNCHED();
-        return CM2_OK;
-    }
     // threads per CTA (one CTA per SM): 512 by default -- the 16-point butterflies of the first / last pass
     // need the 128 registers per thread that 512 threads leave (measured at L = 4096: 1.81 ms vs 2.12 ms
     // with 1024 threads, which spill); CM2_FFT_THREADS=1024 selects the other instantiation
@@ -552,12 +482,10 @@ static int fft_launch(const double *coef, int nband, int64_t nblocks, int64_t bl
     }();
     if (threads == 512) {
         CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_toeplitz_fft<512><<<grid, 512, smem, st>>>(cf, tw, nband, nblocks, blocksize, blk_start, win_first, d, out, nt, tw2,
-                                                    FftSegOut{});
+        k_toeplitz_fft<512><<<grid, 512, smem, st>>>(cf, tw, nband, nblocks, blocksize, blk_start, win_first, d, out, nt, tw2);
     } else {
         CM2_CUDA(cudaFuncSetAttribute(k_toeplitz_fft<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_toeplitz_fft<1024><<<grid, 1024, smem, st>>>(cf, tw, nband, nblocks, blocksize, blk_start, win_first, d, out, nt, tw2,
-                                                      FftSegOut{});
+        k_toeplitz_fft<1024><<<grid, 1024, smem, st>>>(cf, tw, nband, nblocks, blocksize, blk_start, win_first, d, out, nt, tw2);
     }
     CM2_LAUNCHED();
     return CM2_OK;
@@ -570,18 +498,5 @@ static int fft_launch(const double *coef, int nband, int64_t nblocks, int64_t bl
 extern "C" int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
                                             const int64_t *blk_start, const double *d, double *out, int64_t nt,
                                             void *scratch, int init, int pair, cm2_stream_t stream) {
-    return fft_launch(coef, nband, nblocks, blocksize, blk_start, d, out, nt, scratch, init, pair, nullptr, as_stream(stream));
-}
-
-// The same apply (one-CTA windows) that ALSO adds, per subscan, the sum of its output over the unflagged samples to
-// seg_sum[nseg] (the caller zeroes it): the noise operator fused with the offset filter that follows it in
-// P.T*F*N*F*P -- mu_k = seg_sum[k] / (unflagged samples of subscan k), then cm2_pointing_t_filter_mu.
-extern "C" int cm2_noise_toeplitz_fft_apply_segsum(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
-                                                   const int64_t *blk_start, const double *d, double *out, int64_t nt,
-                                                   void *scratch, int init, const int32_t *pix, const int64_t *seg_start,
-                                                   const int64_t *seg_end, const int32_t *tile_seg, const uint8_t *tile_flag,
-                                                   int64_t nseg, double *seg_sum, cm2_stream_t stream) {
-    CM2_REQUIRE(pix && tile_seg && tile_flag && seg_sum && nseg >= 0 && (nseg == 0 || (seg_start && seg_end)), "NULL argument");
-    FftSegOut so{pix, seg_start, seg_end, tile_seg, tile_flag, nseg, seg_sum};
-    return fft_launch(coef, nband, nblocks, blocksize, blk_start, d, out, nt, scratch, init, 0, &so, as_stream(stream));
+    return fft_launch(coef, nband, nblocks, blocksize, blk_start, d, out, nt, scratch, init, pair, as_stream(stream));
 }

@@ -899,72 +899,6 @@ class _FusedFilterP(lp.LinearOperator):
         return d
 
 
-FUSE_PT_FILTER_TOEPLITZ = True   # [P.T, F_offset, N_toeplitz(FFT)] -> FFT kernel with per-subscan output sums + one P^T F pass
-
-
-class _FusedPtFilterToeplitz(lp.LinearOperator):
-    """``P^T F N`` for a wide-band Toeplitz ``N`` (one-CTA overlap-save FFT windows) and the offset filter: the FFT
-    kernel sums its own output per subscan while it writes it (cm2_noise_toeplitz_fft_apply_segsum), so the filter
-    needs no pass of its own, and ``P^T (N d - mean)`` is one pass over N d and the pointing
-    (cm2_pointing_t_filter_mu) -- the noise operator fused with the subscan filter, the first three factors of
-    configs[2]'s ``P.T*F*N*F*P``.  Falls back to the chain when the run table or the FFT path is not available."""
-
-    def __init__(self, P, F, N):
-        self.P, self.F, self.N = P, F, N
-        self._runs = None
-        self._inv_cnt = None
-        super(_FusedPtFilterToeplitz, self).__init__(P.nrows, P.pol * P.ncols, matvec=self._run, symmetric=False, device=True)
-
-    def _run(self, d):
-        P, F, N = self.P, self.F, self.N
-        fft = N._toeplitz_state()
-        if self._runs is None:
-            self._runs = _filter_runs(P, F)
-        rt = self._runs
-        if not rt or fft is None or not fft.ok or fft.pair:
-            return P.T._apply(F._apply(N._apply(d)))
-        if self._inv_cnt is None:
-            # unflagged samples per subscan from the run table (column n of run_mom), once
-            n_run = rt["run_mom"].view(-1, 3)[:, 0]
-            csum = torch.cat([torch.zeros(1, dtype=torch.float64, device=n_run.device), torch.cumsum(n_run, 0)])
-            first = rt["seg_first"][:F.nseg]
-            cnt = csum[first + rt["seg_nruns"][:F.nseg].to(torch.int64)] - csum[first]
-            self._inv_cnt = torch.where(cnt > 0, 1.0 / torch.clamp(cnt, min=1.0), torch.zeros_like(cnt))
-            self._seg_sum = dv.zeros_f64(max(F.nseg, 1))
-            self._mu2 = dv.zeros_f64(max(F.nseg, 1))
-        self._seg_sum.zero_()
-        out = dv.empty_f64(P.nrows)
-        nb, bs, startp = N._blk.args()
-        dv.call("cm2_noise_toeplitz_fft_apply_segsum", dv.ptr(fft.coef), fft.nband, nb, bs, startp, dv.ptr(d), dv.ptr(out),
-                P.nrows, dv.ptr(fft.scratch), fft.init, dv.ptr(P._pix_dev), dv.ptr(F._seg_start), dv.ptr(F._seg_end),
-                dv.ptr(rt["tile_seg"]), dv.ptr(rt["tile_flag"]), F.nseg, dv.ptr(self._seg_sum), _stream())
-        fft.init = 0
-        torch.mul(self._seg_sum[:F.nseg], self._inv_cnt, out=self._mu2[:F.nseg])
-        y = dv.out_f64(P.ncols * P.pol)
-        dv.call("cm2_pointing_t_filter_mu", dv.ptr(P._pix_dev), dv.ptr(P._cos_dev), dv.ptr(P._sin_dev), P.nrows, P.pol,
-                dv.ptr(F._seg_start), dv.ptr(F._seg_end), dv.ptr(self._mu2), dv.ptr(rt["tile_seg"]), dv.ptr(rt["tile_flag"]),
-                F.nseg, dv.ptr(out), dv.ptr(y), P.ncols, _stream())
-        return y
-
-
-@lp.register_fuser
-def _fuse_pt_filter_toeplitz(factors):
-    """[P.T, F, N, ...] with the offset filter and a wide-band Toeplitz N: P^T F N becomes the FFT kernel (with
-    per-subscan sums of its output) plus ONE P^T F pass."""
-    if not (fusion_enabled and FUSE_PT_FILTER_TOEPLITZ):
-        return None
-    for i in range(len(factors) - 2):
-        Pt, F, N = factors[i], factors[i + 1], factors[i + 2]
-        if not _is_pt(Pt):
-            continue
-        P = Pt._adjoint_of
-        if (isinstance(F, FilterLO) and F.poly_order == 0 and F._sorted and F.nseg > 0 and F.shape[0] == P.nrows
-                and F._pix_dev.data_ptr() == P._pix_dev.data_ptr() and isinstance(N, BlockLO) and N.isoffdiag
-                and TOEPLITZ_FFT_MIN_BAND <= N._nband < TOEPLITZ_FFT_PAIR_MIN_BAND and N.shape[0] == P.nrows):
-            return factors[:i] + [_FusedPtFilterToeplitz(P, F, N)] + factors[i + 3:]
-    return None
-
-
 class _FusedToeplitzA(lp.LinearOperator):
     """P^T N P for a short-band Toeplitz N = BlockLO(offdiag=True) (the reference tests' composition,
     tests/test_2level_preconditioner.py:16-29) as ONE kernel without a TOD temporary."""

@@ -135,22 +135,6 @@ int64_t cm2_toeplitz_fft_scratch_bytes(int64_t nblocks);
 int cm2_noise_toeplitz_fft_apply(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
                                  const int64_t *blk_start, const double *d, double *out,
                                  int64_t nt, void *scratch, int init, int pair, cm2_stream_t stream);
-/* The same apply (one-CTA windows) that also adds, per subscan, the sum of its OUTPUT over the unflagged samples
- * (pix >= 0) to seg_sum[nseg] (zeroed by the caller): the noise operator fused with the offset filter that follows
- * it in P.T*F*N*F*P (FilterLO.mult interfaces/linearoperators.py:129-168 over ToeplitzLO.mult :582-595) -- F never
- * makes its own pass over the TOD: mu_k = seg_sum[k] / (unflagged samples of subscan k), then
- * cm2_pointing_t_filter_mu.  Tile tables as for cm2_pointing_filter_mu. */
-int cm2_noise_toeplitz_fft_apply_segsum(const double *coef, int nband, int64_t nblocks, int64_t blocksize,
-                                        const int64_t *blk_start, const double *d, double *out, int64_t nt,
-                                        void *scratch, int init, const int32_t *pix, const int64_t *seg_start,
-                                        const int64_t *seg_end, const int32_t *tile_seg, const uint8_t *tile_flag,
-                                        int64_t nseg, double *seg_sum, cm2_stream_t stream);
-/* y = P^T F d for the offset filter given the subscan means seg_mu of d: y = P^T (d - mu_seg) over the unflagged
- * samples inside subscans, in one pass over d and the pointing (28 B/sample instead of F then P^T) */
-int cm2_pointing_t_filter_mu(const int32_t *pix, const double *cos2phi, const double *sin2phi,
-                             int64_t nt, int pol, const int64_t *seg_start, const int64_t *seg_end,
-                             const double *seg_mu, const int32_t *tile_seg, const uint8_t *tile_flag,
-                             int64_t nseg, const double *d, double *y, int64_t npix, cm2_stream_t stream);
 /* subscan offset filter (FilterLO.mult :129-168): out = 0; for each segment [seg_start[k],
  * seg_end[k]): mu = mean of d over unflagged samples; skipped if none; out = d - mu */
 int cm2_filter_offset_apply(const int32_t *pix, const int64_t *seg_start, const int64_t *seg_end,
