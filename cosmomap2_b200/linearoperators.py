@@ -29,8 +29,6 @@ class SparseLO(lp.LinearOperator):
     (the reference aliases the caller's array, :531).
     """
 
-    _graph_safe = True
-
     def __init__(self, n, m, pix_samples, pol=1, angle_processed=None):
         dv.require_cuda()
         self.ncols = int(n)
@@ -172,8 +170,6 @@ class _Blocks(object):
 class ToeplitzLO(lp.LinearOperator):
     """Symmetric banded Toeplitz block, zero boundaries -- interfaces/linearoperators.py:560-602."""
 
-    _graph_safe = True
-
     def __init__(self, a, size):
         self.array = a
         self._blocks = _Blocks([0, int(size)])
@@ -289,8 +285,6 @@ class WeightingLO(lp.LinearOperator):
     """Per-(CES, detector) scalar weight -- interfaces/linearoperators.py:604-625.
     The reference scales ``d`` IN PLACE and returns it (:613); so does this."""
 
-    _graph_safe = True
-
     def __init__(self, bolos_per_ces, samples_per_bolopair, weights):
         self.ndet_pairs = bolos_per_ces
         self.nsample_per_pair = samples_per_bolopair
@@ -321,8 +315,6 @@ class WeightingLO(lp.LinearOperator):
 class BlockDiagonalLinearOperator(lp.LinearOperator):
     """Generic block-diagonal of operators -- interfaces/blkop.py:140-242 (kept for API
     compatibility; BlockLO overrides the application with single-launch kernels)."""
-
-    _graph_safe = True
 
     def __init__(self, blocks, **kwargs):
         try:
@@ -484,8 +476,6 @@ class FilterLO(lp.LinearOperator):
     construction into one list of segments [start, end) and ONE kernel launch applies them all.
     """
 
-    _graph_safe = True
-
     def __init__(self, size, subscan_nsample, samples_per_bolopair, bolos_per_ces, pix_samples,
                  poly_order=0, npool=4):
         dv.require_cuda()
@@ -606,8 +596,6 @@ class _FusedWhiteA(lp.LinearOperator):
       time-domain structure, so the pass runs over a copy of the pointing SORTED BY PIXEL with per-sample
       weights instead (28 B/sample, every pixel one run: 0.45 ms).  Set-up: one stable sort; memory: a second
       copy of the pointing."""
-
-    _graph_safe = True
 
     def __init__(self, P, N):
         self.P, self.N = P, N
@@ -749,8 +737,6 @@ class _FusedFilterA(lp.LinearOperator):
     is built on the device at first use and is used when the segments are sorted and the scan has
     runs (>= 2 samples per run on average).  Otherwise: the two-pass kernel cm2_amatvec_filter."""
 
-    _graph_safe = True
-
     def __init__(self, P, F):
         self.P, self.F = P, F
         self._runs = None
@@ -847,8 +833,6 @@ class _FusedPolyFilterA(lp.LinearOperator):
     ``FILTER_POLY_RUN_TABLE`` (experimental) the well-conditioned subscans go through the single-TOD-pass
     scheme of the offset filter instead: coefficients from a Legendre run table, then one streaming pass."""
 
-    _graph_safe = True
-
     def __init__(self, P, F):
         self.P, self.F = P, F
         self._runs = None
@@ -894,8 +878,6 @@ class _FusedFilterP(lp.LinearOperator):
     d = P x - mu_seg is written directly (the head of chains such as P.T*F*N*F*P).  Falls back to the
     two operators when the run table cannot be used (unsorted subscans, run-free pointing)."""
 
-    _graph_safe = True
-
     def __init__(self, P, F):
         self.P, self.F = P, F
         self._runs = None
@@ -920,8 +902,6 @@ class _FusedFilterP(lp.LinearOperator):
 class _FusedToeplitzA(lp.LinearOperator):
     """P^T N P for a short-band Toeplitz N = BlockLO(offdiag=True) (the reference tests' composition,
     tests/test_2level_preconditioner.py:16-29) as ONE kernel without a TOD temporary."""
-
-    _graph_safe = True
 
     def __init__(self, P, N):
         self.P, self.N = P, N
@@ -1018,8 +998,6 @@ def _moments_from(CES, n, pol):
 
 
 class _PixelBlockLO(lp.LinearOperator):
-    _graph_safe = True
-
     def _attrs_from(self, CES, n, pol):
         self.size = pol * n
         self.pixels = np.arange(n)
@@ -1173,8 +1151,6 @@ def _columns_dev(z):
 class DeflationLO(lp.LinearOperator):
     """Z y and Z^T x -- interfaces/linearoperators.py:1029-1065."""
 
-    _graph_safe = True
-
     def __init__(self, z):
         dv.require_cuda()
         self.nrows, self.ncols = z.shape
@@ -1209,8 +1185,6 @@ class CoarseLO(lp.LinearOperator):
     eigenvalues |lambda/lambda_max| < 1e-6 discarded, :994-1015) is host LAPACK, and the resulting
     r x r inverse is applied on the device.
     """
-
-    _graph_safe = True
 
     def __init__(self, Z, Az, r, apply="LU"):
         dv.require_cuda()
@@ -1300,8 +1274,6 @@ class TwoLevelPreconditionerLO(lp.LinearOperator):
     (one non-zero per pixel, ``A Z`` banded: ``_banded_coarse_space``) the apply reads the band index and three
     entries of AZ per map element instead of 3 r doubles (cm2_m2_banded_apply).
     """
-
-    _graph_safe = True
 
     def __init__(self, Mbd, Zd, AZd, E):
         self.Mbd, self.Zd, self.AZd, self.E = Mbd, Zd, AZd, E

@@ -224,31 +224,6 @@ class _ProductLO(LinearOperator):
         return x
 
 
-def graph_safe(op):
-    """True if applying ``op`` -- after its first use, which may build tables -- only enqueues work on the current
-    stream (no host synchronisation, no host-side arithmetic on device data), so that a PCG iteration over it can be
-    captured in a CUDA graph.  Device operator classes opt in with the class attribute ``_graph_safe``; compositions
-    are safe when their parts are; operators wrapping host callables are not."""
-    if op is None:
-        return True
-    if isinstance(op, _ProductLO):
-        return all(graph_safe(f) for f in op.planned())
-    if isinstance(op, _SumLO):
-        if op._fused is False:
-            return False                          # not applied yet: the fused replacement is decided at first use
-        return graph_safe(op._fused) if op._fused is not None else (graph_safe(op.a) and graph_safe(op.b))
-    if isinstance(op, _ScaledLO):
-        return graph_safe(op.op)
-    if isinstance(op, (IdentityOperator, DiagonalOperator)):
-        return True
-    if not isinstance(op, LinearOperator) or not op._device_native:
-        return False
-    if getattr(op, "_graph_safe", False):
-        return True
-    adj = getattr(op, "_adjoint_of", None)      # the transpose of a device operator is a plain LinearOperator
-    return adj is not None and adj is not op and bool(getattr(adj, "_graph_safe", False))
-
-
 _sum_fusers = []
 
 

@@ -28,17 +28,6 @@ from . import linop as lp
 
 NSCAL = 16
 
-# A solve that is still running after this many iterations captures ONE iteration in a CUDA graph and replays it
-# from then on: per iteration one graph launch instead of 4-8 kernel launches through ctypes + torch calls, which
-# is what bounds small problems (configs[0]: ~30 us of GPU work against ~150 us of host work per iteration).  Only
-# for operators that are capturable (linop.graph_safe) on one GPU; CM2_PCG_GRAPH=0 disables it.
-GRAPH_AFTER = 8
-
-
-def _graphs_enabled():
-    import os
-    return os.environ.get("CM2_PCG_GRAPH", "1") != "0"
-
 
 class _Identity(object):
     def _apply(self, x):
@@ -79,8 +68,6 @@ class PCG(object):
         self._coop = True
         self._queued = 0          # iterations launched since start()
         self._snap = 0            # snapshots enqueued
-        self._graph = None        # a captured iteration (capture_iteration)
-        self._graph_tried = False
 
     # ---- scalars -----------------------------------------------------------------------------
     def norm(self, v):
@@ -138,39 +125,8 @@ class PCG(object):
         f = getattr(self.A, "apply_transient", None)
         return f(p) if f is not None else self.A._apply(p)
 
-    def can_capture(self):
-        """True if one iteration may be captured in a CUDA graph: A and M enqueue device work only."""
-        return (_graphs_enabled() and not self._graph_tried and lp.graph_safe(self.A) and
-                (isinstance(self.M, _Identity) or lp.graph_safe(self.M)))
-
-    def capture_iteration(self):
-        """Capture ONE iteration in a CUDA graph (nothing runs during the capture); ``step_async`` replays it from
-        then on.  Call after a few eager iterations: lazily built tables and buffers then exist, and the graph's
-        private memory pool holds the iteration's temporaries at fixed addresses.  Returns False (and stays eager)
-        if the capture fails."""
-        self._graph_tried = True
-        g = torch.cuda.CUDAGraph()
-        try:
-            with torch.cuda.graph(g):
-                self._step_eager()
-        except Exception as e:                                   # noqa: BLE001 -- stay on the eager path
-            import warnings
-            torch.cuda.synchronize()
-            warnings.warn("PCG iteration could not be captured in a CUDA graph (%s): staying eager" % (e,))
-            return False
-        self._graph = g
-        return True
-
     def step_async(self):
         """Queue one iteration (no host synchronisation)."""
-        if self._graph is not None:
-            self._graph.replay()
-            self._queued += 1
-            return
-        self._step_eager()
-        self._queued += 1
-
-    def _step_eager(self):
         n, st = self.n, dv.stream
         if self.bd is not None:
             # p already holds this iteration's search direction (bd_reset / the previous bd_iter)
@@ -191,6 +147,7 @@ class PCG(object):
             q = self._apply_A(self.p)
             dv.call("cm2_pcg_update_xr", dv.ptr(self.p), dv.ptr(q), dv.ptr(self.x), dv.ptr(self.r), n,
                     dv.ptr(self.scal), st())
+        self._queued += 1
 
     def tick(self):
         """Enqueue an async snapshot of the device scalars and return the PREVIOUS snapshot
@@ -212,8 +169,6 @@ def _run_loop(solver, maxiter, residuals):
     s0 = solver._snap
     solver._snapshot()                      # snapshot s0: state before iteration 0
     for it in range(maxiter):
-        if it == GRAPH_AFTER and getattr(solver, "can_capture", None) is not None and solver.can_capture():
-            solver.capture_iteration()      # iterations from here on are one graph launch each
         solver.step_async()                 # no-op on the device if `done` was already raised
         solver._snapshot()                  # snapshot s0+it+1: state after iteration `it`
         rnorm, done, _iters = solver._read_snapshot(s0 + it)   # state at the TOP of iteration `it`

@@ -219,49 +219,3 @@ def test_config0_from_a_ces_file(cm, tmp_path):
         for k, a in enumerate(h1):
             assert np.count_nonzero(a) <= n1
             gc.exact(a[np.asarray(o1)], x1[k::pol], "HEALPix map %d is a permutation of x" % k)
-
-
-def test_pcg_iteration_as_a_cuda_graph(cm):
-    """A solve that is still running after pcg.GRAPH_AFTER iterations captures one iteration in a CUDA graph and
-    replays it (one launch per iteration instead of 4-8): same iteration count, same solution and residual history as
-    the eager loop, with M_BD (cooperative tail kernel inside the graph) and with the two-level preconditioner
-    (generic tail); operators that wrap host callables are not captured."""
-    import torch
-    from cosmomap2_b200 import synthetic, pcg, _device as dv, linop
-    sc = synthetic.raster_scan(8 * 30000, nside=64, ndet=8, nx=48, ny=24, samples_per_pixel=8.0, seed=1, flag_turnarounds=True)
-    pol = 3
-    npix, P, Mbd, A, b, pts = _build(cm, sc, pol, filt=True)
-    n = pol * npix
-    bd = dv.to_dev_f64(b)
-    Zt = cm.scan_coarse_space(P, 8, sc.ns, A=A, Mbd=Mbd)
-    AZt = torch.stack([A._apply(Zt[i]) for i in range(8)])
-    E = cm.CoarseLO(Zt.t(), AZt.t(), 8, apply="eig")
-    Zd, AZd = cm.DeflationLO(Zt.t()), cm.DeflationLO(AZt.t())
-    M2 = Mbd * (cm.lp.IdentityOperator(n) - AZd * E * Zd.T) + Zd * E * Zd.T
-    for M in (Mbd, M2):
-        runs = {}
-        for graphs in (True, False):
-            old = pcg.GRAPH_AFTER
-            pcg.GRAPH_AFTER = 3 if graphs else 10 ** 9
-            try:
-                s = pcg.PCG(A, M, n)
-                atol = 1e-9 * s.norm(bd)
-                s.start(bd, None, atol)
-                res = []
-                info = pcg._run_loop(s, 300, res)
-                torch.cuda.synchronize()
-                assert (s._graph is not None) == graphs
-                runs[graphs] = (info, np.array(res), dv.to_host(s.x))
-            finally:
-                pcg.GRAPH_AFTER = old
-        (i1, r1, x1), (i0, r0, x0) = runs[True], runs[False]
-        assert i1 == 0 and i0 == 0 and len(r1) == len(r0) and len(r1) > 6
-        assert np.max(np.abs(r1 - r0)) <= 1e-10 * r0[0]
-        gc.close(x1, x0, rtol=1e-10, what="graph-replayed PCG vs eager PCG")
-    # a host callable in the chain: not capturable, the loop stays eager and still solves
-    Ah = cm.lp.LinearOperator(n, n, matvec=lambda v: A * v, symmetric=True)
-    assert not linop.graph_safe(Ah) and linop.graph_safe(A) and linop.graph_safe(M2) and linop.graph_safe(Mbd)
-    xh, ih = cm.cg(Ah, b, M=Mbd, rtol=1e-9, maxiter=300)
-    xg, ig = cm.cg(A, b, M=Mbd, rtol=1e-9, maxiter=300)
-    assert ih == 0 and ig == 0
-    gc.close(xh, xg, rtol=1e-7, what="host-callable operator, eager loop")
