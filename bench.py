@@ -517,6 +517,16 @@ def main():
                 secondary["sensitivity"] = run_sensitivity()
             except Exception as e:                      # noqa: BLE001
                 secondary["sensitivity"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            try:
+                # configs[0], the reference's own CPU-runnable case, on the GPU and (the checker, on the host cores)
+                # through the oracle: the one place besides cpu_baseline where bench.py runs oracle/
+                import oracle
+                from oracle import cloops
+                from cosmomap2_b200 import workloads
+                cloops.build()
+                secondary["configs[0]"] = workloads.real_ces_script(cpu_oracle=oracle)
+            except Exception as e:                      # noqa: BLE001
+                secondary["configs[0]"] = {"error": "%s: %s" % (type(e).__name__, e)}
         run_secondary(world, rank, secondary)
         timer.cancel()
     if line is not None:

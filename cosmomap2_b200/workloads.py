@@ -149,6 +149,51 @@ def _close(A):
 
 
 # -------------------------------------------------------------------------------------------------------
+def real_ces_script(cpu_oracle=None, seed=0):
+    """configs[0]: the reference's real-data script (src/test_BD_precond_onto_real_data.py:8-61) on the stand-in for
+    its absent CES file (synthetic.config_c1: 4 detector pairs, 6.26e6 samples, IQU nside 128, flagged turnarounds):
+    ProcessTimeSamples -> SparseLO -> BlockDiagonalPreconditionerLO -> A = P^T P -> cg(tol=1e-3, maxiter=10), host
+    arrays in and out, timed as a whole.  ``cpu_oracle``: the oracle module (bench.py passes it; the product never
+    imports it) to run the same script on the host cores for the comparison."""
+    import scipy.sparse.linalg as spla
+    import cosmomap2_b200 as cm
+    from cosmomap2_b200 import synthetic
+    sc = synthetic.config_c1(seed=seed)
+    pol = 3
+
+    def script(impl, solver):
+        pix = sc.pix.astype(np.int64)
+        t0 = time.perf_counter()
+        pts = impl.ProcessTimeSamples(pix, sc.npix_full, pol=pol, phi=sc.phi)
+        npix = pts.get_new_pixel[0]
+        P = impl.SparseLO(npix, sc.nt, pix, pol=pol, angle_processed=pts)
+        Mbd = impl.BlockDiagonalPreconditionerLO(pts, npix, pol=pol)
+        A = P.T * P
+        b = P.T * sc.d
+        t1 = time.perf_counter()
+        res = []
+        x, info = solver(A, b, M=Mbd, rtol=1e-3, maxiter=10, callback=lambda xk: res.append(0))
+        if impl is cm:
+            torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        return dict(npix=int(npix), x=np.asarray(x), info=int(info), iterations=len(res), setup_seconds=t1 - t0,
+                    solve_seconds=t2 - t1)
+
+    script(cm, cm.cg)                                   # first use: kernel load, allocator warm-up
+    g = script(cm, cm.cg)
+    out = {"config": "configs[0] stand-in: 4 detector pairs, %d samples, IQU nside 128, A = P^T P, cg(tol=1e-3, maxiter=10)" % sc.nt,
+           "nt": int(sc.nt), "npix": g["npix"], "info": g["info"], "iterations": g["iterations"],
+           "gpu_setup_seconds": g["setup_seconds"], "gpu_solve_seconds": g["solve_seconds"],
+           "samples_per_s_per_pcg_iter": sc.nt * max(g["iterations"], 1) / g["solve_seconds"]}
+    if cpu_oracle is not None:
+        c = script(cpu_oracle, spla.cg)
+        out.update({"cpu_oracle_setup_seconds": c["setup_seconds"], "cpu_oracle_solve_seconds": c["solve_seconds"],
+                    "cpu_iterations": c["iterations"], "npix_equal": c["npix"] == g["npix"],
+                    "x_rel_diff": float(np.max(np.abs(c["x"] - g["x"])) / np.max(np.abs(c["x"]))),
+                    "speedup_whole_script": (c["setup_seconds"] + c["solve_seconds"]) / (g["setup_seconds"] + g["solve_seconds"])})
+    return out
+
+
 def correlated(nt=1.25e8, ndet=8, nband=4096, nside=512, nx=1000, ny=500, rtol=1e-6, maxiter=300, time_iters=20,
                symmetry=True, two_level_r=0):
     """configs[2], one rank's share: ``ndet`` detectors x nt/ndet samples, one symmetric banded Toeplitz block of
