@@ -327,3 +327,89 @@ def test_run_table_legendre_scheme_equals_polyfilter():
             worst = max(worst, np.abs(out - ref)[good].max() / max(np.abs(d).max(), 1e-300))
     assert worst < 1e-11, worst
     assert nhard > 0                                        # the ill-conditioned branch was exercised
+
+
+# ---- round 2 host logic ---------------------------------------------------------------------------------
+def test_partition_pixels_is_balanced_even_and_covers():
+    from cosmomap2_b200 import distributed
+    for npix in (0, 1, 7, 100, 500000, 1280001):
+        for world in (1, 2, 3, 4, 8):
+            lo_ = distributed.partition_pixels(npix, world)
+            assert len(lo_) == world + 1 and lo_[0] == 0 and lo_[-1] == npix
+            assert all(b >= a for a, b in zip(lo_[:-1], lo_[1:]))
+            assert all(b % 2 == 0 for b in lo_[1:-1])          # pol * lo doubles is 16-byte aligned for any pol
+            sizes = np.diff(lo_)
+            assert sizes.max() - sizes.min() <= 2 + (npix % 2) or npix < 2 * world
+
+
+class _FakeP(object):
+    def __init__(self, nrows, ncols, pol):
+        self.nrows, self.ncols, self.pol = nrows, ncols, pol
+
+
+class _FakeF(object):
+    def __init__(self, nsamples):
+        self.nsamples = nsamples
+
+
+def test_tile_order_is_chosen_from_the_map_size_and_the_timeline():
+    big, small = 6000000, 500000                     # pixels: x and y together 288 MB / 24 MB at IQU
+    assert lo._tod_streams(_FakeP(64 * 1000, big, 3), 1000) == 64
+    assert lo._tod_streams(_FakeP(64 * 1000, small, 3), 1000) == 1          # the map stays in L2 in any order
+    assert lo._tod_streams(_FakeP(64 * 1000 + 5, big, 3), 1000) == 1        # not a whole number of timelines
+    assert lo._tod_streams(_FakeP(64 * 1000, big, 3), 0) == 1
+    assert lo._filter_timeline(_FakeF(1000)) == 1000
+    assert lo._filter_timeline(_FakeF([1000, 1000])) == 1000
+    assert lo._filter_timeline(_FakeF([1000, 900])) == 0                    # CES of different lengths: time order
+
+
+class _FakeZ(object):
+    def __init__(self, zt):
+        self._zt = zt
+        self.ncols, self.nrows = zt.shape
+
+
+@pytest.mark.parametrize("pol", [1, 3])
+def test_banded_coarse_space_detection_is_exact(pol):
+    """linearoperators._banded_coarse_space on CPU tensors: an indicator Z with A Z inside the three cyclic bands is
+    compressed without loss; one entry outside, a non-indicator Z or a pixel in two columns are refused."""
+    import torch
+    rng = np.random.default_rng(5)
+    r, npix = 6, 40
+    n = pol * npix
+    band = rng.integers(0, r, npix)
+    band[3] = -1                                       # a pixel in no column
+    Zt = torch.zeros((r, n), dtype=torch.float64)
+    for p_, b in enumerate(band):
+        if b >= 0:
+            Zt[b, pol * p_] = 1.0
+    AZt = torch.zeros((r, n), dtype=torch.float64)
+    for p_, b in enumerate(band):
+        if b < 0:
+            continue
+        for o in (-1, 0, 1):
+            for k in range(pol):
+                AZt[(b + o) % r, pol * p_ + k] = rng.standard_normal()
+    out = lo._banded_coarse_space(_FakeZ(Zt), _FakeZ(AZt), pol)
+    assert out is not None
+    bd, azb = out
+    assert np.array_equal(bd.numpy(), band)
+    for p_, b in enumerate(band):
+        for k in range(pol):
+            for o in range(3):
+                want = AZt[(b + o - 1) % r, pol * p_ + k].item() if b >= 0 else 0.0
+                assert azb[p_, k, o].item() == want
+    bad = AZt.clone()
+    p0 = int(np.nonzero(band == 0)[0][0])
+    bad[3, pol * p0] = 1.0                             # band 0 reaches column 3: outside its neighbours
+    assert lo._banded_coarse_space(_FakeZ(Zt), _FakeZ(bad), pol) is None
+    Z2 = Zt.clone()
+    Z2[1, pol * p0] = 1.0                              # a pixel in two columns
+    assert lo._banded_coarse_space(_FakeZ(Z2), _FakeZ(AZt), pol) is None
+    Z3 = Zt.clone()
+    Z3[0, pol * p0] = 0.5                              # not an indicator
+    assert lo._banded_coarse_space(_FakeZ(Z3), _FakeZ(AZt), pol) is None
+    if pol == 3:
+        Z4 = Zt.clone()
+        Z4[0, 1] = 1.0                                 # a polarisation entry
+        assert lo._banded_coarse_space(_FakeZ(Z4), _FakeZ(AZt), pol) is None
