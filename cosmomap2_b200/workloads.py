@@ -239,27 +239,30 @@ def correlated(nt=1.25e8, ndet=8, nband=4096, nside=512, nx=1000, ny=500, rtol=1
            "plan": [type(f).__name__ for f in A_local.planned()], "cg": cg,
            "samples_per_s_per_pcg_iter": nt * world / (cg["seconds"] / max(cg["iterations"], 1))}
     if two_level_r:
-        # beyond the named configuration (M_BD PCG): the same solve with M_2lvl on the scan coarse space -- the slow
-        # modes of P^T F N F P are those of the offset filter, whatever N is
-        _barrier()
-        t0 = time.perf_counter()
-        r2 = int(two_level_r)
-        Zt = cm.scan_coarse_space(P, r2, ns, A=A, Mbd=Mbd, smooth=2)
-        AZt = torch.stack([A._apply(Zt[i]) for i in range(r2)])
-        E = cm.CoarseLO(Zt.t(), AZt.t(), r2, apply="eig")
-        Zd, AZd = cm.DeflationLO(Zt.t()), cm.DeflationLO(AZt.t())
-        del Zt, AZt
-        M2 = Mbd * (cm.lp.IdentityOperator(n) - AZd * E * Zd.T) + Zd * E * Zd.T
-        M2._apply(b)
-        torch.cuda.synchronize()
-        build = _max_over_ranks(time.perf_counter() - t0)
-        x2, _res2, cg2 = _solve(cm, A, b, M2, rtol, maxiter)
-        cg2.update(r=r2, build_seconds=build)
-        ax1, ax2 = A._apply(x), A._apply(x2)
-        cg2["Ax_agreement"] = float(torch.linalg.norm(ax1 - ax2) / torch.linalg.norm(ax1))
-        cg2["build_plus_solve_vs_M_BD_solve"] = (build + cg2["seconds"]) / cg["seconds"]
-        out["M_2lvl_scan_space"] = cg2
-        del M2, Zd, AZd, E, x2
+        try:
+            # beyond the named configuration (M_BD PCG): the same solve with M_2lvl on the scan coarse space -- the slow
+            # modes of P^T F N F P are those of the offset filter, whatever N is
+            _barrier()
+            t0 = time.perf_counter()
+            r2 = int(two_level_r)
+            Zt = cm.scan_coarse_space(P, r2, ns, A=A, Mbd=Mbd, smooth=2)
+            AZt = torch.stack([A._apply(Zt[i]) for i in range(r2)])
+            E = cm.CoarseLO(Zt.t(), AZt.t(), r2, apply="eig")
+            Zd, AZd = cm.DeflationLO(Zt.t()), cm.DeflationLO(AZt.t())
+            del Zt, AZt
+            M2 = Mbd * (cm.lp.IdentityOperator(n) - AZd * E * Zd.T) + Zd * E * Zd.T
+            M2._apply(b)
+            torch.cuda.synchronize()
+            build = _max_over_ranks(time.perf_counter() - t0)
+            x2, _res2, cg2 = _solve(cm, A, b, M2, rtol, maxiter)
+            cg2.update(r=r2, build_seconds=build)
+            ax1, ax2 = A._apply(x), A._apply(x2)
+            cg2["Ax_agreement"] = float(torch.linalg.norm(ax1 - ax2) / torch.linalg.norm(ax1))
+            cg2["build_plus_solve_vs_M_BD_solve"] = (build + cg2["seconds"]) / cg["seconds"]
+            out["M_2lvl_scan_space"] = cg2
+            del M2, Zd, AZd, E, x2
+        except Exception as e:                      # noqa: BLE001 -- the named configuration (M_BD) stands
+            out["M_2lvl_scan_space"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if symmetry:
         # symmetry of the composed operator (F and N symmetric): <u, A v> = <v, A u>
         u = torch.randn(n, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7))
