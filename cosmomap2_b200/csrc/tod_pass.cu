@@ -803,57 +803,69 @@ __global__ void __launch_bounds__(BLOCK) k_pointing_filter_mu(const int32_t *__r
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
     const int64_t ntiles = (nt + TILE - 1) / TILE;
-    for (int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
+    int64_t tile = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+    if (tile >= ntiles) return;
+    // the subscan lookup of a tile (flag, segment index, and from it the mean) is a chain of dependent L2 accesses:
+    // it is issued one trip ahead (flag / index two trips ahead), as in k_amatvec_filter_mu
+    int flag = __ldg(sg.tile_flag + tile), k0 = __ldg(sg.tile_seg + tile);
+    int flag2 = 0, k02 = 0;
+    if (tile + nwarps < ntiles) { flag2 = __ldg(sg.tile_flag + tile + nwarps); k02 = __ldg(sg.tile_seg + tile + nwarps); }
+    double m0 = flag == 1 ? __ldg(sg.mu + k0) : 0.0;
+    for (; tile < ntiles; tile += nwarps) {
         const int64_t t0 = tile * TILE + (int64_t)lane * K;
-        if (t0 >= nt) continue;
-        int p[K];
-        double c[K], s[K], mu[K], xv[K][POL], out[K];
-        bool in[K];
-        load_pix(pix, t0, nt, p);
-        if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
-        const int flag = __ldg(sg.tile_flag + tile);
-        const int k0 = __ldg(sg.tile_seg + tile);
-        if (flag == 1) {
-            const double m0 = __ldg(sg.mu + k0);
+        // next trip's mean and the lookup of the trip after it, before this tile's loads are waited for
+        const double m0n = (tile + nwarps < ntiles && flag2 == 1) ? __ldg(sg.mu + k02) : 0.0;
+        int flag3 = 0, k03 = 0;
+        if (tile + 2 * nwarps < ntiles) { flag3 = __ldg(sg.tile_flag + tile + 2 * nwarps); k03 = __ldg(sg.tile_seg + tile + 2 * nwarps); }
+        if (t0 < nt) {
+            int p[K];
+            double c[K], s[K], mu[K], xv[K][POL], out[K];
+            bool in[K];
+            load_pix(pix, t0, nt, p);
+            if (POL > 1) { load_f64(cs, t0, nt, c); load_f64(sn, t0, nt, s); }
+            if (flag == 1) {
 #pragma unroll
-            for (int j = 0; j < K; ++j) { mu[j] = m0; in[j] = true; }
-        } else if (flag == 0) {
+                for (int j = 0; j < K; ++j) { mu[j] = m0; in[j] = true; }
+            } else if (flag == 0) {
 #pragma unroll
-            for (int j = 0; j < K; ++j) { mu[j] = 0.0; in[j] = false; }
-        } else {
-            int64_t k = k0;
-            while (k < sg.nseg && __ldg(sg.end + k) <= t0) ++k;
-            int64_t a = k < sg.nseg ? __ldg(sg.start + k) : INT64_MAX, b = k < sg.nseg ? __ldg(sg.end + k) : INT64_MAX;
-            double m = k < sg.nseg ? __ldg(sg.mu + k) : 0.0;
+                for (int j = 0; j < K; ++j) { mu[j] = 0.0; in[j] = false; }
+            } else {
+                int64_t k = k0;
+                while (k < sg.nseg && __ldg(sg.end + k) <= t0) ++k;
+                int64_t a = k < sg.nseg ? __ldg(sg.start + k) : INT64_MAX, b = k < sg.nseg ? __ldg(sg.end + k) : INT64_MAX;
+                double m = k < sg.nseg ? __ldg(sg.mu + k) : 0.0;
 #pragma unroll
-            for (int j = 0; j < K; ++j) {
-                const int64_t t = t0 + j;
-                while (k < sg.nseg && t >= b) {
-                    ++k;
-                    a = k < sg.nseg ? __ldg(sg.start + k) : INT64_MAX;
-                    b = k < sg.nseg ? __ldg(sg.end + k) : INT64_MAX;
-                    m = k < sg.nseg ? __ldg(sg.mu + k) : 0.0;
+                for (int j = 0; j < K; ++j) {
+                    const int64_t t = t0 + j;
+                    while (k < sg.nseg && t >= b) {
+                        ++k;
+                        a = k < sg.nseg ? __ldg(sg.start + k) : INT64_MAX;
+                        b = k < sg.nseg ? __ldg(sg.end + k) : INT64_MAX;
+                        m = k < sg.nseg ? __ldg(sg.mu + k) : 0.0;
+                    }
+                    in[j] = k < sg.nseg && t >= a;
+                    mu[j] = m;
                 }
-                in[j] = k < sg.nseg && t >= a;
-                mu[j] = m;
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j) if (!in[j]) p[j] = -1;
+            gather_x<POL>(x, p, xv);
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                out[j] = in[j] ? (p[j] >= 0 ? project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0) : 0.0) - mu[j] : 0.0;
+            if (t0 + K <= nt) {
+                D4 a, b;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { a.v[j] = out[j]; b.v[j] = out[4 + j]; }
+                st_stream_d4(d + t0, a);
+                st_stream_d4(d + t0 + 4, b);
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; ++j) if (t0 + j < nt) d[t0 + j] = out[j];
             }
         }
-#pragma unroll
-        for (int j = 0; j < K; ++j) if (!in[j]) p[j] = -1;
-        gather_x<POL>(x, p, xv);
-#pragma unroll
-        for (int j = 0; j < K; ++j)
-            out[j] = in[j] ? (p[j] >= 0 ? project<POL>(xv[j], POL > 1 ? c[j] : 0.0, POL > 1 ? s[j] : 0.0) : 0.0) - mu[j] : 0.0;
-        if (t0 + K <= nt) {
-            D4 a, b;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { a.v[j] = out[j]; b.v[j] = out[4 + j]; }
-            st_stream_d4(d + t0, a);
-            st_stream_d4(d + t0 + 4, b);
-        } else {
-#pragma unroll
-            for (int j = 0; j < K; ++j) if (t0 + j < nt) d[t0 + j] = out[j];
-        }
+        flag = flag2; k0 = k02; m0 = m0n;
+        flag2 = flag3; k02 = k03;
     }
 }
 
