@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
     unsigned crank = 0;
     if constexpr (PAIR) asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     const int64_t win0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x, winstep = PAIR ? (gridDim.x >> 1) : gridDim.x;
+    bool join_pending = false;      // PAIR: arrived at the barrier that ends a window's join, not yet waited for
     for (int64_t win = win0; win < nwin; win += winstep) {
         int64_t lo = 0, hi = nblocks;
         while (hi - lo > 1) {
@@ -223,6 +224,14 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                     }
                 }
                 butterfly16<false>(v, __ldg(tw + FFT_M / 4 + pos));
+                if constexpr (PAIR) {
+                    // split-phase cluster barrier: the partner may still be reading this CTA's half of the PREVIOUS
+                    // window; it had this window's loads and 16-point butterflies to finish doing so
+                    if (join_pending) {
+                        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+                        join_pending = false;
+                    }
+                }
 #pragma unroll
                 for (int m = 0; m < 16; ++m) z(i0 + m * q) = v[m];
             }
@@ -395,8 +404,14 @@ __global__ void __launch_bounds__(FFT_THREADS, 1)
                     if (j0 + r0 + 1 < be) out[j0 + r0 + 1] = r.y;
                 }
             }
-            cl.sync();                                                  // the partner has read my half: the next window may overwrite it
+            // the partner has read my half once it, too, arrives here; waited for before the next window's first
+            // shared-memory store (or before the CTA exits)
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            join_pending = true;
         }
+    }
+    if constexpr (PAIR) {
+        if (join_pending) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
 }
 
