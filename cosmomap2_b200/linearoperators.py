@@ -189,12 +189,11 @@ TOEPLITZ_FFT_MIN_BAND = 48     # bands at least this wide go through the overlap
                                # crossover at 1e8 samples: direct 64 lags 2.29 ms, FFT 1.5 ms for any band <= 256)
 
 
-# Bands of at least this many coefficients use 32768-sample windows on 2-CTA clusters.  Measured per 1e8 samples,
-# one-CTA windows / cluster windows: 1.14 / 1.42 ms at 2048 coefficients, 1.45 / 1.51 at 3000, 1.62 / 1.63 at 4096 (the
-# 1.5x fewer window points per output are eaten by the joining stage over distributed shared memory and the second
-# read of the window), so the cluster mode is used where one CTA cannot hold the band at all: 4097..8192
-# coefficients (before: the direct kernel, ~50x slower there).
-TOEPLITZ_FFT_PAIR_MIN_BAND = 4097
+# Bands of at least this many coefficients use 32768-sample windows on 2-CTA clusters (1.5x fewer window points per
+# output at 4096 coefficients, paid for by the join over distributed shared memory and a second read of the window).
+# Measured per 1e8 samples, one-CTA windows / cluster windows: 1.14 / 1.42 ms at 2048 coefficients, 1.46 / 1.43 at 3000,
+# 1.63 / 1.54 at 4096; beyond 4096 one CTA cannot hold the band at all (before: the direct kernel, ~50x slower there).
+TOEPLITZ_FFT_PAIR_MIN_BAND = 3000
 
 
 def _bit_reverse(M):

@@ -197,8 +197,8 @@ def test_krypy_style_arnoldi_and_two_level(cm):
 @pytest.mark.parametrize("pair_min", [None, 2])
 def test_toeplitz_fft_path_equals_direct_path(cm, pair_min):
     """Overlap-save FFT kernel vs the direct shared-memory kernel vs the oracle, multi-block, ragged blocks.
-    ``pair_min = 2`` forces every band through the 32768-sample windows on 2-CTA clusters (by default only bands
-    of more than 4096 coefficients take them: the L = 6000 case below)."""
+    ``pair_min = 2`` forces every band through the 32768-sample windows on 2-CTA clusters (by default bands of 3000
+    coefficients and more take them: the L = 3000, 4096 and 6000 cases below)."""
     import oracle
     from cosmomap2_b200 import linearoperators as lo
     rng = np.random.default_rng(21)
