@@ -247,6 +247,18 @@ def worker(case, out_path):
         res["identical_on_ranks"] = same_on_ranks(x_sh)
         resid = b - A._apply(x_sh)
         res["relres"] = float(torch.linalg.norm(resid) / torch.linalg.norm(b))
+        # the state machine started from the REPLICATED right-hand side (every rank computes p = M_BD b itself, no
+        # exchange: what bench.py's timed loop does) gives the same iterates as the start from per-rank slices
+        from cosmomap2_b200.pcg import make_solver, _run_loop
+        s = make_solver(A, Mbd, b.numel())
+        res["local_start_used_sharded"] = isinstance(s, distributed.ShardedPCG)
+        s.start(b, None, 0.0, 1e-10)
+        r_loc = []
+        info_loc = _run_loop(s, 200, r_loc)
+        x_loc = s.gather_x()
+        res["local_start"] = [int(info_loc), len(r_loc), float((x_loc - x_sh).abs().max() / x_sh.abs().max()),
+                              float(np.max(np.abs(np.array(r_loc) - np.array(r_sh))) / r_sh[0]) if len(r_loc) == len(r_sh) else 1.0,
+                              bool(same_on_ranks(x_loc)), int(s.failed())]
         A.close()
 
     elif case == "m2_sharded":

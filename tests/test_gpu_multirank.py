@@ -181,6 +181,11 @@ def test_ranks_sharded_solve_many_iterations(tmp_path):
         assert r["used_sharded"] and r["info"] == [0, 0]
         assert abs(r["iters"][0] - r["iters"][1]) <= 1
         assert r["x_rel"] < 1e-8 and r["relres"] < 2e-10 and r["identical_on_ranks"]
+        # the exchange-free start from the replicated right-hand side: same exit, same number of residuals, same
+        # residual history (relative to ||b||-scaled first residual) and solution, bit-identical on the ranks
+        info_loc, n_loc, x_rel_loc, hist_rel, same, failed = r["local_start"]
+        assert r["local_start_used_sharded"] and info_loc == 0 and n_loc == r["iters"][0] and failed == 0
+        assert x_rel_loc < 1e-10 and hist_rel < 1e-10 and same
 
 
 @needs2
