@@ -279,8 +279,10 @@ def correlated(nt=1.25e8, ndet=8, nband=4096, nside=512, nx=1000, ny=500, rtol=1
     del d
     out.update({"A_apply_ms": a_ms, "A_local_apply_ms": al_ms, "A_apply_samples_per_s": nt * world / (a_ms * 1e-3),
                 "roofline": _roofline("k_toeplitz_fft (cm2_noise_toeplitz_apply, %d coefficients)" % nband, 16.0 * nt, n_ms,
-                                      "bound in practice by the shared-memory data pipe of the in-CTA FFT, not by HBM "
-                                      "(DESIGN section 4); 16 B/sample is the HBM floor"),
+                                      "16 B/sample is the HBM floor the contract asks for; the kernel is bound by the fp64 and "
+                                      "shared-memory pipes of its in-CTA FFT (ncu, profiles/r02_fft_ncu.txt: fp64 pipe 46 %, "
+                                      "L1/shared-memory data pipe 57 % busy, DRAM 10 %; ~150 flop/sample instead of the 16 382 of "
+                                      "the direct form; DESIGN sections 4, 4b)"),
                 "roofline_A_apply": _roofline("A_local = P^T F N F P (%d kernels)" % len(A_local.planned()),
                                               20.0 * nt + 48.0 * npix, al_ms,
                                               "against the ideal-fusion 20 B/sample + 48 B/pixel of SURVEY 8(d)"),
