@@ -254,16 +254,21 @@ def _cg_replicated(A, b_in, x0, want_numpy, rtol, atol, maxiter, M, callback, re
     n = b_in.shape[0]
     solver = PCG(A, M, n)
     bd = dv.to_dev_f64(b_in)
-    bnrm2 = solver.norm(bd)
-    atol = max(float(atol), float(rtol) * bnrm2)
-    if bnrm2 == 0:
-        return (b_in.copy() if want_numpy else bd.clone()), 0
     x0d = None
     if x0 is not None:
         x0d = dv.to_dev_f64(x0).reshape(-1)
         if x0d.shape[0] != n:
             raise ValueError("shapes of A and x0 are incompatible")
-    solver.start(bd, x0d, atol)
+    if solver.bd is not None and x0d is None:
+        # M_BD, x0 = 0: SciPy's atol = max(atol, rtol ||b||) and its b = 0 exit (x = 0, info = 0) are evaluated by
+        # the start kernel on the device -- no host round trip for ||b||
+        solver.start(bd, None, float(atol), float(rtol))
+    else:
+        bnrm2 = solver.norm(bd)
+        atol = max(float(atol), float(rtol) * bnrm2)
+        if bnrm2 == 0:
+            return (b_in.copy() if want_numpy else bd.clone()), 0
+        solver.start(bd, x0d, atol)
 
     def out(v):
         return dv.to_host(v) if want_numpy else v.clone()

@@ -219,3 +219,29 @@ def test_config0_from_a_ces_file(cm, tmp_path):
         for k, a in enumerate(h1):
             assert np.count_nonzero(a) <= n1
             gc.exact(a[np.asarray(o1)], x1[k::pol], "HEALPix map %d is a permutation of x" % k)
+
+
+def test_device_side_tolerance_and_zero_rhs(cm):
+    """cg(A, b, M=M_BD) with x0 = None evaluates SciPy's atol = max(atol, rtol ||b||) and its b = 0 exit in the start
+    kernel (no host round trip for ||b||): same exit code, iteration count and iterates as the path that takes the
+    norm on the host (x0 = zeros), for rtol-, atol- and maxiter-limited solves; b = 0 returns x = 0, info = 0 like
+    scipy.sparse.linalg.cg."""
+    from cosmomap2_b200 import synthetic
+    sc = synthetic.raster_scan(6 * 30000, nside=64, ndet=6, nx=60, ny=30, samples_per_pixel=6.0, seed=3, flag_turnarounds=True)
+    npix, P, Mbd, A, b, pts = _build(cm, sc, 3, filt=True)
+    n = 3 * npix
+    bn = np.linalg.norm(b)
+    for kw in (dict(rtol=1e-8, maxiter=500), dict(rtol=0.0, atol=1e-6 * bn, maxiter=500), dict(rtol=1e-30, maxiter=7),
+               dict(rtol=1e-4, atol=1e-3 * bn, maxiter=500)):
+        r0, r1 = [], []
+        x_dev, i_dev = cm.cg(A, b, M=Mbd, residuals=r0, **kw)                      # device-side tolerance
+        x_host, i_host = cm.cg(A, b, x0=np.zeros(n), M=Mbd, residuals=r1, **kw)    # norm on the host
+        assert i_dev == i_host and len(r0) == len(r1)
+        assert np.max(np.abs(np.array(r0) - np.array(r1))) <= 1e-10 * bn
+        gc.close(x_dev, x_host, rtol=1e-10, what="device-side vs host-side tolerance %r" % (kw,))
+        xs, i_s = spla.cg(A, b, M=Mbd, **kw)
+        assert i_s == i_dev
+    for M in (Mbd, None):
+        x0_, i0_ = cm.cg(A, np.zeros(n), M=M, rtol=1e-8, maxiter=50)
+        xs, i_s = spla.cg(A, np.zeros(n), M=M, rtol=1e-8, maxiter=50)
+        assert i0_ == 0 and i_s == 0 and not np.any(x0_) and not np.any(xs)
