@@ -252,7 +252,19 @@ def cg(A, b, x0=None, *, rtol=1e-5, atol=0., maxiter=None, M=None, callback=None
 
 def _cg_replicated(A, b_in, x0, want_numpy, rtol, atol, maxiter, M, callback, residuals):
     n = b_in.shape[0]
-    solver = PCG(A, M, n)
+    # the state machine (five n-vectors, scalars, pinned snapshot buffers) is kept on the operator between calls with
+    # the same preconditioner: start() resets all of it, results are handed out as copies
+    solver = None
+    cached = getattr(A, "_cm2_pcg", None) if isinstance(A, lp.LinearOperator) else None
+    if cached is not None and cached[0] is M and cached[1].n == n:
+        solver = cached[1]
+    if solver is None:
+        solver = PCG(A, M, n)
+        if isinstance(A, lp.LinearOperator) and (M is None or isinstance(M, lp.LinearOperator)):
+            try:
+                A._cm2_pcg = (M, solver)
+            except AttributeError:
+                pass
     bd = dv.to_dev_f64(b_in)
     x0d = None
     if x0 is not None:
