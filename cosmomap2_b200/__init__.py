@@ -21,7 +21,8 @@ from .linearoperators import (SparseLO, ToeplitzLO, WeightingLO, BlockLO, Filter
                               TwoLevelPreconditionerLO)
 from .process_ces import ProcessTimeSamples, BlockWeights  # noqa: F401
 from .deflationlib import (arnoldi, build_hess, build_Z, run_krypy_arnoldi,  # noqa: F401
-                           find_ritz_eigenvalues, krypy_arnoldi, krypy_ritz, eigsh, scan_coarse_space)
+                           find_ritz_eigenvalues, krypy_arnoldi, krypy_ritz, eigsh, scan_coarse_space,
+                           coarse_products)
 from .utilities import (dgemm, norm2, scalprod, get_legendre_polynomials, is_sorted,  # noqa: F401
                         bash_colors, filter_warnings, angles_gen, pairs_gen, checking_output,
                         noise_val, subscan_resize, system_setup, reorganize_map, profile_run,

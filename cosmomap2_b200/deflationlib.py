@@ -441,3 +441,56 @@ def scan_coarse_space(P, r, samples_per_detector, group=None, A=None, Mbd=None, 
         idx = torch.nonzero(seen).reshape(-1)
         Zt[band[idx], pol * idx] = 1.0
     return Zt
+
+
+def coarse_products(A, Zt, pol, probe=True):
+    """``A Z`` column by column, as an (r, n) CUDA tensor (row k = A z_k) -- the ``Az`` of
+    ``CoarseLO(Z, Az, r)`` (tests/test_coarse_operator.py:19-23 builds it with one A apply per column).
+
+    For a SUBDOMAIN coarse space (``scan_coarse_space``: column k = intensity indicator of band k) the columns have
+    disjoint supports and ``A z_k`` lives on band k and its two cyclic neighbours, so the r products follow from
+    ``c`` applies to the sums of every c-th column (probing / colouring, c = 4..7 with r divisible by c so that the
+    colours stay consistent around the cyclic seam): at a pixel of band b the colours of b-1, b, b+1 are distinct
+    and give the three entries; the other colours MUST be exactly zero there -- that is checked for every map
+    element, and any non-zero (a band narrower than the reach of A) falls back to one apply per column.  Exact in
+    the same sense as repeated applies (atomic adds of the same terms).  With r = 32: 4 applies instead of 32."""
+    dv.require_cuda()
+    A = _as_op(A)
+    r, n = Zt.shape
+    pol = int(pol)
+
+    def exact():
+        return torch.stack([A._apply(Zt[i].contiguous()) for i in range(r)])
+
+    ncol = next((c for c in (4, 5, 6, 7) if r % c == 0 and r >= 2 * c), None)
+    if not probe or ncol is None or pol not in (1, 3) or n % pol:
+        return exact()
+    zi = Zt[:, 0::pol]
+    ones = zi == 1.0
+    if not bool(((zi == 0.0) | ones).all().item()):
+        return exact()
+    cnt = ones.sum(dim=0)
+    if int(cnt.max().item()) > 1 or (pol == 3 and (bool((Zt[:, 1::3] != 0).any().item()) or bool((Zt[:, 2::3] != 0).any().item()))):
+        return exact()
+    band = torch.where(cnt > 0, ones.to(torch.int8).argmax(dim=0), torch.full_like(cnt, -1))      # (npix,) int64
+    del zi, ones
+    Y = torch.stack([A._apply(Zt[c::ncol].sum(dim=0)).clone() for c in range(ncol)])                 # (ncol, n)
+    Yp = Y.view(ncol, n // pol, pol)
+    seen = band >= 0
+    bsafe = torch.clamp(band, min=0)
+    # every colour that is not the colour of band-1, band, band+1 must vanish at the pixel (all components)
+    for d in range(2, ncol - 1):
+        c = torch.remainder(bsafe + d, ncol)
+        far = Yp.gather(0, c.view(1, -1, 1).expand(1, -1, pol)).squeeze(0)
+        if bool((far[seen] != 0).any().item()):
+            return exact()
+    if bool((Yp[:, ~seen, :] != 0).any().item()):
+        return exact()
+    AZt = torch.zeros((r, n), dtype=torch.float64, device=Zt.device)
+    idx = torch.nonzero(seen).reshape(-1)
+    for o in (-1, 0, 1):
+        k = torch.remainder(band[idx] + o, r)
+        c = torch.remainder(k, ncol)
+        for comp in range(pol):
+            AZt[k, pol * idx + comp] = Yp[c, idx, comp]
+    return AZt

@@ -246,7 +246,7 @@ def correlated(nt=1.25e8, ndet=8, nband=4096, nside=512, nx=1000, ny=500, rtol=1
             t0 = time.perf_counter()
             r2 = int(two_level_r)
             Zt = cm.scan_coarse_space(P, r2, ns, A=A, Mbd=Mbd, smooth=2)
-            AZt = torch.stack([A._apply(Zt[i]) for i in range(r2)])
+            AZt = cm.coarse_products(A, Zt, pol)
             E = cm.CoarseLO(Zt.t(), AZt.t(), r2, apply="eig")
             Zd, AZd = cm.DeflationLO(Zt.t()), cm.DeflationLO(AZt.t())
             del Zt, AZt
@@ -349,7 +349,7 @@ def two_level(nt=5e8, nside=1024, nx=1600, ny=800, ndet=64, r=32, coarse="scan",
         Z, r, _th = cm.find_ritz_eigenvalues(H, V, threshold=thr, eigenvalues=True)
         Zt = Z.t().contiguous()
         del V, Z
-    AZt = torch.stack([A._apply(Zt[i]) for i in range(r)])
+    AZt = cm.coarse_products(A, Zt, pol) if coarse == "scan" else torch.stack([A._apply(Zt[i]) for i in range(r)])
     E = cm.CoarseLO(Zt.t(), AZt.t(), r, apply="eig")
     Zd, AZd = cm.DeflationLO(Zt.t()), cm.DeflationLO(AZt.t())
     del Zt, AZt

@@ -136,6 +136,17 @@ def test_banded_two_level_apply_equals_dense(dense, pol):
     A = P.T * F * P
     Zt = cm.scan_coarse_space(P, r, sc.ns, A=A, Mbd=Mbd, smooth=2)
     AZt = torch.stack([A._apply(Zt[i]) for i in range(r)])
+    # A Z by probing (4 applies to sums of every 4th column instead of 12) equals the column-by-column products; a
+    # space whose bands are narrower than the reach of A (96 bands on 96 rows) fails the zero check and falls back
+    n0 = A.nMatvec if hasattr(A, "nMatvec") else None
+    AZp = cm.coarse_products(A, Zt, pol)
+    assert float((AZp - AZt).abs().max() / AZt.abs().max()) < 1e-13
+    Zt_thin = cm.scan_coarse_space(P, 96, sc.ns, A=A, Mbd=Mbd, smooth=2)
+    AZ_thin = cm.coarse_products(A, Zt_thin, pol)
+    for k in (0, 17, 95):
+        ref_k = A._apply(Zt_thin[k])
+        assert float((AZ_thin[k] - ref_k).abs().max()) <= 1e-13 * max(float(ref_k.abs().max()), 1e-300)
+    del n0
     E = cm.CoarseLO(Zt.t(), AZt.t(), r, apply="eig")
     Zd, AZd = cm.DeflationLO(Zt.t()), cm.DeflationLO(AZt.t())
     v = dv.to_dev_f64(np.random.default_rng(3).standard_normal(n))
