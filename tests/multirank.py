@@ -199,7 +199,13 @@ def worker(case, out_path):
         # slices: gather="shard" returns this rank's part of the same solution
         x_slice, _ = cm.cg(A, b, M=Mbd, rtol=1e-12, maxiter=60, gather="shard")
         lo = distributed.partition_pixels(npix, world)
-        res["slice_equal"] = bool(torch.equal(x_slice, x_sh[pol * lo[rank]:pol * lo[rank + 1]]))
+        # a second solve: the fp64 reductions of the TOD pass land in a run-dependent order, so the two solutions
+        # agree to rounding (1e-10 of the solution, as every other comparison here), not always bit for bit
+        mine = x_sh[pol * lo[rank]:pol * lo[rank + 1]]
+        res["slice_shape_ok"] = tuple(x_slice.shape) == tuple(mine.shape)
+        res["slice_rel"] = float((x_slice - mine).abs().max() / x_sh.abs().max()) if mine.numel() else 0.0
+        res["slice_equal"] = res["slice_shape_ok"] and res["slice_rel"] < 1e-10
+        res["slice_bit_equal"] = bool(torch.equal(x_slice, mine))
         res["identical_on_ranks"] = same_on_ranks(x_sh)
         res["info"] = [int(info_sh), int(info_rep)]
         res["iters"] = [len(r_sh), len(r_rep)]
