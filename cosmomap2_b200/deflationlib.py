@@ -452,8 +452,9 @@ def coarse_products(A, Zt, pol, probe=True):
     ``c`` applies to the sums of every c-th column (probing / colouring, c = 4..7 with r divisible by c so that the
     colours stay consistent around the cyclic seam): at a pixel of band b the colours of b-1, b, b+1 are distinct
     and give the three entries; the other colours MUST be exactly zero there -- that is checked for every map
-    element, and any non-zero (a band narrower than the reach of A) falls back to one apply per column.  Exact in
-    the same sense as repeated applies (atomic adds of the same terms).  With r = 32: 4 applies instead of 32."""
+    element, and any non-zero (a band narrower than the reach of A) falls back to one apply per column; a weighted
+    checksum (one more apply) rules out a coupling that skips the checked bands.  Exact in the same sense as
+    repeated applies (atomic adds of the same terms).  With r = 32: 5 applies instead of 32."""
     dv.require_cuda()
     A = _as_op(A)
     r, n = Zt.shape
@@ -493,4 +494,17 @@ def coarse_products(A, Zt, pol, probe=True):
         c = torch.remainder(k, ncol)
         for comp in range(pol):
             AZt[k, pol * idx + comp] = Yp[c, idx, comp]
+    # the zero check covers the bands at distance 2 .. ncol-2; a coupling that skips them (distance ncol-1 or more
+    # with nothing in between) would have been attributed to the wrong column.  One more apply settles it: with
+    # distinct weights u_k, A (sum_k u_k z_k) must equal sum_k u_k (A z_k) to rounding (the same products summed in
+    # another order); the weights are a fixed sequence, so that every rank of a multi-GPU job takes the same branch
+    u = 1.0 + np.modf(0.6180339887498949 * np.arange(1, r + 1))[0]
+    zw, azw = torch.zeros_like(Zt[0]), torch.zeros_like(Zt[0])
+    for k in range(r):                      # r axpys each (no library GEMV: its first call costs 60 ms of set-up)
+        zw.add_(Zt[k], alpha=float(u[k]))
+        azw.add_(AZt[k], alpha=float(u[k]))
+    yw = A._apply(zw)
+    err = float((azw - yw).abs().max().item())
+    if not err <= 1e-10 * max(float(yw.abs().max().item()), 1e-300):
+        return exact()
     return AZt

@@ -138,15 +138,15 @@ def test_banded_two_level_apply_equals_dense(dense, pol):
     AZt = torch.stack([A._apply(Zt[i]) for i in range(r)])
     # A Z by probing (4 applies to sums of every 4th column instead of 12) equals the column-by-column products; a
     # space whose bands are narrower than the reach of A (96 bands on 96 rows) fails the zero check and falls back
-    n0 = A.nMatvec if hasattr(A, "nMatvec") else None
+    n0 = A.nMatvec
     AZp = cm.coarse_products(A, Zt, pol)
+    assert A.nMatvec - n0 == 5, "4 probes + 1 checksum apply expected, not the column-by-column fallback"
     assert float((AZp - AZt).abs().max() / AZt.abs().max()) < 1e-13
     Zt_thin = cm.scan_coarse_space(P, 96, sc.ns, A=A, Mbd=Mbd, smooth=2)
     AZ_thin = cm.coarse_products(A, Zt_thin, pol)
     for k in (0, 17, 95):
         ref_k = A._apply(Zt_thin[k])
         assert float((AZ_thin[k] - ref_k).abs().max()) <= 1e-13 * max(float(ref_k.abs().max()), 1e-300)
-    del n0
     E = cm.CoarseLO(Zt.t(), AZt.t(), r, apply="eig")
     Zd, AZd = cm.DeflationLO(Zt.t()), cm.DeflationLO(AZt.t())
     v = dv.to_dev_f64(np.random.default_rng(3).standard_normal(n))
@@ -172,3 +172,35 @@ def test_banded_two_level_apply_equals_dense(dense, pol):
     far = int(np.nonzero(band == 0)[0][0])
     AZbad[r // 2, pol * far] = 1.0
     assert lo.TwoLevelPreconditionerLO(Mbd, Zd, cm.DeflationLO(AZbad.t()), E)._banded is None
+
+
+@pytest.mark.parametrize("pol", [1, 3])
+def test_coarse_products_refuses_a_coupling_that_skips_the_checked_bands(pol):
+    """A couples band b to b-3 and b+3 only (nothing at distance 1 and 2): with 4 colours the zero check of the
+    colour of b+2 passes, and the entry of band b-3 would be booked on band b+1 (same colour).  The weighted checksum
+    must notice and coarse_products must return the column-by-column products; a nearest-band coupling on the same
+    space goes through the probing path (counted by the number of A applies)."""
+    import torch
+    import cosmomap2_b200 as cm
+    from cosmomap2_b200 import linop as lp
+    r, w = 12, 50
+    npix = r * w
+    n = pol * npix
+    Zt = torch.zeros((r, n), dtype=torch.float64, device="cuda")
+    for k in range(r):
+        Zt[k, pol * k * w:pol * (k + 1) * w:pol] = 1.0
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dg = 1.0 + torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+
+    def coupled(shift):
+        def mv(x):
+            return dg * x + 0.25 * (torch.roll(x, pol * shift * w) + torch.roll(x, -pol * shift * w))
+        return lp.LinearOperator(n, n, matvec=mv, symmetric=True, device=True)
+
+    for shift, applies in ((1, 5), (3, 5 + r)):
+        A = coupled(shift)
+        n0 = A.nMatvec
+        AZ = cm.coarse_products(A, Zt, pol)
+        assert A.nMatvec - n0 == applies, (shift, A.nMatvec - n0)
+        for k in range(r):
+            assert torch.equal(AZ[k], A._apply(Zt[k])), (shift, k)

@@ -413,3 +413,40 @@ def test_banded_coarse_space_detection_is_exact(pol):
         Z4 = Zt.clone()
         Z4[0, 1] = 1.0                                 # a polarisation entry
         assert lo._banded_coarse_space(_FakeZ(Z4), _FakeZ(AZt), pol) is None
+
+
+@pytest.mark.parametrize("pol", [1, 3])
+def test_coarse_products_probing_algebra_on_a_toy_operator(pol, monkeypatch):
+    """The colouring / attribution / checksum logic of deflationlib.coarse_products is index work on tensors; here it
+    runs on CPU tensors against a toy banded operator (the CUDA requirement is lifted for this test only -- no kernel
+    of the library is involved).  Nearest-band coupling: 4 probes + 1 checksum apply; a coupling that skips the
+    checked bands (distance 3 only) must be caught by the checksum and fall back to one apply per column."""
+    import torch
+    from cosmomap2_b200 import _device as dv, linop as lp, deflationlib as dl
+    monkeypatch.setattr(dv, "require_cuda", lambda: None)
+    r, w = 12, 40
+    n = pol * r * w
+    Zt = torch.zeros((r, n), dtype=torch.float64)
+    for k in range(r):
+        Zt[k, pol * k * w:pol * (k + 1) * w:pol] = 1.0
+    dg = 1.0 + torch.rand(n, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+
+    def coupled(shift):
+        def mv(x):
+            return dg * x + 0.25 * (torch.roll(x, pol * shift * w) + torch.roll(x, -pol * shift * w))
+        return lp.LinearOperator(n, n, matvec=mv, symmetric=True, device=True)
+
+    for shift, applies in ((1, 5), (3, 5 + r)):
+        A = coupled(shift)
+        n0 = A.nMatvec
+        AZ = dl.coarse_products(A, Zt, pol)
+        assert A.nMatvec - n0 == applies
+        for k in range(r):
+            assert torch.equal(AZ[k], A._apply(Zt[k]))
+    # not an indicator space (a second non-zero per pixel): column by column from the start
+    Zb = Zt.clone()
+    Zb[1, 0] = 1.0
+    A = coupled(1)
+    n0 = A.nMatvec
+    dl.coarse_products(A, Zb, pol)
+    assert A.nMatvec - n0 == r
