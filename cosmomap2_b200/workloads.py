@@ -375,7 +375,11 @@ def two_level(nt=5e8, nside=1024, nx=1600, ny=800, ndet=64, r=32, coarse="scan",
     out["A_local_apply_ms"] = al_ms
     out["M_2lvl_apply_ms"] = m2_ms
     out["roofline"] = _roofline("k_seg_mean + k_amatvec_filter_mu (P^T F P, cm2_amatvec_filter_mu)" if poly_order == 0
-                                else "P^T F_K P (Legendre order %d)" % poly_order, 20.0 * nt + 48.0 * npix, al_ms)
+                                else "P^T F_K P (Legendre order %d)" % poly_order, 20.0 * nt + 48.0 * npix, al_ms,
+                                note=("DRAM traffic of the pair measured by ncu at 1e8 samples, 8 samples per pixel crossing "
+                                      "(profiles/r02_filter_mu_ncu.txt): 2.41 GB against 2.024 GB algorithmic -- k_amatvec_filter_mu "
+                                      "reads 1.00x its 20 B/sample, the rest is the run table of k_seg_mean (28 B per run); "
+                                      "not measured at this size, hence traffic = null") if poly_order == 0 else None)
     out["hbm_GB"] = torch.cuda.max_memory_allocated() / 1e9
     _close(A)
     return out
