@@ -78,68 +78,24 @@ template <int POL>
 __global__ void __launch_bounds__(FB) k_seg_mean(const int32_t *__restrict__ run_pix, const double *__restrict__ run_mom,
                                                  const int64_t *__restrict__ seg_first, const int32_t *__restrict__ seg_nruns,
                                                  int64_t nseg, const double *__restrict__ x, double *__restrict__ mu) {
-    // A subscan of a raster scan has ~1000-2000 runs: each thread takes SU runs per trip and issues all of their
-    // table loads, then all of the map gathers, before the first use (one trip of dependent DRAM -> L2 latencies per
-    // subscan instead of four; ncu before: DRAM 58 % busy, long-scoreboard stalls).  The per-thread order of the
-    // sums and the reduction tree are those of the one-run-per-trip loop: same bits.
-    constexpr int SU = 4;
-    __shared__ double red[2][32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int64_t k = blockIdx.x;
-    int64_t f = 0;
-    int nr = 0;
-    if (k < nseg) { f = seg_first[k]; nr = seg_nruns[k]; }
-    for (; k < nseg; k += gridDim.x) {
-        const int64_t kn = k + gridDim.x;                 // the next subscan's header, ahead of this one's work
-        int64_t fn = 0;
-        int nrn = 0;
-        if (kn < nseg) { fn = seg_first[kn]; nrn = seg_nruns[kn]; }
+    __shared__ double red[32];
+    for (int64_t k = blockIdx.x; k < nseg; k += gridDim.x) {
+        const int64_t f = seg_first[k];
+        const int nr = seg_nruns[k];
         double dsum = 0.0, cnt = 0.0;
-        for (int i0 = threadIdx.x; i0 < nr; i0 += SU * FB) {
-            int32_t p[SU];
-            double n[SU], c[SU], s[SU], xv[SU][POL];
-#pragma unroll
-            for (int u = 0; u < SU; ++u) {
-                const int i = i0 + u * FB;
-                p[u] = 0;
-                n[u] = c[u] = s[u] = 0.0;
-                if (i < nr) {
-                    const int64_t r = f + i;
-                    p[u] = __ldcs(run_pix + r);
-                    n[u] = __ldcs(run_mom + 3 * r);
-                    c[u] = __ldcs(run_mom + 3 * r + 1);
-                    s[u] = __ldcs(run_mom + 3 * r + 2);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < SU; ++u) {
-                const double *xp = x + (int64_t)POL * p[u];
-#pragma unroll
-                for (int q = 0; q < POL; ++q) xv[u][q] = (i0 + u * FB < nr) ? __ldg(xp + q) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < SU; ++u) {
-                if (i0 + u * FB < nr) {
-                    if constexpr (POL == 1) dsum = fma(n[u], xv[u][0], dsum);
-                    else if constexpr (POL == 2) dsum = fma(s[u], xv[u][1], fma(c[u], xv[u][0], dsum));
-                    else dsum = fma(s[u], xv[u][2], fma(c[u], xv[u][1], fma(n[u], xv[u][0], dsum)));
-                    cnt += n[u];
-                }
-            }
+        for (int i = threadIdx.x; i < nr; i += FB) {
+            const int64_t r = f + i;
+            const int32_t p = __ldcs(run_pix + r);
+            const double n = __ldcs(run_mom + 3 * r), c = __ldcs(run_mom + 3 * r + 1), s = __ldcs(run_mom + 3 * r + 2);
+            const double *xp = x + (int64_t)POL * p;
+            if constexpr (POL == 1) dsum = fma(n, __ldg(xp), dsum);
+            else if constexpr (POL == 2) dsum = fma(s, __ldg(xp + 1), fma(c, __ldg(xp), dsum));
+            else dsum = fma(s, __ldg(xp + 2), fma(c, __ldg(xp + 1), fma(n, __ldg(xp), dsum)));
+            cnt += n;
         }
-        dsum = warp_sum(dsum);
-        cnt = warp_sum(cnt);
-        __syncthreads();                                  // the previous subscan's readers of red are done
-        if (lane == 0) { red[0][w] = dsum; red[1][w] = cnt; }
-        __syncthreads();
-        if (w == 0) {
-            double ts = lane < FB / 32 ? red[0][lane] : 0.0, tc = lane < FB / 32 ? red[1][lane] : 0.0;
-            ts = warp_sum(ts);
-            tc = warp_sum(tc);
-            if (lane == 0) mu[k] = tc > 0.0 ? ts / tc : 0.0;
-        }
-        f = fn;
-        nr = nrn;
+        const double ts = block_sum(dsum, red);
+        const double tc = block_sum(cnt, red);
+        if (threadIdx.x == 0) mu[k] = tc > 0.0 ? ts / tc : 0.0;
     }
 }
 
